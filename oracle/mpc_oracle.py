@@ -149,7 +149,7 @@ def _build_constraints(w_cur, H, N, tau, has_u, allow_short):
     return G, np.asarray(h), A, np.ones(H)
 
 
-def solve_dense(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e-11, max_iter=80):
+def solve_dense(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e-10, tol_dual=1e-9, max_iter=120):
     """Generic primal-dual interior point (Mehrotra predictor-corrector) with dense KKT solves."""
     w_cur = np.asarray(w_cur, dtype=np.float64)
     R = gross_returns_f32(yhat) if R is None else np.asarray(R, dtype=np.float64)
@@ -186,7 +186,7 @@ def solve_dense(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e-11, 
         r_p = A @ x - b
         gap = float(s @ z) if m else 0.0
         res = (float(np.abs(r_p).max()), float(np.abs(r_d).max()), gap)
-        if max(res[0], res[1]) < tol and gap < tol:
+        if res[0] < tol and res[1] < tol_dual and gap < tol:
             status = STATUS_OPTIMAL
             break
         if max(res[0], res[1]) < 1e-7 and gap < 1e-7:
@@ -230,7 +230,8 @@ def solve_dense(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e-11, 
             dxa, dnua, dza, dsa = newton(np.zeros(m))
             aa = max_step(dsa, dza, dxa)
             mu_aff = float((s + aa * dsa) @ (z + aa * dza)) / m
-            sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
+            # conservative centring floor: the generic solver favours robustness over iteration count
+            sigma = max(0.05, min(1.0, (mu_aff / mu) ** 3)) if mu > 0 else 0.0
             cterm = sigma * mu - dsa * dza
         else:
             cterm = np.zeros(0)

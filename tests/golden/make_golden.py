@@ -1,0 +1,204 @@
+"""Generate the golden fixtures in this directory from the REFERENCE ITSELF (/root/reference, Python,
+importable in the build container only).  Run:  python tests/golden/make_golden.py
+
+Nothing under tests/ reads /root/reference at test time: the GPU box does not have it.  The fixtures are
+small .npz files; large weights are regenerated from seeds by koopman_mpc_portfolio_rebalancing_b200.synthetic.
+
+  data_small.npz       compute_standardization_stats / create_finance_splits / time_delay_embedding
+                       (data_finance.py:211-353) on a synthetic business-day frame
+  forecast_*.npz       model.encode / step_latent / decode + extract/destandardize rollouts
+                       (model.py, backtest.py:85-121) for GenericKM (relu/id, tanh/ball, gelu + MLP decoder)
+                       and LISTAKM (linear and MLP encoder); weights stored (tiny models)
+  forecast_cfg1.npz    finance_sparse preset, TARGET_SIZE=128, N=10, d=20 (BASELINE config 1); weights from seed
+  backtest_cfg1.npz    UNMODIFIED reference run_backtest + KoopmanMPCStrategy + calculate_metrics on config 1
+                       with the substitute mpc module (tests/golden/_shims/mpc.py): history, metrics, every
+                       MPC call's (w_cur, yhat, w_opt, value)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "_shims"))  # must precede /root/reference: mpc, matplotlib
+
+import pandas as pd  # noqa: E402
+import torch  # noqa: E402
+
+import config as ref_config  # noqa: E402
+import data_finance as ref_data  # noqa: E402
+import model as ref_model  # noqa: E402
+import backtest as ref_backtest  # noqa: E402
+import mpc as shim_mpc  # noqa: E402
+
+from koopman_mpc_portfolio_rebalancing_b200 import synthetic  # noqa: E402
+
+torch.set_num_threads(1)
+
+
+def make_frame(seed, T, N, start="2012-01-02"):
+    lr = synthetic.gbm_log_returns(seed, T, N)
+    dates = pd.bdate_range(start, periods=T)
+    return pd.DataFrame(lr, index=dates, columns=[f"A{i}" for i in range(N)])
+
+
+def build_env(frame, train_end, val_end, d, seq_len=1):
+    stats = ref_data.compute_standardization_stats(frame, train_end)
+    tr, trd, va, vad, te, ted = ref_data.create_finance_splits(frame, stats, train_end, val_end, d)
+    env = ref_data.FinanceEnv(
+        ref_data.FinanceDataset(tr, trd, seq_len), ref_data.FinanceDataset(va, vad, seq_len),
+        ref_data.FinanceDataset(te, ted, seq_len), stats,
+        {"n_assets": frame.shape[1], "embedding_dim": d})
+    return env, stats, (tr, va, te)
+
+
+def gen_data_small():
+    frame = make_frame(11, 80, 3)
+    d = 4
+    train_end, val_end = str(frame.index[39].date()), str(frame.index[59].date())
+    env, stats, (tr, va, te) = build_env(frame, train_end, val_end, d)
+    std_all = ref_data.standardize_returns(frame, stats).values.astype(np.float32)
+    emb = ref_data.time_delay_embedding(std_all, d)
+    np.savez(os.path.join(HERE, "data_small.npz"), log_returns=frame.values, n_train_days=40, n_val_days=20,
+             d=d, mean=stats.mean, std=stats.std, standardized=std_all, embedded=emb, train=tr, val=va, test=te,
+             test_len=len(env.test_dataset))
+
+
+def ref_forecast(model, env_like, obs, H):
+    """The forecast loop of KoopmanMPCStrategy.rebalance (backtest.py:85-121), batched over rows."""
+    out = []
+    with torch.no_grad():
+        model.eval()
+        z = model.encode(torch.from_numpy(obs))
+        for _ in range(H):
+            z = model.step_latent(z)
+            x = model.decode(z)
+            y = env_like.destandardize_returns(env_like.extract_current_returns(x))
+            out.append(y.numpy())
+    return np.stack(out, axis=1)  # [M, H, N]
+
+
+class EnvLike:
+    def __init__(self, N, mean, std):
+        self.n_assets = N
+        self.stats = ref_data.FinanceStats(mean=mean, std=std, tickers=[])
+
+    extract_current_returns = ref_data.FinanceEnv.extract_current_returns
+    destandardize_returns = ref_data.FinanceEnv.destandardize_returns
+
+
+def gen_forecast(name, cfg, N, d, sd_np, H, M, seed, store_weights=True, lista_L=None):
+    obs_size = N * d
+    model = ref_model.make_model(cfg, obs_size)
+    missing = model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd_np.items()}, strict=True)
+    rng = np.random.default_rng(seed)
+    obs = rng.standard_normal((M, obs_size)).astype(np.float32)
+    mean = rng.normal(3e-4, 1e-4, N)
+    std = rng.uniform(0.008, 0.02, N)
+    yhat = ref_forecast(model, EnvLike(N, mean, std), obs, H)
+    with torch.no_grad():
+        z0 = model.encode(torch.from_numpy(obs)).numpy()
+    out = dict(obs=obs, mean=mean, std=std, yhat=yhat, z0=z0, H=H, N=N, d=d)
+    if store_weights:
+        out.update({"sd::" + k: v for k, v in sd_np.items()})
+    np.savez(os.path.join(HERE, f"forecast_{name}.npz"), **out)
+    return model
+
+
+def gen_forecasts():
+    # 1. GenericKM relu / id / bias / linear decoder (shape of the finance_sparse preset, tiny)
+    cfg = ref_config.get_config("finance_sparse")
+    cfg.MODEL.TARGET_SIZE = 8
+    cfg.MODEL.ENCODER.LAYERS = [16, 16]
+    sd = synthetic.generic_km_weights(1, 12, [16, 16], 8)
+    gen_forecast("generic_small", cfg, 3, 4, sd, 5, 7, 101)
+    # 2. tanh, ball norm, last_relu False, no bias
+    cfg = ref_config.get_config("generic")
+    cfg.MODEL.TARGET_SIZE = 8
+    cfg.MODEL.ENCODER.LAYERS = [16]
+    cfg.MODEL.ENCODER.ACTIVATION = "tanh"
+    cfg.MODEL.NORM_FN = "ball"
+    sd = synthetic.generic_km_weights(2, 12, [16], 8, enc_bias=False)
+    gen_forecast("generic_tanh_ball", cfg, 3, 4, sd, 3, 5, 102)
+    # 3. gelu encoder with last_relu, MLP decoder (relu) with bias
+    cfg = ref_config.get_config("generic_sparse")
+    cfg.MODEL.TARGET_SIZE = 8
+    cfg.MODEL.ENCODER.LAYERS = [16, 12]
+    cfg.MODEL.ENCODER.ACTIVATION = "gelu"
+    cfg.MODEL.DECODER.LAYERS = [10]
+    cfg.MODEL.DECODER.USE_BIAS = True
+    sd = synthetic.generic_km_weights(3, 12, [16, 12], 8, dec_layers=[10], dec_bias=True)
+    gen_forecast("generic_gelu_mlpdec", cfg, 3, 4, sd, 4, 6, 103)
+    # 4. LISTAKM, linear encoder
+    cfg = ref_config.get_config("lista")
+    cfg.MODEL.TARGET_SIZE = 16
+    sd, L = synthetic.lista_km_weights(4, 12, 16)
+    cfg.MODEL.ENCODER.LISTA.L = L
+    gen_forecast("lista_linear", cfg, 3, 4, sd, 5, 6, 104)
+    np.savez(os.path.join(HERE, "forecast_lista_linear_meta.npz"), L=L, alpha=cfg.MODEL.ENCODER.LISTA.ALPHA,
+             loops=cfg.MODEL.ENCODER.LISTA.NUM_LOOPS)
+    # 5. LISTAKM, MLP encoder (lista_nonlinear preset: relu, bias, last_relu True)
+    cfg = ref_config.get_config("lista_nonlinear")
+    cfg.MODEL.TARGET_SIZE = 16
+    cfg.MODEL.ENCODER.LAYERS = [12, 12]
+    sd, L = synthetic.lista_km_weights(5, 12, 16, enc_layers=[12, 12])
+    cfg.MODEL.ENCODER.LISTA.L = 50.0
+    cfg.MODEL.ENCODER.LISTA.ALPHA = 0.5
+    gen_forecast("lista_mlp", cfg, 3, 4, sd, 5, 6, 105)
+    np.savez(os.path.join(HERE, "forecast_lista_mlp_meta.npz"), L=50.0, alpha=0.5, loops=cfg.MODEL.ENCODER.LISTA.NUM_LOOPS)
+
+
+def cfg1_model():
+    cfg = ref_config.get_config("finance_sparse")
+    cfg.MODEL.TARGET_SIZE = 128
+    sd = synthetic.generic_km_weights(0, 200, [1024, 1024], 128)
+    return cfg, sd
+
+
+def gen_cfg1():
+    cfg, sd = cfg1_model()
+    model = gen_forecast("cfg1", cfg, 10, 20, sd, 5, 16, 106, store_weights=False)
+    # --- the reference backtest, unmodified, on config 1 ---
+    N, d, H = 10, 20, 5
+    T = 1200
+    frame = make_frame(0, T, N)
+    # test split = exactly 252 embedded rows
+    val_end = str(frame.index[T - 253].date())
+    train_end = str(frame.index[T - 253 - 200].date())
+    env, stats, (tr, va, te) = build_env(frame, train_end, val_end, d)
+    assert te.shape == (252, 200), te.shape
+    mpc_cfg = shim_mpc.MPCConfig(horizon=H, cost_coeff=1e-3, max_turnover=0.2)
+    bt_cfg = ref_backtest.BacktestConfig(initial_capital=1e4, horizon=H, cost_coeff=1e-3)
+    shim_mpc.CALLS.clear()
+    strat = ref_backtest.KoopmanMPCStrategy(model, mpc_cfg, device="cpu")
+    df = ref_backtest.run_backtest(strat, env, bt_cfg, verbose=False)
+    metrics = ref_backtest.calculate_metrics(df)
+    calls = shim_mpc.CALLS
+    assert len(df) == 246 == len(calls)
+    bh = ref_backtest.run_backtest(ref_backtest.BuyAndHoldStrategy(), env, bt_cfg, verbose=False)
+    bh_metrics = ref_backtest.calculate_metrics(bh)
+    np.savez(
+        os.path.join(HERE, "backtest_cfg1.npz"),
+        T=T, n_train_days=T - 253 - 200 + 1, n_val_days=200, log_returns_seed=0,
+        mean=stats.mean, std=stats.std,
+        history=df[["portfolio_value", "return", "turnover", "cost"]].values.astype(np.float64),
+        metrics=np.array([metrics[k] for k in ("Sharpe Ratio", "Max Drawdown", "Avg Turnover", "Final Value", "Total Return")]),
+        bh_history=bh[["portfolio_value", "return", "turnover", "cost"]].values.astype(np.float64),
+        bh_metrics=np.array([bh_metrics[k] for k in ("Sharpe Ratio", "Max Drawdown", "Avg Turnover", "Final Value", "Total Return")]),
+        yhat=np.stack([c[1] for c in calls]).astype(np.float32),
+        w_cur=np.stack([c[0] for c in calls]), w_opt=np.stack([c[2] for c in calls]),
+        value=np.array([np.nan if c[3] is None else c[3] for c in calls]),
+        test_first_rows=te[:3], test_len=len(env.test_dataset),
+    )
+    print("cfg1 metrics", metrics)
+    print("buy&hold    ", bh_metrics)
+
+
+if __name__ == "__main__":
+    gen_data_small()
+    gen_forecasts()
+    gen_cfg1()
+    print("golden fixtures written to", HERE)

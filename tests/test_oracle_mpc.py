@@ -1,0 +1,100 @@
+"""MPC oracle: the reference's own tests (reference tests/test_mpc.py T1-T3), the exact optima derived in
+SURVEY.md §8c, an LP cross-check, and dense-vs-structured agreement."""
+import types
+
+import numpy as np
+import pytest
+from scipy.optimize import linprog
+
+from oracle import mpc_oracle as mo
+
+
+def cfg(**kw):
+    d = dict(horizon=5, gamma=0.0, cost_coeff=0.001, max_turnover=0.2, allow_short=False, solver="ECOS")
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+@pytest.mark.parametrize("method", ["dense", "structured"])
+def test_T1_feasibility(method):
+    N, H = 5, 3
+    w, info = mo.solve_mpc_log_utility(np.ones(N) / N, np.zeros((H, N)), cfg(horizon=H, cost_coeff=0.0), method)
+    assert info["status"] == "optimal" and w.shape == (H, N)
+    for t in range(H):
+        assert np.isclose(w[t].sum(), 1.0) and np.all(w[t] >= -1e-5)
+    assert abs(info["value"]) < 1e-12
+
+
+@pytest.mark.parametrize("method", ["dense", "structured"])
+def test_T2_preference_exact(method):
+    R = np.exp(np.array([[0.1, 0.0]]))
+    r = (mo.solve_dense if method == "dense" else mo.solve_structured)(np.array([0.5, 0.5]), None, 0.0, 0.2, R=R)
+    assert r.status == mo.STATUS_OPTIMAL
+    assert r.w[0, 0] > 0.5 > r.w[0, 1]
+    assert np.allclose(r.w[0], [0.6, 0.4], atol=1e-8)
+    assert abs(r.value - 0.06119156775022542) < 1e-10
+
+
+@pytest.mark.parametrize("method", ["dense", "structured"])
+def test_T3_transaction_costs(method):
+    w, info = mo.solve_mpc_log_utility(np.array([1.0, 0.0]), np.array([[0.0, 0.01]]), cfg(horizon=1, cost_coeff=10.0), method)
+    assert np.allclose(w[0], [1.0, 0.0], atol=1e-2)
+    assert np.allclose(w[0], [1.0, 0.0], atol=1e-8) and abs(info["value"]) < 1e-9
+
+
+def test_lp_crosscheck_lam0_H1():
+    """lam=0, H=1: log is monotone, so the optimiser maximises R.w over simplex ∩ L1-ball -> an LP."""
+    rng = np.random.default_rng(7)
+    for N in (4, 9, 20):
+        w0 = rng.dirichlet(np.ones(N))
+        R = np.exp(rng.standard_normal((1, N)) * 0.02)
+        tau = 0.3
+        # variables [w, u]: max R.w  s.t. sum w = 1, |w - w0| <= u, sum u <= tau, w >= 0
+        c = np.concatenate([-R[0], np.zeros(N)])
+        A_ub = np.block([[np.eye(N), -np.eye(N)], [-np.eye(N), -np.eye(N)], [np.zeros((1, N)), np.ones((1, N))]])
+        b_ub = np.concatenate([w0, -w0, [tau]])
+        lp = linprog(c, A_ub=A_ub, b_ub=b_ub, A_eq=np.concatenate([np.ones(N), np.zeros(N)])[None], b_eq=[1.0],
+                     bounds=[(0, None)] * (2 * N), method="highs")
+        for fn in (mo.solve_dense, mo.solve_structured):
+            r = fn(w0, None, 0.0, tau, R=R)
+            assert r.status == mo.STATUS_OPTIMAL
+            assert abs(np.log(-lp.fun) - r.value) < 1e-9
+
+
+def test_dense_vs_structured_random():
+    rng = np.random.default_rng(1)
+    worst_obj = worst_w = 0.0
+    for (N, H) in [(3, 2), (5, 3), (10, 5), (20, 5)]:
+        for trial in range(6):
+            w0 = rng.dirichlet(np.ones(N) * rng.choice([0.3, 1, 5]))
+            y = (rng.standard_normal((H, N)) * rng.choice([0.003, 0.01, 0.05])).astype(np.float32)
+            lam, tau = (1e-3, 0.2) if trial < 3 else (rng.choice([0, 1e-4, 1e-2]), rng.choice([0.05, 1.0, 0.0]))
+            a, b = mo.solve_dense(w0, y, lam, tau), mo.solve_structured(w0, y, lam, tau)
+            assert a.status == mo.STATUS_OPTIMAL and b.status == mo.STATUS_OPTIMAL
+            worst_obj = max(worst_obj, abs(a.value - b.value) / max(abs(a.value), 1e-3))
+            worst_w = max(worst_w, np.abs(a.w - b.w).max())
+            # feasibility of the structured solution
+            assert np.allclose(b.w.sum(axis=1), 1.0, atol=1e-9) and b.w.min() > -1e-12
+            if tau > 0:
+                d = np.abs(np.diff(np.vstack([w0, b.w]), axis=0)).sum(axis=1)
+                assert d.max() <= tau + 1e-8
+    assert worst_obj < 1e-6, worst_obj
+    assert worst_w < 1e-4, worst_w
+
+
+def test_fallback_on_nonfinite():
+    y = np.zeros((2, 3), np.float32); y[0, 1] = np.nan
+    w0 = np.array([0.2, 0.3, 0.5])
+    w, info = mo.solve_mpc_log_utility(w0, y, cfg(horizon=2))
+    assert info["value"] is None and info["status"] not in ("optimal", "optimal_inaccurate")
+    assert np.array_equal(w, np.tile(w0, (2, 1)))
+
+
+def test_allow_short_and_no_cap():
+    rng = np.random.default_rng(5)
+    w0 = rng.dirichlet(np.ones(4)); y = (rng.standard_normal((2, 4)) * 0.01).astype(np.float32)
+    a = mo.solve_dense(w0, y, 5e-3, 0.3, allow_short=True)
+    b = mo.solve_structured(w0, y, 5e-3, 0.3, allow_short=True)
+    assert a.status == 0 and b.status == 0 and abs(a.value - b.value) < 1e-8
+    a = mo.solve_dense(w0, y, 2e-2, 0.0); b = mo.solve_structured(w0, y, 2e-2, 0.0)
+    assert a.status == 0 and b.status == 0 and abs(a.value - b.value) < 1e-8
