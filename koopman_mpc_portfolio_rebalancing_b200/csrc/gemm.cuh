@@ -1,0 +1,58 @@
+// GEMM interface of the forecast path:  C = epilogue(A[M,K] . W[Nout,K]^T)
+// (nn.Linear convention: weight [out,in] row-major, x @ W^T + b, model.py:96-117).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kmpc {
+
+enum : int { EPI_NONE = 0, EPI_RELU = 1, EPI_TANH = 2, EPI_GELU = 3, EPI_SHRINK = 4 };
+
+struct GemmArgs {
+  // A row m starts at A + (m / a_rows_per_group) * a_group_stride + (m % a_rows_per_group) * lda  (elements).
+  // A plain matrix uses a_rows_per_group = M.  The delay-embedded window view of a standardised series
+  // [B,T,ld] uses rows_per_group = rows per path, group_stride = T*ld, lda = ld, K = d*ld: consecutive rows
+  // overlap and the embedded matrix is never materialised.
+  const float* A;
+  long long a_group_stride;
+  int a_rows_per_group;
+  int lda;
+  const float* W;      // [Nout, K], row stride ldw
+  int ldw;
+  int M, Nout, K;
+  const float* bias;   // [Nout] or null
+  const float* addend; // [M, ld_add] added before the activation (LISTA: z @ S + c), or null
+  int ld_add;
+  int act;             // EPI_*
+  float shrink_thr;    // EPI_SHRINK: sign(x) * max(|x| - thr, 0)   (model.py:30-40)
+  // de-standardise epilogue (data_finance.py:740-742): out = fl(fl(x * std32[g,col]) + mean32[g,col]),
+  // g = m / stat_rows_per_group (0 = shared stats).  Enabled when std32 != null.
+  const float* std32;
+  const float* mean32;
+  int stat_rows_per_group;
+  int stat_ld;
+  float* C;            // output, row stride ldc, only columns < n_store are written
+  long long ldc;
+  int n_store;
+  // optional second output holding the fp32 residual of the TF32 rounding of C (3xTF32 operand split)
+  float* C_lo;
+};
+
+// fp32 SIMT path (exact fp32 FMA accumulation; any shape / alignment)
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
+
+__device__ __forceinline__ float epilogue_apply(float x, int act, float thr) {
+  switch (act) {
+    case EPI_RELU: return (x < 0.0f) ? 0.0f : x;               // NaN propagates like torch.relu
+    case EPI_TANH: return tanhf(x);
+    case EPI_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case EPI_SHRINK: {
+      if (x != x) return x;                                       // sign(nan) * maximum(nan, 0) = nan
+      const float m = fmaxf(fabsf(x) - thr, 0.0f);
+      return (x > 0.0f) ? m : ((x < 0.0f) ? -m : 0.0f * m);
+    }
+    default: return x;
+  }
+}
+
+}  // namespace kmpc

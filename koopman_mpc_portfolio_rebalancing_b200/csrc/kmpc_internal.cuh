@@ -1,0 +1,64 @@
+// Internal declarations shared by the .cu files of libkmpc (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mpc_ipm.cuh"
+
+namespace kmpc {
+
+struct MpcSolveArgs {
+  const float* yhat;        // [P,H,N] predicted log-returns (fp32, as the strategy passes them) or null
+  const double* yhat64;     // [P,H,N] fp64 log-returns (R = exp in fp64) when yhat == null
+  const double* w_cur;      // [P,N]
+  const double* lam;        // [P] or null -> lam0
+  const double* tau;        // [P] or null -> tau0
+  double lam0, tau0;
+  int allow_short, P, N;
+  double* w_out;            // [P,H,N]
+  double* obj;              // [P]  (NaN when the fallback was taken)
+  double* kkt;              // [P,3] primal residual, dual residual, complementarity gap
+  int* status;              // [P]
+  int* iters;               // [P]
+  IpmOptions opt;
+};
+
+struct BacktestArgs {
+  const float* yhat;        // forecasts, row t of backtest b at yhat + index(b)*yhat_stride + t*H*N
+  const float* realized;    // de-standardised log-returns of every test row, [.., rows, N]
+  const int* yhat_index;    // [B] or null (identity)
+  const int* realized_index;
+  long long yhat_stride, realized_stride;   // elements
+  int rows, n_steps, rebalance_freq, n_hist;
+  const double* lam; const double* tau; const double* cost_coeff; const double* capital;   // [B] or null
+  double lam0, tau0, cost_coeff0, capital0;
+  int allow_short, B, N;
+  double* history;          // [B, n_hist, 4] or null: portfolio_value, return, turnover, cost
+  double* metrics;          // [B,5] Sharpe, MaxDD, AvgTurnover, FinalValue, TotalReturn
+  long long* solve_stats;   // [B,4] or null: #optimal, #inaccurate, #fallback, total IPM iterations
+  double* final_weights;    // [B,N] or null
+  int* work_counter;        // device int, zeroed before launch
+  IpmOptions opt;
+};
+
+int dispatch_mpc_solve(const MpcSolveArgs& A, int H, int sm_count, cudaStream_t st);
+int dispatch_backtest(const BacktestArgs& A, int H, int sm_count, cudaStream_t st);
+
+}  // namespace kmpc
+
+namespace kmpc {
+int mpc_variant_supported(int H, int N);
+int launch_standardize(const double* y, const double* mean, const double* sd, int spp, int B, int T, int N, float* out,
+                       int ld, int sm_count, cudaStream_t st);
+int launch_embed_gather(const float* data, int ld, int B, int T, int N, int d, float* out, int sm_count, cudaStream_t st);
+int launch_current_returns(const float* z, int ld, const double* mean, const double* sd, int spp, int B, int T, int N,
+                           int d, int row0, int rows, float* out, int sm_count, cudaStream_t st);
+}  // namespace kmpc
+
+struct kmpc_handle {
+  int device;
+  int sm_count;
+  long long launches;
+  int* work_counter;      // device int for the persistent backtest kernel
+  void* scratch;          // device workspace (forecast activations), grown on demand
+  size_t scratch_bytes;
+};

@@ -1,0 +1,89 @@
+"""MPC module — same names, arguments and error behaviour as /root/reference/mpc.py, solved on the GPU.
+
+``MPCConfig`` mirrors mpc.py:17-25 field for field; ``solve_mpc_log_utility`` mirrors mpc.py:27-117: it never
+raises on solver failure, it falls back to ``np.tile(current_weights, (H, 1))`` with ``value=None`` and a
+non-"optimal" status string.  The solve itself is the warp-per-problem fp64 interior-point kernel of
+csrc/mpc_ipm.cuh, reached through the C ABI (kmpc_mpc_solve_host / kmpc_mpc_solve).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Tuple
+
+import numpy as np
+
+from . import _capi
+
+STATUS_STRINGS = {0: "optimal", 1: "optimal_inaccurate", 2: "solver_error", 3: "nonfinite_input"}
+
+
+@dataclass
+class MPCConfig:
+    """Configuration for MPC solver (mpc.py:17-25)."""
+    horizon: int = 5
+    gamma: float = 0.0          # unused by the log-utility program (kept for signature parity)
+    cost_coeff: float = 0.001   # lambda of the objective
+    max_turnover: float = 0.2   # tau; <= 0 disables the cap (mpc.py:94)
+    allow_short: bool = False
+    solver: str = "ECOS"        # accepted and ignored: the CUDA interior-point solver is the only backend
+
+
+def solve_mpc_log_utility(current_weights: np.ndarray, predicted_log_returns: np.ndarray, config: MPCConfig,
+                          device: int = 0) -> Tuple[np.ndarray, Dict]:
+    """maximize sum_t [ log(w_t . exp(y_t)) - cost * ||w_t - w_{t-1}||_1 ]  s.t. sum(w_t)=1, w_t>=0,
+    ||w_t - w_{t-1}||_1 <= max_turnover.  Returns (optimal_weights [H,N] float64, {"status", "value"})."""
+    y = np.asarray(predicted_log_returns)
+    if y.ndim != 2:
+        raise ValueError("predicted_log_returns must be [horizon, n_assets]")   # the reference fails at H, N = shape
+    H, N = y.shape
+    f64 = y.dtype != np.float32
+    y = np.ascontiguousarray(y, dtype=np.float64 if f64 else np.float32)
+    w0 = np.ascontiguousarray(current_weights, dtype=np.float64).reshape(N)
+    w = np.empty((H, N), dtype=np.float64)
+    obj = np.empty(1, dtype=np.float64)
+    kkt = np.empty(3, dtype=np.float64)
+    st = np.empty(1, dtype=np.int32)
+    it = np.empty(1, dtype=np.int32)
+    h = _capi.Handle.get(device)
+    _capi.check(_capi.lib().kmpc_mpc_solve_host(
+        h.ptr, _capi.ptr(y), int(f64), _capi.ptr(w0), float(config.cost_coeff), float(config.max_turnover),
+        int(bool(config.allow_short)), 1, H, N, _capi.ptr(w), _capi.ptr(obj), _capi.ptr(kkt), _capi.ptr(st), _capi.ptr(it)))
+    status = STATUS_STRINGS[int(st[0])]
+    if status not in ("optimal", "optimal_inaccurate"):
+        return np.tile(w0, (H, 1)), {"status": status, "value": None, "kkt": tuple(kkt), "iterations": int(it[0])}
+    return w, {"status": status, "value": float(obj[0]), "kkt": tuple(kkt), "iterations": int(it[0])}
+
+
+def solve_mpc_batch(w_cur, yhat, lam=None, tau=None, cost_coeff: float = 1e-3, max_turnover: float = 0.2,
+                    allow_short: bool = False):
+    """P problems resident on the device.  w_cur [P,N] f64, yhat [P,H,N] f32 (or f64) CUDA tensors; lam/tau
+    optional [P] f64 CUDA tensors.  Returns dict of CUDA tensors: w [P,H,N], value [P], kkt [P,3], status [P],
+    iterations [P]."""
+    import torch
+    assert yhat.is_cuda and w_cur.is_cuda
+    P, H, N = yhat.shape
+    dev = yhat.device.index or 0
+    yhat = yhat.contiguous()
+    w_cur = w_cur.contiguous().to(torch.float64)
+    out = {
+        "w": torch.empty((P, H, N), dtype=torch.float64, device=yhat.device),
+        "value": torch.empty(P, dtype=torch.float64, device=yhat.device),
+        "kkt": torch.empty((P, 3), dtype=torch.float64, device=yhat.device),
+        "status": torch.empty(P, dtype=torch.int32, device=yhat.device),
+        "iterations": torch.empty(P, dtype=torch.int32, device=yhat.device),
+    }
+    if lam is not None:
+        lam = lam.contiguous().to(torch.float64)
+    if tau is not None:
+        tau = tau.contiguous().to(torch.float64)
+    y32 = yhat if yhat.dtype == torch.float32 else None
+    y64 = yhat if yhat.dtype == torch.float64 else None
+    if y32 is None and y64 is None:
+        raise TypeError("yhat must be float32 or float64")
+    h = _capi.Handle.get(dev)
+    _capi.check(_capi.lib().kmpc_mpc_solve(
+        h.ptr, _capi.ptr(y32), _capi.ptr(y64), _capi.ptr(w_cur), _capi.ptr(lam), _capi.ptr(tau), float(cost_coeff),
+        float(max_turnover), int(bool(allow_short)), P, H, N, _capi.ptr(out["w"]), _capi.ptr(out["value"]),
+        _capi.ptr(out["kkt"]), _capi.ptr(out["status"]), _capi.ptr(out["iterations"]), _capi.stream_ptr(dev)))
+    return out

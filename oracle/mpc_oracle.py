@@ -379,8 +379,7 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
         zw = gw0 + nu[:, None]
     nb = (3 if has_c else 2) * H
     status, res, it = STATUS_MAXITER, (np.inf,) * 3, 0
-    best = None
-    for it in range(1, max_iter + 1):
+    for it in range(1, max_iter + 2):
         rho = (w * R).sum(axis=1)
         gw = -R / rho[:, None]
         y = zp - zq
@@ -399,8 +398,8 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
         if res[0] < tol and res[1] < tol_dual and gap < tol:
             status = STATUS_OPTIMAL
             break
-        if res[0] < 1e-8 and res[1] < 1e-6 and gap < 1e-8 and (best is None or gap < best[1][2]):
-            best = (w.copy(), res)
+        if it == max_iter + 1:
+            break
         mu = gap / max(m, 1)
 
         Dw0 = zw / w if has_w else zHN
@@ -546,12 +545,9 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
             zp = zp + b_ * dzp; zq = zq + b_ * dzq
         if has_c:
             sc_ = sc_ + a_ * dsc; zc = zc + b_ * dzc
-    else:
-        if best is not None:
-            w, res = best
-            status = STATUS_INACCURATE
-    if status == STATUS_MAXITER and best is not None:
-        w, res = best
+    # not converged (iteration cap, numerical breakdown): accept the *current* iterate if it meets the loose
+    # tolerances ("optimal_inaccurate", mpc.py:113), else fall back to holding the weights (mpc.py:113-115)
+    if status != STATUS_OPTIMAL and np.isfinite(res[1] + res[2]) and res[0] < 1e-8 and res[1] < 1e-6 and res[2] < 1e-8:
         status = STATUS_INACCURATE
     return _finish(w.copy(), w_cur, R, lam, status, it, res, H)
 

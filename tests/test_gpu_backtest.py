@@ -1,0 +1,89 @@
+"""Persistent backtest kernel (MPC + portfolio step + metrics fused) vs the oracle loop and the golden history of
+the unmodified reference run_backtest (tests/golden/backtest_cfg1.npz)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt
+    from oracle import backtest_oracle as bo, data_oracle as do
+    return torch, bt, bo, do
+
+
+def test_cfg1_history_vs_reference_golden(golden):
+    """Same forecasts as the reference run -> same decisions; history within the fp32-exp ulp noise documented
+    in oracle/backtest_oracle.py (return <= 1.2e-7 abs per day, value 2e-6 rel)."""
+    torch, bt, bo, do = _mods()
+    from koopman_mpc_portfolio_rebalancing_b200 import synthetic
+    g = golden("backtest_cfg1.npz")
+    T, d, N, H = int(g["T"]), 20, 10, 5
+    lr = synthetic.gbm_log_returns(int(g["log_returns_seed"]), T, N)
+    z = do.standardize(lr, g["mean"], g["std"])
+    emb = do.time_delay_embedding(z, d)
+    _, _, (c0, c1) = do.split_rows(T, int(g["n_train_days"]), int(g["n_val_days"]), d)
+    all_ret = do.destandardize(do.extract_current_returns(emb[c0:c1], N), g["mean"], g["std"])
+    yhat = torch.from_numpy(g["yhat"]).cuda().unsqueeze(0)
+    realized = torch.from_numpy(all_ret).cuda().unsqueeze(0)
+    out = bt.run_backtest_batched(yhat, realized, n_steps=246, horizon=H, want_history=True)
+    hist = out["history"][0].cpu().numpy(); met = out["metrics"][0].cpu().numpy(); stats = out["stats"][0].cpu().numpy()
+    assert stats[0] == 246 and stats[1] == 0 and stats[2] == 0, stats
+    ref_hist, _ = bo.run_backtest(bo.koopman_mpc_decider(g["yhat"], 1e-3, 0.2), all_ret, int(g["test_len"]), H)
+    # vs the oracle loop with the same (platform-independent) exp convention: tight
+    assert np.allclose(hist[:, 1], ref_hist[:, 1], atol=2e-9), np.abs(hist[:, 1] - ref_hist[:, 1]).max()
+    assert np.allclose(hist[:, 0], ref_hist[:, 0], rtol=1e-7)
+    assert np.allclose(hist[:, 2], ref_hist[:, 2], atol=2e-6)
+    m = bo.calculate_metrics(ref_hist)
+    assert np.allclose(met, [m[k] for k in bo.METRIC_KEYS], rtol=1e-6, atol=1e-7)
+    # vs the unmodified reference run: numpy's fp32 exp is not correctly rounded (<= 1 ulp of ~1.0 per day)
+    assert np.abs(hist[:, 1] - g["history"][:, 1]).max() < 2.5e-7
+    assert np.allclose(hist[:, 0], g["history"][:, 0], rtol=5e-6)
+    assert np.allclose(met, g["metrics"], rtol=2e-4, atol=2e-5)
+    # device metrics == calculate_metrics on the device history
+    import pandas as pd
+    df = pd.DataFrame(hist, columns=list(bt.HISTORY_COLS))
+    m2 = bt.calculate_metrics(df)
+    assert np.allclose(met, [m2[k] for k in bt.METRIC_KEYS], rtol=1e-10, atol=1e-12)
+
+
+def test_batched_sweep_matches_individual_runs():
+    """lambda/tau sweep over shared forecasts + several price paths (config-4 shape, tiny): every backtest equals its
+    own oracle run; sharing indices must not mix paths."""
+    torch, bt, bo, do = _mods()
+    rng = np.random.default_rng(3)
+    N, H, rows = 12, 3, 40
+    n_steps = rows - 1 - H
+    S, Q = 2, 3
+    yhat = (3e-4 + 0.01 * rng.standard_normal((S, n_steps, H, N))).astype(np.float32)
+    realized = (0.012 * rng.standard_normal((Q, rows, N))).astype(np.float32)
+    lam = np.array([1e-3, 1e-2, 0.0, 1e-4, 1e-3, 5e-3]); tau = np.array([0.2, 0.05, 0.5, 0.0, 1.0, 0.2])
+    yi = np.array([0, 1, 0, 1, 0, 1], np.int32); ri = np.array([0, 1, 2, 0, 1, 2], np.int32)
+    cc = np.array([1e-3, 2e-3, 0.0, 1e-3, 1e-3, 5e-4]); cap = np.array([1e4, 5e3, 1.0, 1e4, 2e4, 1e4])
+    out = bt.run_backtest_batched(torch.from_numpy(yhat).cuda(), torch.from_numpy(realized).cuda(), n_steps=n_steps,
+                                  horizon=H, lam=lam, tau=tau, cost_coeff=cc, capital=cap, yhat_index=yi,
+                                  realized_index=ri, want_history=True)
+    hist = out["history"].cpu().numpy(); met = out["metrics"].cpu().numpy()
+    for b in range(6):
+        rh, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat[yi[b]], lam[b], tau[b]), realized[ri[b]], rows - 1, H,
+                                initial_capital=cap[b], cost_coeff=cc[b])
+        assert np.allclose(hist[b][:, 0], rh[:, 0], rtol=1e-6), b
+        assert np.allclose(hist[b][:, 1], rh[:, 1], atol=1e-7), b
+        m = bo.calculate_metrics(rh)
+        assert np.allclose(met[b], [m[k] for k in bo.METRIC_KEYS], rtol=1e-5, atol=1e-6), b
+
+
+def test_rebalance_freq_and_short_horizon():
+    torch, bt, bo, do = _mods()
+    rng = np.random.default_rng(4)
+    N, H, rows = 5, 2, 30
+    n_steps = rows - 1 - H
+    yhat = (0.01 * rng.standard_normal((1, n_steps, H, N))).astype(np.float32)
+    realized = (0.012 * rng.standard_normal((1, rows, N))).astype(np.float32)
+    out = bt.run_backtest_batched(torch.from_numpy(yhat).cuda(), torch.from_numpy(realized).cuda(), n_steps=n_steps,
+                                  horizon=H, rebalance_freq=3, want_history=True)
+    rh, ts = bo.run_backtest(bo.koopman_mpc_decider(yhat[0], 1e-3, 0.2), realized[0], rows - 1, H, rebalance_freq=3)
+    hist = out["history"][0].cpu().numpy()
+    assert hist.shape == rh.shape == (len(range(0, n_steps, 3)), 4)
+    assert np.allclose(hist[:, 0], rh[:, 0], rtol=1e-6)

@@ -1,0 +1,104 @@
+"""CUDA MPC solver (through the C ABI) vs the fp64 oracle.  Parity bar (BASELINE.json north_star): objective
+within 1e-6 relative, weights within 1e-4 L-inf (where the optimiser is well conditioned), KKT residuals reported."""
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+OBJ_RTOL = 1e-6      # |obj_gpu - obj_oracle| <= OBJ_RTOL * max(|obj_oracle|, OBJ_FLOOR)
+OBJ_FLOOR = 1e-3     # objectives are sums of daily log-growth; below 1e-3 the bar is absolute 1e-9
+W_ATOL = 1e-4
+
+
+def _mods():
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import mpc
+    from oracle import mpc_oracle as mo
+    return torch, mpc, mo
+
+
+def test_reference_tests_T1_T2_T3():
+    """reference tests/test_mpc.py, verbatim semantics, through the drop-in signature"""
+    torch, mpc, mo = _mods()
+    N, H = 5, 3
+    w, info = mpc.solve_mpc_log_utility(np.ones(N) / N, np.zeros((H, N)), mpc.MPCConfig(horizon=H, cost_coeff=0.0))
+    assert info["status"] == "optimal" and w.shape == (H, N)
+    for t in range(H):
+        assert np.isclose(np.sum(w[t]), 1.0) and np.all(w[t] >= -1e-5)
+    w, info = mpc.solve_mpc_log_utility(np.array([0.5, 0.5]), np.array([[0.1, 0.0]]), mpc.MPCConfig(horizon=1, cost_coeff=0.0))
+    assert w[0, 0] > 0.5 and w[0, 1] < 0.5
+    assert np.allclose(w[0], [0.6, 0.4], atol=1e-7) and abs(info["value"] - 0.06119156775022542) < 1e-9
+    w, info = mpc.solve_mpc_log_utility(np.array([1.0, 0.0]), np.array([[0.0, 0.01]]), mpc.MPCConfig(horizon=1, cost_coeff=10.0))
+    assert np.allclose(w[0], [1.0, 0.0], atol=1e-2)
+    assert np.allclose(w[0], [1.0, 0.0], atol=1e-7) and abs(info["value"]) < 1e-8
+
+
+def test_fallback_never_raises():
+    torch, mpc, mo = _mods()
+    y = np.zeros((2, 3), np.float32); y[0, 1] = np.nan
+    w0 = np.array([0.2, 0.3, 0.5])
+    w, info = mpc.solve_mpc_log_utility(w0, y, mpc.MPCConfig(horizon=2))
+    assert info["value"] is None and info["status"] not in ("optimal", "optimal_inaccurate")
+    assert np.array_equal(w, np.tile(w0, (2, 1)))
+
+
+@pytest.mark.parametrize("N,H", [(2, 1), (5, 3), (10, 5), (33, 2), (50, 5), (64, 4)])
+def test_random_instances_vs_oracle(N, H):
+    torch, mpc, mo = _mods()
+    rng = np.random.default_rng(100 * N + H)
+    P = 48
+    w0 = np.stack([rng.dirichlet(np.ones(N) * rng.choice([0.3, 1.0, 5.0])) for _ in range(P)])
+    y = np.stack([(3e-4 + rng.standard_normal((H, N)) * rng.choice([0.003, 0.01, 0.03])) for _ in range(P)]).astype(np.float32)
+    lam = np.where(rng.random(P) < 0.5, 1e-3, rng.choice([0.0, 1e-4, 1e-2], P))
+    tau = np.where(rng.random(P) < 0.5, 0.2, rng.choice([0.05, 1.0, 0.0], P))
+    out = mpc.solve_mpc_batch(torch.from_numpy(w0).cuda(), torch.from_numpy(y).cuda(),
+                              lam=torch.from_numpy(lam).cuda(), tau=torch.from_numpy(tau).cuda())
+    W = out["w"].cpu().numpy(); val = out["value"].cpu().numpy(); st = out["status"].cpu().numpy()
+    kkt = out["kkt"].cpu().numpy(); its = out["iterations"].cpu().numpy()
+    worst_obj = worst_w = 0.0
+    for p in range(P):
+        ref = mo.solve_structured(w0[p], y[p], float(lam[p]), float(tau[p]))
+        assert ref.status == mo.STATUS_OPTIMAL
+        assert st[p] == 0, (p, st[p], kkt[p], its[p])
+        worst_obj = max(worst_obj, abs(val[p] - ref.value) / max(abs(ref.value), OBJ_FLOOR))
+        worst_w = max(worst_w, np.abs(W[p] - ref.w).max())
+        assert np.allclose(W[p].sum(axis=1), 1.0, atol=1e-8) and W[p].min() > -1e-10
+        if tau[p] > 0:
+            turn = np.abs(np.diff(np.vstack([w0[p], W[p]]), axis=0)).sum(axis=1)
+            assert turn.max() <= tau[p] + 1e-7
+        assert kkt[p, 0] < 1e-8 and kkt[p, 1] < 1e-6 and kkt[p, 2] < 1e-8       # reported KKT residuals
+    print(f"N={N} H={H}: worst rel obj gap {worst_obj:.2e}, worst |dw|_inf {worst_w:.2e}, mean iters {its.mean():.1f}")
+    assert worst_obj < OBJ_RTOL, worst_obj
+    assert worst_w < W_ATOL, worst_w
+
+
+def test_dense_oracle_crosscheck_small():
+    """independent algorithm (generic dense IPM) on a few instances: objective parity"""
+    torch, mpc, mo = _mods()
+    rng = np.random.default_rng(9)
+    for (N, H) in [(4, 2), (10, 5), (20, 5)]:
+        w0 = rng.dirichlet(np.ones(N)); y = (rng.standard_normal((H, N)) * 0.01).astype(np.float32)
+        w, info = mpc.solve_mpc_log_utility(w0, y, mpc.MPCConfig(horizon=H))
+        ref = mo.solve_dense(w0, y, 1e-3, 0.2)
+        assert info["status"] == "optimal" and ref.status == 0
+        assert abs(info["value"] - ref.value) <= OBJ_RTOL * max(abs(ref.value), OBJ_FLOOR)
+
+
+def test_allow_short_and_uncapped():
+    torch, mpc, mo = _mods()
+    rng = np.random.default_rng(5)
+    w0 = rng.dirichlet(np.ones(6)); y = (rng.standard_normal((3, 6)) * 0.01).astype(np.float32)
+    for kw in (dict(cost_coeff=5e-3, max_turnover=0.3, allow_short=True), dict(cost_coeff=2e-2, max_turnover=0.0)):
+        w, info = mpc.solve_mpc_log_utility(w0, y, mpc.MPCConfig(horizon=3, **kw))
+        ref = mo.solve_structured(w0, y, kw["cost_coeff"], kw["max_turnover"], kw.get("allow_short", False))
+        assert info["status"] == "optimal"
+        assert abs(info["value"] - ref.value) <= OBJ_RTOL * max(abs(ref.value), OBJ_FLOOR)
+
+
+def test_unsupported_shape_fails_loudly():
+    torch, mpc, mo = _mods()
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    with pytest.raises(_capi.KmpcError):
+        mpc.solve_mpc_log_utility(np.ones(700) / 700, np.zeros((5, 700), np.float32), mpc.MPCConfig())
