@@ -1,9 +1,384 @@
-// placeholder until the forecast path lands (next commit)
+// Koopman forecast path: encoder (MLP or LISTA) -> H x (z <- z @ K [norm]) -> decoder -> first N columns ->
+// de-standardise.  Replaces model.py (MLPCoder 67-117, LISTA 120-209, GenericKM 701-797, LISTAKM 801-870) on the
+// backtest path (backtest.py:85-121) for all rebalancing steps of all backtests at once.
+//
+// Layout: activations row-major fp32 [rows, width], processed in row chunks small enough to stay L2-resident
+// between consecutive layers.  The delay-embedded input is never materialised: row (b,t) of the first GEMM is
+// the window z[b, t .. t+d-1, :] of the standardised series (forward time order, row stride ld = pad4(N)), and
+// the first-layer weight columns are permuted once at load time to undo the [y_t, y_{t-1}, ...] ordering of
+// data_finance.py:290-298.
+#include <vector>
+#include <stdio.h>
 #include "../../include/kmpc.h"
-extern "C" {
-int kmpc_model_load(kmpc_handle*, const kmpc_model_desc*, kmpc_model**) { return KMPC_E_UNSUPPORTED; }
-int kmpc_model_free(kmpc_model*) { return KMPC_OK; }
-int kmpc_forecast(kmpc_handle*, const kmpc_model*, const float*, int, const double*, const double*, int, int, int, int, int, int, int, float*, void*) { return KMPC_E_UNSUPPORTED; }
-int kmpc_encode(kmpc_handle*, const kmpc_model*, const float*, int, float*, void*) { return KMPC_E_UNSUPPORTED; }
-int kmpc_rollout(kmpc_handle*, const kmpc_model*, const float*, int, int, int, float*, void*) { return KMPC_E_UNSUPPORTED; }
+#include "kmpc_internal.cuh"
+#include "gemm.cuh"
+
+int kmpc_fail_cuda(cudaError_t e, const char* what);
+namespace kmpc { int launch_gemm(const GemmArgs& g, cudaStream_t st, long long* launches); }
+
+struct kmpc_model {
+  kmpc_handle* h;
+  int kind, obs, N, d, Z, ld, norm_fn;
+  int n_enc, enc_act, enc_last_relu;
+  std::vector<int> enc_dims;
+  std::vector<float*> enc_w, enc_b;
+  float* enc_w0_win;           // first encoder / We layer re-laid for the in-place window read [h1, d*ld]
+  int n_dec, dec_act;
+  std::vector<int> dec_dims;
+  std::vector<float*> dec_w, dec_b;
+  float* kmatT;                // [Z,Z] = kmat^T  (GEMM computes A . W^T)
+  int lista_linear, lista_loops;
+  float lista_thr;
+  float* lista_ST;             // S^T
+  float* lista_wdT;            // [obs, Z]: (dict / ||dict||_row.clamp(1e-4))^T
+  std::vector<void*> owned;
+};
+
+namespace kmpc {
+
+__global__ void transpose_kernel(const float* __restrict__ in, int R, int Cc, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? in[(size_t)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) out[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
 }
+
+// Wwin[o, jj*ld + a] = W[o, (d-1-jj)*N + a] for a < N, 0 in the padding columns
+__global__ void window_permute_kernel(const float* __restrict__ W, int out_f, int N, int d, int ld, float* __restrict__ Wwin) {
+  const long long total = (long long)out_f * d * ld;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(idx / (d * ld));
+    const int rem = (int)(idx - (long long)o * d * ld);
+    const int jj = rem / ld, a = rem - jj * ld;
+    Wwin[idx] = (a < N) ? W[(size_t)o * d * N + (size_t)(d - 1 - jj) * N + a] : 0.f;
+  }
+}
+
+// wdT[c, z] = dict[z, c] / max(||dict[z,:]||_2, 1e-4)   (model.py:848-850); one warp per dictionary row z
+__global__ void dict_normalize_transpose_kernel(const float* __restrict__ dict, int Z, int obs, float* __restrict__ wdT) {
+  const int z = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (z >= Z) return;
+  float s = 0.f;
+  for (int c = lane; c < obs; c += 32) { const float v = dict[(size_t)z * obs + c]; s = fmaf(v, v, s); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float nrm = fmaxf(sqrtf(s), 1e-4f);
+  for (int c = lane; c < obs; c += 32) wdT[(size_t)c * Z + z] = dict[(size_t)z * obs + c] / nrm;
+}
+
+// z <- z / ||z||_2 per row (GenericKM 'ball' norm, model.py:751-752; no epsilon, like the reference)
+__global__ void row_normalize_kernel(float* __restrict__ z, int M, int Z) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float s = 0.f;
+  for (int c = lane; c < Z; c += 32) { const float v = z[(size_t)m * Z + c]; s = fmaf(v, v, s); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float nrm = sqrtf(s);
+  for (int c = lane; c < Z; c += 32) z[(size_t)m * Z + c] = z[(size_t)m * Z + c] / nrm;
+}
+
+__global__ void shrink_kernel(const float* __restrict__ c, float* __restrict__ z, long long n, float thr) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    z[i] = epilogue_apply(c[i], EPI_SHRINK, thr);
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __double2float_rn(in[i]);
+}
+
+static int act_to_epi(int act) { return act == KMPC_ACT_RELU ? EPI_RELU : (act == KMPC_ACT_TANH ? EPI_TANH : EPI_GELU); }
+
+struct AView {            // how the rows of the first GEMM are addressed
+  const float* A; long long group_stride; int rows_per_group; int lda; int K; bool window;
+};
+
+static GemmArgs base_args() {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.act = EPI_NONE;
+  return g;
+}
+
+// Runs the whole chain for `M` rows.  out_mode 0: latent z0 -> out [M,Z];  1: yhat de-standardised [M,H,N];
+// 2: standardised decoder output, first n_cols columns [M,H,n_cols].
+static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M, int H, int out_mode, int n_cols,
+                     const float* std32, const float* mean32, int stat_rows_per_group, float* out, cudaStream_t st) {
+  const int Z = m->Z;
+  int maxw = Z;
+  for (int v : m->enc_dims) if (v > maxw) maxw = v;
+  for (int v : m->dec_dims) if (v > maxw) maxw = v;
+  // chunk rows so that the ping-pong activations (~4 buffers) stay inside the 126 MB L2
+  long long ch = (96ll << 20) / (4ll * 4 * maxw);
+  ch = (ch / 128) * 128;
+  if (ch < 128) ch = 128;
+  if (ch > M) ch = M;
+  const int CH = (int)ch;
+  const size_t need = (size_t)CH * maxw * 4 * sizeof(float) + 256;
+  if (h->scratch_bytes < need) {
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr; h->scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&h->scratch, need);
+    if (e != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(forecast scratch)");
+    h->scratch_bytes = need;
+  }
+  float* buf[4];
+  for (int i = 0; i < 4; ++i) buf[i] = (float*)h->scratch + (size_t)i * CH * maxw;
+  int rc;
+  for (int r0 = 0; r0 < M; r0 += CH) {
+    const int rows = (M - r0 < CH) ? (M - r0) : CH;
+    // ---------------- encoder ----------------
+    const float* x = nullptr; int xld = 0;
+    float* zcur = buf[2];
+    float* cbuf = buf[3];                 // LISTA pre-activation c
+    const bool mlp_enc = (m->kind == KMPC_MODEL_GENERIC) || !m->lista_linear;
+    if (mlp_enc) {
+      for (int li = 0; li < m->n_enc; ++li) {
+        GemmArgs g = base_args();
+        const bool last = (li == m->n_enc - 1);
+        if (li == 0) {
+          g.A = av.A; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda;
+          g.row0 = r0; g.K = av.K;
+          g.W = av.window ? m->enc_w0_win : m->enc_w[0]; g.ldw = av.K;
+        } else {
+          g.A = x; g.a_group_stride = 0; g.a_rows_per_group = rows; g.lda = xld; g.row0 = 0; g.K = m->enc_dims[li];
+          g.W = m->enc_w[li]; g.ldw = m->enc_dims[li];
+        }
+        g.M = rows; g.Nout = m->enc_dims[li + 1]; g.n_store = g.Nout;
+        g.bias = m->enc_b[li];
+        g.act = last ? (m->enc_last_relu ? EPI_RELU : EPI_NONE) : act_to_epi(m->enc_act);
+        float* o = last ? ((m->kind == KMPC_MODEL_LISTA) ? cbuf : zcur) : buf[li & 1];
+        g.C = o; g.ldc = g.Nout;
+        if ((rc = launch_gemm(g, st, &h->launches))) return rc;
+        x = o; xld = g.Nout;
+      }
+    } else {   // LISTA linear encoder: c = x @ We^T
+      GemmArgs g = base_args();
+      g.A = av.A; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda; g.row0 = r0;
+      g.K = av.K; g.W = av.window ? m->enc_w0_win : m->enc_w[0]; g.ldw = av.K;
+      g.M = rows; g.Nout = Z; g.n_store = Z; g.C = cbuf; g.ldc = Z;
+      if ((rc = launch_gemm(g, st, &h->launches))) return rc;
+    }
+    if (m->kind == KMPC_MODEL_LISTA) {
+      const long long n = (long long)rows * Z;
+      int blocks = (int)((n + 255) / 256); if (blocks > h->sm_count * 8) blocks = h->sm_count * 8;
+      shrink_kernel<<<blocks, 256, 0, st>>>(cbuf, zcur, n, m->lista_thr); h->launches++;
+      float* zalt = buf[0];
+      for (int it = 0; it < m->lista_loops; ++it) {          // z = shrink(z @ S + c)
+        GemmArgs g = base_args();
+        g.A = zcur; g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->lista_ST; g.ldw = Z;
+        g.M = rows; g.Nout = Z; g.n_store = Z; g.addend = cbuf; g.ld_add = Z; g.act = EPI_SHRINK; g.shrink_thr = m->lista_thr;
+        g.C = zalt; g.ldc = Z;
+        if ((rc = launch_gemm(g, st, &h->launches))) return rc;
+        float* t = zcur; zcur = zalt; zalt = t;
+      }
+      if (zcur != buf[2]) {   // keep the convention zcur == buf[2] or buf[0]; both are fine below
+      }
+    } else if (m->norm_fn == KMPC_NORM_BALL) {
+      row_normalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(zcur, rows, Z); h->launches++;
+    }
+    if (out_mode == 0) {
+      cudaError_t e = cudaMemcpyAsync(out + (size_t)r0 * Z, zcur, (size_t)rows * Z * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return kmpc_fail_cuda(e, "copy latent");
+      continue;
+    }
+    // ---------------- K unroll + decoder ----------------
+    float* znext = (zcur == buf[2]) ? buf[0] : buf[2];
+    float* hbuf[2] = {buf[1], buf[3]};
+    for (int k = 0; k < H; ++k) {
+      GemmArgs g = base_args();
+      g.A = zcur; g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->kmatT; g.ldw = Z;
+      g.M = rows; g.Nout = Z; g.n_store = Z; g.C = znext; g.ldc = Z;
+      if ((rc = launch_gemm(g, st, &h->launches))) return rc;
+      { float* t = zcur; zcur = znext; znext = t; }
+      if (m->kind == KMPC_MODEL_GENERIC && m->norm_fn == KMPC_NORM_BALL) {
+        row_normalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(zcur, rows, Z); h->launches++;
+      }
+      const int ncol = (out_mode == 1) ? m->N : n_cols;
+      float* dst = out + ((size_t)r0 * H + k) * ncol;
+      if (m->kind == KMPC_MODEL_GENERIC) {
+        const float* xx = zcur; int xl = Z;
+        for (int li = 0; li < m->n_dec; ++li) {
+          GemmArgs d = base_args();
+          const bool last = (li == m->n_dec - 1);
+          d.A = xx; d.a_rows_per_group = rows; d.lda = xl; d.K = m->dec_dims[li]; d.W = m->dec_w[li]; d.ldw = m->dec_dims[li];
+          d.M = rows; d.bias = m->dec_b[li];
+          if (last) {
+            d.Nout = ncol; d.n_store = ncol; d.C = dst; d.ldc = (long long)H * ncol;
+            if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.row0 = r0; }
+          } else {
+            d.Nout = m->dec_dims[li + 1]; d.n_store = d.Nout; d.act = act_to_epi(m->dec_act); d.C = hbuf[li & 1]; d.ldc = d.Nout;
+          }
+          if ((rc = launch_gemm(d, st, &h->launches))) return rc;
+          xx = d.C; xl = d.Nout;
+        }
+      } else {
+        GemmArgs d = base_args();
+        d.A = zcur; d.a_rows_per_group = rows; d.lda = Z; d.K = Z; d.W = m->lista_wdT; d.ldw = Z;
+        d.M = rows; d.Nout = ncol; d.n_store = ncol; d.C = dst; d.ldc = (long long)H * ncol;
+        if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.row0 = r0; }
+        if ((rc = launch_gemm(d, st, &h->launches))) return rc;
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace kmpc
+
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char f_err[256];
+static int ffail(int code, const char* msg) { snprintf(f_err, sizeof(f_err), "%s", msg); return code; }
+#define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return kmpc_fail_cuda(e_, #call); } while (0)
+
+static int dev_copy(kmpc_model* m, const float* src, size_t n, float** out) {
+  float* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, n * sizeof(float));
+  if (e != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(model)");
+  m->owned.push_back(p);
+  if (src) { e = cudaMemcpy(p, src, n * sizeof(float), cudaMemcpyDeviceToDevice); if (e != cudaSuccess) return kmpc_fail_cuda(e, "copy weights"); }
+  *out = p;
+  return 0;
+}
+
+extern "C" {
+
+int kmpc_model_free(kmpc_model* m) {
+  if (!m) return KMPC_OK;
+  cudaSetDevice(m->h->device);
+  for (void* p : m->owned) cudaFree(p);
+  delete m;
+  return KMPC_OK;
+}
+
+int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) {
+  if (!h || !D || !out) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: NULL argument");
+  if (D->obs != D->n_assets * D->delay || D->latent <= 0 || D->n_assets <= 0)
+    return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: obs must equal n_assets*delay");
+  FCK(cudaSetDevice(h->device));
+  kmpc_model* m = new kmpc_model();
+  m->h = h; m->kind = D->kind; m->obs = D->obs; m->N = D->n_assets; m->d = D->delay; m->Z = D->latent;
+  m->ld = ((D->n_assets + 3) / 4) * 4; m->norm_fn = D->norm_fn;
+  m->n_enc = 0; m->enc_act = D->enc_act; m->enc_last_relu = D->enc_last_relu; m->enc_w0_win = nullptr;
+  m->n_dec = 0; m->dec_act = D->dec_act; m->kmatT = nullptr;
+  m->lista_linear = D->lista_linear_encoder; m->lista_loops = D->lista_loops; m->lista_thr = D->lista_threshold;
+  m->lista_ST = nullptr; m->lista_wdT = nullptr;
+  int rc = 0;
+  auto bail = [&](int code) { kmpc_model_free(m); return code; };
+  const bool mlp_enc = (D->kind == KMPC_MODEL_GENERIC) || !D->lista_linear_encoder;
+  const float* first_w = nullptr; int first_out = 0;
+  if (mlp_enc) {
+    if (D->n_enc <= 0 || !D->enc_dims_host || !D->enc_w_host) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: encoder layers missing"));
+    m->n_enc = D->n_enc;
+    m->enc_dims.assign(D->enc_dims_host, D->enc_dims_host + D->n_enc + 1);
+    if (m->enc_dims[0] != D->obs || m->enc_dims[D->n_enc] != D->latent) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: encoder dims must run obs -> latent"));
+    for (int i = 0; i < D->n_enc; ++i) {
+      float *w = nullptr, *b = nullptr;
+      if ((rc = dev_copy(m, D->enc_w_host[i], (size_t)m->enc_dims[i] * m->enc_dims[i + 1], &w))) return bail(rc);
+      if (D->enc_b_host && D->enc_b_host[i]) { if ((rc = dev_copy(m, D->enc_b_host[i], m->enc_dims[i + 1], &b))) return bail(rc); }
+      m->enc_w.push_back(w); m->enc_b.push_back(b);
+    }
+    first_w = m->enc_w[0]; first_out = m->enc_dims[1];
+  } else {
+    if (!D->lista_We) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: lista_We missing"));
+    float* w = nullptr;
+    if ((rc = dev_copy(m, D->lista_We, (size_t)D->latent * D->obs, &w))) return bail(rc);
+    m->enc_w.push_back(w); m->enc_b.push_back(nullptr);
+    m->enc_dims = {D->obs, D->latent};
+    first_w = w; first_out = D->latent;
+  }
+  {  // first layer re-laid for the window read
+    if ((rc = dev_copy(m, nullptr, (size_t)first_out * m->d * m->ld, &m->enc_w0_win))) return bail(rc);
+    kmpc::window_permute_kernel<<<h->sm_count * 4, 256>>>(first_w, first_out, m->N, m->d, m->ld, m->enc_w0_win);
+  }
+  if (!D->kmat) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: kmat missing"));
+  if ((rc = dev_copy(m, nullptr, (size_t)m->Z * m->Z, &m->kmatT))) return bail(rc);
+  {
+    dim3 grid((m->Z + 31) / 32, (m->Z + 31) / 32), blk(32, 8);
+    kmpc::transpose_kernel<<<grid, blk>>>(D->kmat, m->Z, m->Z, m->kmatT);
+  }
+  if (D->kind == KMPC_MODEL_GENERIC) {
+    if (D->n_dec <= 0 || !D->dec_dims_host || !D->dec_w_host) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: decoder layers missing"));
+    m->n_dec = D->n_dec;
+    m->dec_dims.assign(D->dec_dims_host, D->dec_dims_host + D->n_dec + 1);
+    if (m->dec_dims[0] != D->latent || m->dec_dims[D->n_dec] != D->obs) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: decoder dims must run latent -> obs"));
+    for (int i = 0; i < D->n_dec; ++i) {
+      float *w = nullptr, *b = nullptr;
+      if ((rc = dev_copy(m, D->dec_w_host[i], (size_t)m->dec_dims[i] * m->dec_dims[i + 1], &w))) return bail(rc);
+      if (D->dec_b_host && D->dec_b_host[i]) { if ((rc = dev_copy(m, D->dec_b_host[i], m->dec_dims[i + 1], &b))) return bail(rc); }
+      m->dec_w.push_back(w); m->dec_b.push_back(b);
+    }
+  } else {
+    if (!D->lista_S || !D->lista_dict) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: lista_S / lista_dict missing"));
+    if ((rc = dev_copy(m, nullptr, (size_t)m->Z * m->Z, &m->lista_ST))) return bail(rc);
+    dim3 grid((m->Z + 31) / 32, (m->Z + 31) / 32), blk(32, 8);
+    kmpc::transpose_kernel<<<grid, blk>>>(D->lista_S, m->Z, m->Z, m->lista_ST);
+    if ((rc = dev_copy(m, nullptr, (size_t)m->obs * m->Z, &m->lista_wdT))) return bail(rc);
+    kmpc::dict_normalize_transpose_kernel<<<(m->Z + 7) / 8, 256>>>(D->lista_dict, m->Z, m->obs, m->lista_wdT);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return bail(kmpc_fail_cuda(e, "kmpc_model_load kernels"));
+  h->launches += 3;
+  *out = m;
+  return KMPC_OK;
+}
+
+static int stats_to_f32(kmpc_handle* h, const double* mean, const double* std, int n, float** std32, float** mean32, cudaStream_t st) {
+  // small per-call conversion buffer kept at the tail of the handle (re-allocated if the size grows)
+  static thread_local float* buf = nullptr; static thread_local int cap = 0;
+  if (cap < 2 * n) {
+    if (buf) cudaFree(buf);
+    cudaError_t e = cudaMalloc(&buf, (size_t)2 * n * sizeof(float));
+    if (e != cudaSuccess) { buf = nullptr; cap = 0; return kmpc_fail_cuda(e, "cudaMalloc(stats)"); }
+    cap = 2 * n;
+  }
+  int blocks = (n + 255) / 256;
+  kmpc::f64_to_f32_kernel<<<blocks, 256, 0, st>>>(std, buf, n);
+  kmpc::f64_to_f32_kernel<<<blocks, 256, 0, st>>>(mean, buf + n, n);
+  h->launches += 2;
+  *std32 = buf; *mean32 = buf + n;
+  return 0;
+}
+
+int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z, const double* mean, const double* std,
+                  int stats_per_path, int B, int T, int row0, int t0, int t1, int H, float* yhat, void* stream) {
+  if (!h || !m || !z || !mean || !std || !yhat) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_forecast: NULL argument");
+  if (ld_z != m->ld) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_forecast: ld_z must be n_assets rounded up to a multiple of 4");
+  if (B <= 0 || H <= 0 || t1 <= t0 || row0 < 0 || t0 < 0 || row0 + t1 + m->d - 1 > T)
+    return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_forecast: bad row range");
+  FCK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float *std32, *mean32;
+  int rc = stats_to_f32(h, mean, std, (stats_per_path ? B : 1) * m->N, &std32, &mean32, st);
+  if (rc) return rc;
+  const int rpp = t1 - t0;
+  kmpc::AView av;
+  av.A = z + (size_t)(row0 + t0) * ld_z; av.group_stride = (long long)T * ld_z; av.rows_per_group = rpp; av.lda = ld_z;
+  av.K = m->d * ld_z; av.window = true;
+  return kmpc::run_chain(h, m, av, B * rpp, H, 1, m->N, std32, mean32, stats_per_path ? rpp : 0, yhat, st);
+}
+
+int kmpc_encode(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, float* latent, void* stream) {
+  if (!h || !m || !obs || !latent || M <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_encode: bad argument");
+  FCK(cudaSetDevice(h->device));
+  kmpc::AView av; av.A = obs; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
+  return kmpc::run_chain(h, m, av, M, 0, 0, 0, nullptr, nullptr, 0, latent, (cudaStream_t)stream);
+}
+
+int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, int H, int obs_cols, float* pred, void* stream) {
+  if (!h || !m || !obs || !pred || M <= 0 || H <= 0 || obs_cols <= 0 || obs_cols > m->obs)
+    return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_rollout: bad argument");
+  FCK(cudaSetDevice(h->device));
+  kmpc::AView av; av.A = obs; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
+  return kmpc::run_chain(h, m, av, M, H, 2, obs_cols, nullptr, nullptr, 0, pred, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -17,6 +17,7 @@ struct GemmArgs {
   long long a_group_stride;
   int a_rows_per_group;
   int lda;
+  int row0;            // logical index of row 0 of this launch (chunked launches over a grouped view)
   const float* W;      // [Nout, K], row stride ldw
   int ldw;
   int M, Nout, K;

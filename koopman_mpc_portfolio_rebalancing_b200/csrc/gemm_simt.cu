@@ -8,6 +8,7 @@ namespace kmpc {
 constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8, NT = 256;
 
 __device__ __forceinline__ const float* a_row_ptr(const GemmArgs& g, int m) {
+  m += g.row0;
   const int grp = m / g.a_rows_per_group;
   const int r = m - grp * g.a_rows_per_group;
   return g.A + (long long)grp * g.a_group_stride + (long long)r * g.lda;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * 4 + (i >> 2) * 64 + (i & 3);
     if (m >= g.M) continue;
-    const int sg = (g.std32 && g.stat_rows_per_group > 0) ? m / g.stat_rows_per_group : 0;
+    const int sg = (g.std32 && g.stat_rows_per_group > 0) ? (m + g.row0) / g.stat_rows_per_group : 0;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * 4 + (j >> 2) * 64 + (j & 3);
