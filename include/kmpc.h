@@ -139,6 +139,10 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
 
 /* model.encode on explicit embedded rows obs[M,obs] -> latent[M,Z]  (parity hook, model.py:765, 837) */
 int kmpc_encode(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, float* latent, void* stream);
+/* KoopmanMachine.step_latent (model.py:311-321, 787-797): out[M,Z] = norm(z[M,Z] @ kmat) */
+int kmpc_step_latent(kmpc_handle* h, const kmpc_model* m, const float* z, int M, float* out, void* stream);
+/* KoopmanMachine.decode (model.py:768-777, 839-850): out[M,obs] */
+int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, float* out, void* stream);
 /* rollout on explicit embedded rows: pred[M,H,obs_cols] standardised decoder output, first obs_cols columns */
 int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, int H, int obs_cols, float* pred,
                  void* stream);

@@ -1,0 +1,10 @@
+"""koopman_mpc_portfolio_rebalancing_b200 — B200-native implementation of the Koopman-forecast + MPC rebalancing
+hot path of yli421/koopman-mpc-portfolio-rebalancing.
+
+Modules mirror the reference's for this path: ``mpc`` (MPCConfig, solve_mpc_log_utility), ``backtest``
+(BacktestConfig, Strategy, KoopmanMPCStrategy, run_backtest, calculate_metrics), ``model`` (GenericKM / SparseKM /
+LISTAKM forward path), ``data_finance`` (embedding, splits, FinanceDataset, FinanceEnv), plus ``engine`` (the
+batch-resident data-parallel form).  All compute goes through libkmpc.so (include/kmpc.h); nothing here imports
+``oracle/`` and there is no CPU fallback.
+"""
+__all__ = ["mpc", "backtest", "model", "data_finance", "engine", "synthetic"]

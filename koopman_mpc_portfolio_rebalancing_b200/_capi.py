@@ -64,6 +64,8 @@ SIGNATURES = {
     "kmpc_forecast": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, vp, vp]),
     "kmpc_encode": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "kmpc_step_latent": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "kmpc_decode": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "kmpc_rollout": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kmpc_mpc_solve": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                  vp, vp, vp, vp, vp, vp]),

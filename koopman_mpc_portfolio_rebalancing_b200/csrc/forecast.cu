@@ -381,4 +381,56 @@ int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, i
   return kmpc::run_chain(h, m, av, M, H, 2, obs_cols, nullptr, nullptr, 0, pred, (cudaStream_t)stream);
 }
 
+// KoopmanMachine.step_latent (model.py:311-321, 787-797): out = norm(z @ kmat)
+int kmpc_step_latent(kmpc_handle* h, const kmpc_model* m, const float* z, int M, float* out, void* stream) {
+  if (!h || !m || !z || !out || M <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_step_latent: bad argument");
+  FCK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  kmpc::GemmArgs g = kmpc::base_args();
+  g.A = z; g.a_rows_per_group = M; g.lda = m->Z; g.K = m->Z; g.W = m->kmatT; g.ldw = m->Z;
+  g.M = M; g.Nout = m->Z; g.n_store = m->Z; g.C = out; g.ldc = m->Z;
+  int rc = kmpc::launch_gemm(g, st, &h->launches);
+  if (rc) return rc;
+  if (m->kind == KMPC_MODEL_GENERIC && m->norm_fn == KMPC_NORM_BALL) {
+    kmpc::row_normalize_kernel<<<(M + 7) / 8, 256, 0, st>>>(out, M, m->Z); h->launches++;
+  }
+  return KMPC_OK;
+}
+
+// KoopmanMachine.decode (model.py:768-777, 839-850): out [M, obs]
+int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, float* out, void* stream) {
+  if (!h || !m || !z || !out || M <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_decode: bad argument");
+  FCK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (m->kind == KMPC_MODEL_LISTA) {
+    kmpc::GemmArgs d = kmpc::base_args();
+    d.A = z; d.a_rows_per_group = M; d.lda = m->Z; d.K = m->Z; d.W = m->lista_wdT; d.ldw = m->Z;
+    d.M = M; d.Nout = m->obs; d.n_store = m->obs; d.C = out; d.ldc = m->obs;
+    return kmpc::launch_gemm(d, st, &h->launches);
+  }
+  int maxw = 0;
+  for (int v : m->dec_dims) if (v > maxw) maxw = v;
+  const size_t need = (size_t)2 * M * maxw * sizeof(float);
+  if (m->n_dec > 1 && h->scratch_bytes < need) {
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr; h->scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&h->scratch, need);
+    if (e != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(decode scratch)");
+    h->scratch_bytes = need;
+  }
+  const float* xx = z; int xl = m->Z;
+  for (int li = 0; li < m->n_dec; ++li) {
+    kmpc::GemmArgs d = kmpc::base_args();
+    const bool last = (li == m->n_dec - 1);
+    d.A = xx; d.a_rows_per_group = M; d.lda = xl; d.K = m->dec_dims[li]; d.W = m->dec_w[li]; d.ldw = m->dec_dims[li];
+    d.M = M; d.bias = m->dec_b[li]; d.Nout = m->dec_dims[li + 1]; d.n_store = d.Nout;
+    d.act = last ? kmpc::EPI_NONE : kmpc::act_to_epi(m->dec_act);
+    d.C = last ? out : (float*)h->scratch + (size_t)(li & 1) * M * maxw; d.ldc = d.Nout;
+    if ((rc = kmpc::launch_gemm(d, st, &h->launches))) return rc;
+    xx = d.C; xl = d.Nout;
+  }
+  return KMPC_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,124 @@
+"""Batch-resident hot path: for many independent backtests at once
+    standardise -> (virtual) delay embedding -> Koopman forecast of every step -> persistent MPC/portfolio loop -> metrics.
+
+This is the data-parallel form of run_experiment.py:124-125 / README.md:45-68 (``KoopmanMPCStrategy`` +
+``run_backtest`` + ``calculate_metrics``) for scenario paths, lambda/tau sweeps and Monte-Carlo stress tests.
+Independent backtests shard across ranks with no communication; ``gather_metrics`` is the single collective.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from .backtest import BacktestConfig, run_backtest_batched
+from .data_finance import pad4, standardize_device
+from .mpc import MPCConfig
+
+
+@dataclass
+class PathBatch:
+    """Inputs of a batch of scenario backtests: log-returns of the window [first lag day .. last test day]."""
+    log_returns: "object"       # [B, T, N] float64, torch tensor (CUDA, or pinned host) or numpy
+    mean: "object"              # [B, N] or [N] float64: training-split statistics (data_finance.py:211-240)
+    std: "object"
+    row0: int = 0               # embedded-row index of the first test row inside the window
+    rows: int = 252             # rows of the test split
+
+
+class BatchedBacktester:
+    def __init__(self, model, n_assets: int, delay: int, mpc_config: Optional[MPCConfig] = None,
+                 bt_config: Optional[BacktestConfig] = None, sequence_length: int = 1, device="cuda"):
+        import torch
+        self.model = model
+        self.N, self.d = int(n_assets), int(delay)
+        self.mpc = mpc_config or MPCConfig()
+        self.bt = bt_config or BacktestConfig()
+        self.seq_len = sequence_length
+        self.device = torch.device(device)
+        self._buf = {}
+
+    def _tensor(self, name, shape, dtype):
+        import torch
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    def n_steps(self, rows: int) -> int:
+        return (rows - self.seq_len) - self.bt.horizon          # backtest.py:150, data_finance.py:389
+
+    def run_device(self, log_returns, mean, std, row0: int, rows: int, lam=None, tau=None, want_history=False,
+                   timings: Optional[dict] = None):
+        """All inputs already on the device.  Returns dict(metrics [B,5], history, stats, yhat)."""
+        import torch
+        B, T, N = log_returns.shape
+        H = self.mpc.horizon
+        ns = self.n_steps(rows)
+        ev = None
+        if timings is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+        z = self._tensor("z", (B, T, pad4(N)), torch.float32)
+        h = _capi.Handle.get(self.device.index or 0)
+        per_path = int(mean.dim() == 2)
+        sp = _capi.stream_ptr(self.device.index or 0)
+        _capi.check(_capi.lib().kmpc_standardize(h.ptr, _capi.ptr(log_returns), _capi.ptr(mean), _capi.ptr(std), per_path,
+                                                B, T, N, _capi.ptr(z), z.shape[2], sp))
+        realized = self._tensor("realized", (B, rows, N), torch.float32)
+        _capi.check(_capi.lib().kmpc_current_returns(h.ptr, _capi.ptr(z), z.shape[2], _capi.ptr(mean), _capi.ptr(std),
+                                                    per_path, B, T, N, self.d, row0, rows, _capi.ptr(realized), sp))
+        if ev: ev[1].record()
+        yhat = self._tensor("yhat", (B, ns, H, N), torch.float32)
+        self.model.forecast_series(z, mean, std, N, self.d, row0, 0, ns, H, out=yhat)
+        if ev: ev[2].record()
+        metrics = self._tensor("metrics", (B, 5), torch.float64)
+        out = run_backtest_batched(yhat, realized, n_steps=ns, horizon=H, lam=lam, tau=tau, lam0=self.mpc.cost_coeff,
+                                   tau0=self.mpc.max_turnover, cost_coeff0=self.bt.cost_coeff,
+                                   capital0=self.bt.initial_capital, rebalance_freq=self.bt.rebalance_freq,
+                                   allow_short=self.mpc.allow_short, want_history=want_history, out_metrics=metrics)
+        if ev:
+            ev[3].record()
+            timings["_events"] = ev
+        out["yhat"] = yhat
+        out["realized"] = realized
+        return out
+
+    def run(self, batch: PathBatch, lam=None, tau=None, want_history=False):
+        """Host or device inputs -> metrics as a numpy array [B,5] (one H2D of the inputs, one D2H of the result)."""
+        import torch
+        lr = torch.as_tensor(batch.log_returns)
+        lr_d = lr.to(self.device, dtype=torch.float64, non_blocking=True)
+        mean = torch.as_tensor(batch.mean).to(self.device, dtype=torch.float64, non_blocking=True)
+        std = torch.as_tensor(batch.std).to(self.device, dtype=torch.float64, non_blocking=True)
+        out = self.run_device(lr_d.contiguous(), mean.contiguous(), std.contiguous(), batch.row0, batch.rows, lam, tau,
+                              want_history)
+        res = {"metrics": out["metrics"].cpu().numpy(), "stats": out["stats"].cpu().numpy() if out["stats"] is not None else None}
+        if want_history:
+            res["history"] = out["history"].cpu().numpy()
+        return res
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of n independent backtests for one rank."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def gather_metrics(local_metrics, n_total: int, rank: int, world: int):
+    """The only collective of the path: all ranks' [B_local,5] metric rows -> [n_total,5] on every rank
+    (torch.distributed all_gather over NCCL on GPUs, gloo on CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local_metrics
+    per = (n_total + world - 1) // world
+    pad = torch.zeros((per, local_metrics.shape[1]), dtype=local_metrics.dtype, device=local_metrics.device)
+    pad[:local_metrics.shape[0]] = local_metrics
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    return torch.cat(bufs, dim=0)[:n_total]

@@ -1,0 +1,87 @@
+"""The drop-in boundary on CPU: the C-ABI library loads and exports every symbol include/kmpc.h declares, the
+product never routes through oracle/, and it fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "koopman_mpc_portfolio_rebalancing_b200")
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "kmpc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kmpc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    assert os.path.exists(_capi.LIB_PATH), "run `python -m koopman_mpc_portfolio_rebalancing_b200.build` first"
+    L = ctypes.CDLL(_capi.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/kmpc.h but not exported"
+    assert set(names) == set(_capi.SIGNATURES), set(names) ^ set(_capi.SIGNATURES)
+    assert _capi.lib().kmpc_version() == 100
+
+
+def test_embed_index_host_matches_oracle_and_rejects_short_series():
+    import numpy as np
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, data_finance
+    from oracle import data_oracle
+    idx = data_finance.embedding_index(12, 3, 4)
+    assert idx.dtype == np.int32 and np.array_equal(idx, data_oracle.embedding_index(12, 3, 4))
+    with pytest.raises(ValueError):
+        data_finance.embedding_index(3, 2, 5)
+    buf = np.zeros(4, np.int32)
+    assert _capi.lib().kmpc_embed_index_host(3, 2, 5, _capi.ptr(buf)) == -1
+    assert b"embedding_dim" in _capi.lib().kmpc_last_error()
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle\b", txt, flags=re.M), fn
+                assert not re.search(r"import_module\(.*oracle|CDLL\(.*oracle|#include\s+\".*oracle", txt), fn
+
+
+def test_variant_table():
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    L = _capi.lib()
+    assert L.kmpc_mpc_supported(5, 50) == 1 and L.kmpc_mpc_supported(5, 10) == 1 and L.kmpc_mpc_supported(3, 64) == 1
+    assert L.kmpc_mpc_supported(5, 5000) == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, mpc
+    with pytest.raises(_capi.KmpcError):
+        mpc.solve_mpc_log_utility(np.ones(3) / 3, np.zeros((2, 3), np.float32), mpc.MPCConfig(horizon=2))
+
+
+def test_split_rows_and_stats_host_logic(golden):
+    import numpy as np
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df
+    g = golden("data_small.npz")
+    st = df.compute_standardization_stats(g["log_returns"], n_train_rows=int(g["n_train_days"]))
+    assert np.array_equal(st.mean, g["mean"]) and np.array_equal(st.std, g["std"])
+    (a0, a1), (b0, b1), (c0, c1) = df.split_rows(g["log_returns"].shape[0], int(g["n_train_days"]), int(g["n_val_days"]), int(g["d"]))
+    assert (a1 - a0, b1 - b0, c1 - c0) == (g["train"].shape[0], g["val"].shape[0], g["test"].shape[0])
+
+
+def test_shard_range_covers_everything():
+    from koopman_mpc_portfolio_rebalancing_b200.engine import shard_range
+    for n, w in [(10, 1), (10, 3), (4096, 8), (5, 8), (65536, 4)]:
+        seen = []
+        for r in range(w):
+            lo, hi = shard_range(n, r, w)
+            seen += list(range(lo, hi))
+        assert seen == list(range(n))

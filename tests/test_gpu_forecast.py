@@ -1,0 +1,124 @@
+"""CUDA forecast path vs golden vectors of /root/reference/model.py (torch CPU fp32) and the numpy oracle.
+Bar: 1e-5 relative, measured norm-wise per row (||dy||_inf / ||y||_inf) because standardised returns cross zero."""
+import numpy as np
+import pytest
+
+from conftest import sd_from_npz
+
+pytestmark = pytest.mark.gpu
+FORECAST_RTOL = 1e-5
+
+
+def rowwise_rel(a, b):
+    a = a.reshape(a.shape[0], -1); b = b.reshape(b.shape[0], -1)
+    return float(np.max(np.abs(a - b).max(axis=1) / np.abs(b).max(axis=1)))
+
+
+def build(name, g, meta=None):
+    from koopman_mpc_portfolio_rebalancing_b200 import model as km
+    obs = g["obs"].shape[1]
+    if name == "generic_small" or name == "cfg1":
+        h = [16, 16] if name == "generic_small" else [1024, 1024]
+        Z = 8 if name == "generic_small" else 128
+        cfg = km.model_config("GenericKM", Z, h, enc_bias=True)
+    elif name == "generic_tanh_ball":
+        cfg = km.model_config("GenericKM", 8, [16], enc_act="tanh", norm_fn="ball")
+    elif name == "generic_gelu_mlpdec":
+        cfg = km.model_config("SparseKM", 8, [16, 12], dec_layers=[10], enc_bias=True, dec_bias=True, enc_act="gelu", last_relu=True)
+    elif name == "lista_linear":
+        cfg = km.model_config("LISTAKM", 16, lista_loops=int(meta["loops"]), lista_L=float(meta["L"]), lista_alpha=float(meta["alpha"]), lista_linear=True)
+    elif name == "lista_mlp":
+        cfg = km.model_config("LISTAKM", 16, [12, 12], enc_bias=True, last_relu=True, lista_loops=int(meta["loops"]),
+                              lista_L=float(meta["L"]), lista_alpha=float(meta["alpha"]), lista_linear=False)
+    return km.make_model(cfg, obs)
+
+
+def check_model(m, g):
+    import torch
+    N, d, H = int(g["N"]), int(g["d"]), int(g["H"])
+    obs = torch.from_numpy(g["obs"]).cuda()
+    z0 = m.encode(obs)
+    assert rowwise_rel(z0.cpu().numpy(), g["z0"]) < FORECAST_RTOL
+    # step-by-step API (encode / step_latent / decode), the loop of backtest.py:99-121
+    z = z0
+    std32 = torch.from_numpy(g["std"]).float().cuda(); mean32 = torch.from_numpy(g["mean"]).float().cuda()
+    ys = []
+    for _ in range(H):
+        z = m.step_latent(z)
+        ys.append(m.decode(z)[..., :N] * std32 + mean32)
+    y_steps = torch.stack(ys, dim=1).cpu().numpy()
+    assert rowwise_rel(y_steps, g["yhat"]) < FORECAST_RTOL
+    # fused rollout
+    pred = m.rollout(obs, H, n_cols=N)            # [H, M, N] standardised
+    y_roll = (pred.permute(1, 0, 2) * std32 + mean32).cpu().numpy()
+    assert rowwise_rel(y_roll, g["yhat"]) < FORECAST_RTOL
+    return y_steps
+
+
+@pytest.mark.parametrize("name", ["generic_small", "generic_tanh_ball", "generic_gelu_mlpdec"])
+def test_generic_vs_reference(golden, name):
+    g = golden(f"forecast_{name}.npz")
+    m = build(name, g)
+    m.load_state_dict(sd_from_npz(g))
+    check_model(m, g)
+
+
+@pytest.mark.parametrize("name", ["lista_linear", "lista_mlp"])
+def test_lista_vs_reference(golden, name):
+    g = golden(f"forecast_{name}.npz")
+    m = build(name, g, golden(f"forecast_{name}_meta.npz"))
+    m.load_state_dict(sd_from_npz(g))
+    check_model(m, g)
+
+
+def test_cfg1_vs_reference_and_strict_keys(golden):
+    from koopman_mpc_portfolio_rebalancing_b200 import synthetic
+    g = golden("forecast_cfg1.npz")
+    m = build("cfg1", g)
+    sd = synthetic.generic_km_weights(0, 200, [1024, 1024], 128)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({**sd, "bogus": np.zeros(1, np.float32)})
+    m.load_state_dict(sd)
+    check_model(m, g)
+
+
+def test_window_forecast_equals_explicit_embedding(golden):
+    """forecast_series reads the delay window in place (permuted first-layer weights): must equal the forecast of
+    the materialised embedding, for per-path statistics and a ragged N (padding columns)."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df, model as km, synthetic
+    from oracle import forecast_oracle as fo, data_oracle as do
+    rng = np.random.default_rng(8)
+    B, T, N, d, H, Z = 3, 40, 10, 6, 4, 32
+    lr = rng.standard_normal((B, T, N)) * 0.012
+    mean = rng.normal(3e-4, 1e-4, (B, N)); std = rng.uniform(0.008, 0.02, (B, N))
+    sd = synthetic.generic_km_weights(5, N * d, [48, 40], Z)
+    m = km.make_model(km.model_config("GenericKM", Z, [48, 40], enc_bias=True), N * d)
+    m.load_state_dict(sd)
+    z = df.standardize_device(lr, mean, std)
+    row0, t0, t1 = 3, 2, 30
+    y = m.forecast_series(z, torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda(), N, d, row0, t0, t1, H).cpu().numpy()
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    for b in range(B):
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)[row0 + t0: row0 + t1]
+        want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
+        assert rowwise_rel(y[b], want) < FORECAST_RTOL, b
+
+
+def test_lista_window_forecast_large_latent():
+    """LISTAKM at a non-trivial size (Z=256, obs=120): window path vs oracle."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df, model as km, synthetic
+    from oracle import forecast_oracle as fo, data_oracle as do
+    rng = np.random.default_rng(2)
+    T, N, d, H, Z = 60, 12, 10, 5, 256
+    lr = rng.standard_normal((T, N)) * 0.012
+    mean = rng.normal(3e-4, 1e-4, N); std = rng.uniform(0.008, 0.02, N)
+    sd, L = synthetic.lista_km_weights(3, N * d, Z)
+    m = km.make_model(km.model_config("LISTAKM", Z, lista_loops=10, lista_L=L, lista_alpha=5e-3, lista_linear=True), N * d)
+    m.load_state_dict(sd)
+    z = df.standardize_device(lr, mean, std).unsqueeze(0)
+    y = m.forecast_series(z, torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda(), N, d, 0, 0, T - d + 1, H)[0].cpu().numpy()
+    spec = fo.ModelSpec(kind="lista", linear_encoder=True, alpha=5e-3, L=L, loops=10, act="relu", last_relu=False)
+    want = fo.forecast(do.time_delay_embedding(do.standardize(lr, mean, std), d), sd, spec, H, N, mean, std)
+    assert rowwise_rel(y, want) < FORECAST_RTOL

@@ -1,0 +1,71 @@
+"""End-to-end through the reference-shaped API: KoopmanMPCStrategy + run_backtest + calculate_metrics on config 1
+vs the golden run of the unmodified reference; the batched engine vs per-path oracle runs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def cfg1(golden):
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df, model as km, synthetic
+    g = golden("backtest_cfg1.npz")
+    lr = synthetic.gbm_log_returns(int(g["log_returns_seed"]), int(g["T"]), 10)
+    env = df.create_finance_env_from_returns(lr, embedding_dim=20, n_train_days=int(g["n_train_days"]),
+                                             n_val_days=int(g["n_val_days"]))
+    m = km.make_model(km.model_config("GenericKM", 128, [1024, 1024], enc_bias=True), 200)
+    m.load_state_dict(synthetic.generic_km_weights(0, 200, [1024, 1024], 128))
+    return g, env, m
+
+
+def test_config1_drop_in_run_backtest(golden):
+    """README.md:45-68 call pattern.  Forecasts match the reference's to 1e-5; the LP-like MPC can amplify a 1e-6
+    forecast difference into a different vertex on near-ties, so history/metrics get the looser bar documented in
+    tests/test_oracle_backtest.py::test_full_oracle_path_reproduces_reference_backtest."""
+    from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt
+    g, env, m = cfg1(golden)
+    assert np.array_equal(env.test_dataset.data[:3].cpu().numpy(), g["test_first_rows"])
+    strat = bt.KoopmanMPCStrategy(m, bt.MPCConfig(horizon=5, cost_coeff=1e-3, max_turnover=0.2))
+    yhat = strat.forecast(env, 0, 246).cpu().numpy()
+    rel = np.abs(yhat - g["yhat"]).reshape(246, -1).max(1) / np.abs(g["yhat"]).reshape(246, -1).max(1)
+    assert rel.max() < 1e-5, rel.max()
+    df_ = bt.run_backtest(strat, env, bt.BacktestConfig(initial_capital=1e4, horizon=5, cost_coeff=1e-3), verbose=False)
+    assert list(df_.columns) == ["date", "portfolio_value", "return", "turnover", "cost"] and len(df_) == 246
+    met = bt.calculate_metrics(df_)
+    assert np.allclose([met[k] for k in bt.METRIC_KEYS], g["metrics"], rtol=2e-4, atol=2e-4)
+    assert np.allclose(df_["portfolio_value"].values, g["history"][:, 0], rtol=1e-4)
+    assert df_.attrs["solve_stats"][2] == 0          # no fallback decisions
+    # single-step drop-in: Strategy.rebalance(t, w, env) (backtest.py:80-131)
+    w = strat.rebalance(0, np.ones(10) / 10, env)
+    assert np.abs(w - g["w_opt"][0, 0]).max() < 1e-4
+    # Buy & Hold through the generic host loop
+    bh = bt.run_backtest(bt.BuyAndHoldStrategy(), env, bt.BacktestConfig(initial_capital=1e4, horizon=5, cost_coeff=1e-3), verbose=False)
+    assert np.allclose(bh["portfolio_value"].values, g["bh_history"][:, 0], rtol=1e-6)
+
+
+def test_batched_engine_vs_oracle_paths():
+    """scenario batch (config-2 shape, tiny): every path equals its own oracle backtest"""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import engine, model as km, synthetic, backtest as bt
+    from oracle import backtest_oracle as bo, data_oracle as do, forecast_oracle as fo
+    B, N, d, H, rows, Z = 5, 16, 8, 5, 40, 64
+    T = rows + d - 1
+    lr = synthetic.gbm_log_returns_batch(100, B, T, N)
+    mean = lr.mean(axis=1); std = lr.std(axis=1, ddof=1)
+    sd = synthetic.generic_km_weights(1, N * d, [96, 96], Z)
+    m = km.make_model(km.model_config("GenericKM", Z, [96, 96], enc_bias=True), N * d)
+    m.load_state_dict(sd)
+    eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H), bt.BacktestConfig(horizon=H))
+    res = eng.run(engine.PathBatch(lr, mean, std, 0, rows), want_history=True)
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    ns = rows - 1 - H
+    worst = 0.0
+    for b in range(B):
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)
+        yhat = fo.forecast(emb[:ns], sd, spec, H, N, mean[b], std[b])
+        allr = do.destandardize(do.extract_current_returns(emb, N), mean[b], std[b])
+        rh, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat, 1e-3, 0.2), allr, rows - 1, H)
+        worst = max(worst, np.abs(res["history"][b][:, 0] / rh[:, 0] - 1).max())
+        mo_ = bo.calculate_metrics(rh)
+        assert np.allclose(res["metrics"][b], [mo_[k] for k in bo.METRIC_KEYS], rtol=5e-4, atol=5e-4), b
+    assert worst < 2e-4, worst
+    assert res["stats"][:, 2].sum() == 0
