@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — MPC rebalance decisions/sec of the batch-resident hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # host-CPU reference arm (oracle port, all cores)
+
+One *step* = one whole pass of the hot path over one batch of synthetic scenario backtests:
+standardise -> (in-place) delay embedding -> Koopman forecast of every rebalancing step -> persistent MPC +
+portfolio loop -> metrics [B,5] (+ the NCCL metric gather when N > 1).  Workload at any N: BASELINE config 2 per
+GPU (GenericKM finance_sparse architecture 1000->1024->1024->1024, 50 assets, d=20, H=5, 4096 backtests x 246
+decisions), i.e. weak scaling: independent backtests shard across ranks with no data-path collective.
+
+`value`  : decisions/s with the inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same through the public API with HOST (pinned) inputs: H2D of the log-returns and statistics and
+           D2H of the metrics inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MPC rebalance decisions/sec"
+UNIT = "decisions/s"
+
+WORKLOADS = {
+    # name: (n_assets, delay, horizon, enc_layers, latent, backtests per GPU, test rows)
+    "cfg2": dict(N=50, d=20, H=5, enc=[1024, 1024], Z=1024, B=4096, rows=252,
+                 desc="cfg2: GenericKM (finance_sparse arch 1000->1024->1024->1024, linear decoder), 50 assets, d=20, "
+                      "H=5, lambda=1e-3, tau=0.2, 4096 synthetic-GBM scenario backtests x 246 decisions per GPU"),
+    "cfg1": dict(N=10, d=20, H=5, enc=[1024, 1024], Z=128, B=1, rows=252,
+                 desc="cfg1: finance_sparse SparseKM target_size=128, 10 assets, single backtest x 246 decisions"),
+    "tiny": dict(N=10, d=6, H=5, enc=[64, 64], Z=32, B=64, rows=40, desc="tiny smoke workload"),
+}
+
+
+def flops_per_decision(w):
+    dims = [w["N"] * w["d"]] + w["enc"] + [w["Z"]]
+    f_enc = 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    return f_enc + w["H"] * 2 * w["Z"] * w["Z"] + w["H"] * 2 * w["Z"] * w["N"]
+
+
+def make_inputs(w, B, seed):
+    from koopman_mpc_portfolio_rebalancing_b200 import synthetic
+    T = w["rows"] + w["d"] - 1
+    lr = synthetic.gbm_log_returns_batch(seed, B, T, w["N"])
+    # training-split statistics of each scenario (here: of the generated window; any fixed [B,N] stats would do)
+    mean = lr.mean(axis=1)
+    std = np.maximum(lr.std(axis=1, ddof=1), 1e-8)
+    return np.ascontiguousarray(lr, dtype=np.float64), mean, std, T
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host-CPU baseline: the oracle port (forecast in numpy fp32, structured fp64 IPM, reference loop arithmetic)
+# ------------------------------------------------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    (wname, seed, n_dec) = args
+    import numpy as np
+    from oracle import backtest_oracle as bo, data_oracle as do, forecast_oracle as fo
+    from koopman_mpc_portfolio_rebalancing_b200 import synthetic
+    w = WORKLOADS[wname]
+    sd = _cpu_weights(wname)
+    lr, mean, std, T = make_inputs(w, 1, seed)
+    t0 = time.perf_counter()
+    z = do.standardize(lr[0], mean[0], std[0])
+    emb = do.time_delay_embedding(z, w["d"])
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    yhat = fo.forecast(emb[:n_dec], sd, spec, w["H"], w["N"], mean[0], std[0])
+    allr = do.destandardize(do.extract_current_returns(emb, w["N"]), mean[0], std[0])
+    hist, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat, 1e-3, 0.2), allr, n_dec + w["H"], w["H"])
+    assert len(hist) == n_dec
+    return time.perf_counter() - t0
+
+
+_W_CACHE = {}
+
+
+def _cpu_weights(wname):
+    if wname not in _W_CACHE:
+        from koopman_mpc_portfolio_rebalancing_b200 import synthetic
+        w = WORKLOADS[wname]
+        _W_CACHE[wname] = synthetic.generic_km_weights(0, w["N"] * w["d"], w["enc"], w["Z"])
+    return _W_CACHE[wname]
+
+
+def cpu_baseline_single(wname, n_dec):
+    """single process, oracle port, one scenario x n_dec decisions"""
+    dt = _cpu_worker((wname, 12345, n_dec))
+    return n_dec / dt, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path (the oracle port: cvxpy/SCS cannot be installed offline, so the
+    solver is the fp64 structured IPM; forecast and loop arithmetic are the reference's) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    wname = args.workload
+    w = WORKLOADS[wname]
+    cores = os.cpu_count() or 1
+    n_dec = min(args.cpu_decisions, w["rows"] - 1 - w["H"])
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    _cpu_weights(wname)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_worker, [(wname, 1000 + i, max(2, n_dec // 4)) for i in range(cores)])
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_cpu_worker, [(wname, 2000 + s * cores + i, n_dec) for i in range(cores)])
+        dt = time.perf_counter() - t0
+    decisions = args.steps * cores * n_dec
+    val = decisions / dt
+    sample = f"{cores} processes x 1 scenario x {n_dec} decisions per step (of 246), oracle port: numpy fp32 forecast + fp64 structured IPM"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 forecast + f64 solver", "data": "synthetic",
+            "config": {"workload": w["desc"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, backtest as bt, engine, model as km, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    B = args.paths or w["B"]
+    N, d, H, Z = w["N"], w["d"], w["H"], w["Z"]
+    rows = w["rows"]
+    ns = rows - 1 - H
+    decisions_per_step_rank = B * ns
+
+    model = km.make_model(km.model_config("GenericKM", Z, w["enc"], enc_bias=True), N * d, device=dev)
+    model.load_state_dict(synthetic.generic_km_weights(0, N * d, w["enc"], Z))
+    eng = engine.BatchedBacktester(model, N, d, bt.MPCConfig(horizon=H, cost_coeff=1e-3, max_turnover=0.2),
+                                   bt.BacktestConfig(initial_capital=1e4, horizon=H, cost_coeff=1e-3), device=dev)
+    lr, mean, std, T = make_inputs(w, B, 10_000 * (rank + 1))
+    lr_h = torch.from_numpy(lr).pin_memory(); mean_h = torch.from_numpy(mean).pin_memory(); std_h = torch.from_numpy(std).pin_memory()
+    lr_d, mean_d, std_d = lr_h.to(dev), mean_h.to(dev), std_h.to(dev)
+    handle = _capi.Handle.get(local)
+    B_total = B * world
+
+    def step_device(timings=None):
+        out = eng.run_device(lr_d, mean_d, std_d, 0, rows, timings=timings)
+        m = out["metrics"]
+        if world > 1:
+            m = engine.gather_metrics(m, B_total, rank, world)
+        return out, m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = handle.launches
+    stage_ev = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        tm = {}
+        out, m_all = step_device(tm)
+        stage_ev.append(tm["_events"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = handle.launches - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * decisions_per_step_rank * args.steps / (ms * 1e-3)
+    st_data = np.mean([e[0].elapsed_time(e[1]) for e in stage_ev])
+    st_fc = np.mean([e[1].elapsed_time(e[2]) for e in stage_ev])
+    st_bt = np.mean([e[2].elapsed_time(e[3]) for e in stage_ev])
+    stats = out["stats"].cpu().numpy()
+    metrics_host = m_all.cpu().numpy()
+
+    # ---- e2e: host buffers in, host metrics out, through the public API ----
+    def step_e2e():
+        res = eng.run(engine.PathBatch(lr_h, mean_h, std_h, 0, rows))
+        return res["metrics"]
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mh = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * decisions_per_step_rank * args.steps / float(t.item())
+    h2d = lr_h.numel() * 8 + mean_h.numel() * 8 + std_h.numel() * 8
+    d2h = B * 5 * 8 + B * 4 * 8
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured" if peaks else "fallback"
+        fpd = flops_per_decision(w)
+        fc_tflops = fpd * decisions_per_step_rank / (st_fc * 1e-3) / 1e12
+        # fp32-accurate tensor rate = TF32 dense / 3 (3xTF32 split), TF32 dense taken as bf16 / 2
+        tensor_peak = bf16 / 2.0 / 3.0
+        hbm_bytes_bt = (8 * N + 8 * H * N + 32) * decisions_per_step_rank
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        dominant = "backtest_kernel" if st_bt >= st_fc else "forecast_gemm_chain"
+        roof_fc = {"kernel": "forecast GEMM chain (encoder + K-unroll + decoder)", "bound": "tensor", "achieved": fc_tflops,
+                   "peak": tensor_peak, "unit": "TFLOP/s", "frac": fc_tflops / tensor_peak, "traffic": None,
+                   "peak_source": f"{peak_src} bf16 sustained / 2 (TF32) / 3 (3xTF32 split for fp32 accuracy)",
+                   "flops_per_decision": fpd, "ms": st_fc}
+        bt_gbs = hbm_bytes_bt / (st_bt * 1e-3) / 1e9
+        roof_bt = {"kernel": "backtest_kernel (warp-per-backtest fp64 IPM + portfolio step)", "bound": "hbm", "achieved": bt_gbs,
+                   "peak": hbm_peak, "unit": "GB/s", "frac": bt_gbs / hbm_peak, "traffic": None,
+                   "note": "algorithmic HBM traffic is 2432 B/decision: the solver is SM-issue/latency bound, not HBM bound; "
+                           "see solver.iterations_per_decision and profiles/ for issue-slot utilisation",
+                   "ms": st_bt}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_dec = min(args.cpu_decisions, ns)
+            v, dt = cpu_baseline_single(args.workload, n_dec)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"1 scenario x {n_dec} decisions of the same workload (oracle port: numpy fp32 forecast with "
+                             f"{os.cpu_count()} BLAS threads available, scalar fp64 structured IPM), {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 forecast + f64 solver", "data": "synthetic",
+            "config": {"workload": w["desc"], "backtests_per_gpu": B, "decisions_per_step": world * decisions_per_step_rank,
+                       "l2": f"inputs larger than L2: {lr_d.numel() * 8 / 2**20:.0f} MiB of log-returns + "
+                             f"{B * ns * H * N * 4 / 2**20:.0f} MiB of forecasts per step vs 126 MiB L2"},
+            "roofline": roof_bt if dominant == "backtest_kernel" else roof_fc,
+            "roofline_other": roof_fc if dominant == "backtest_kernel" else roof_bt,
+            "stages_ms": {"standardize+returns": st_data, "forecast": st_fc, "mpc+portfolio": st_bt},
+            "solver": {"iterations_per_decision": float(stats[:, 3].sum() / max(1, B * ns)),
+                       "optimal": int(stats[:, 0].sum()), "inaccurate": int(stats[:, 1].sum()), "fallback": int(stats[:, 2].sum())},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "result_check": {"mean_final_value": float(np.mean(metrics_host[:, 3])), "mean_sharpe": float(np.mean(metrics_host[:, 0]))},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--paths", type=int, default=0, help="backtests per GPU (default: the workload's)")
+    ap.add_argument("--cpu-decisions", type=int, default=96, help="decisions in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
