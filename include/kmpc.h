@@ -147,6 +147,12 @@ int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, floa
 int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, int H, int obs_cols, float* pred,
                  void* stream);
 
+/* diagnostics: choose the GEMM kernel family process-wide (1 = tcgen05 3xTF32 where eligible [default],
+ * 0 = fp32 SIMT everywhere) and run one bare GEMM C[M,Nout] = A[M,K] . W[Nout,K]^T through a chosen kernel
+ * (mode 0 = SIMT, 1 = tcgen05; KMPC_E_CUDA with "not eligible" if the shape cannot use it). */
+int kmpc_set_gemm_mode(int use_tensor_cores);
+int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode);
+
 /* ---------------------------------------------------------------------------------------------
  * MPC — replaces mpc.solve_mpc_log_utility (mpc.py:27-117)
  * ------------------------------------------------------------------------------------------- */

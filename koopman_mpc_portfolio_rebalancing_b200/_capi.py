@@ -67,6 +67,8 @@ SIGNATURES = {
     "kmpc_step_latent": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "kmpc_decode": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "kmpc_rollout": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "kmpc_set_gemm_mode": (C.c_int, [C.c_int]),
+    "kmpc_debug_gemm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
     "kmpc_mpc_solve": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                  vp, vp, vp, vp, vp, vp]),
     "kmpc_mpc_solve_host": (C.c_int, [vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -14,23 +14,27 @@
 #include "gemm.cuh"
 
 int kmpc_fail_cuda(cudaError_t e, const char* what);
-namespace kmpc { int launch_gemm(const GemmArgs& g, cudaStream_t st, long long* launches); }
 
 struct kmpc_model {
   kmpc_handle* h;
   int kind, obs, N, d, Z, ld, norm_fn;
   int n_enc, enc_act, enc_last_relu;
   std::vector<int> enc_dims;
-  std::vector<float*> enc_w, enc_b;
+  std::vector<float*> enc_w, enc_b, enc_w_lo;
   float* enc_w0_win;           // first encoder / We layer re-laid for the in-place window read [h1, d*ld]
+  float* enc_w0_win_lo;
   int n_dec, dec_act;
   std::vector<int> dec_dims;
-  std::vector<float*> dec_w, dec_b;
+  std::vector<float*> dec_w, dec_b, dec_w_lo;
   float* kmatT;                // [Z,Z] = kmat^T  (GEMM computes A . W^T)
+  float* kmatT_lo;
   int lista_linear, lista_loops;
   float lista_thr;
   float* lista_ST;             // S^T
+  float* lista_ST_lo;
   float* lista_wdT;            // [obs, Z]: (dict / ||dict||_row.clamp(1e-4))^T
+  float* z_lo;                 // residual twin of the standardised series of the current forecast call
+  size_t z_lo_cap;
   std::vector<void*> owned;
 };
 
@@ -74,7 +78,9 @@ __global__ void dict_normalize_transpose_kernel(const float* __restrict__ dict, 
 }
 
 // z <- z / ||z||_2 per row (GenericKM 'ball' norm, model.py:751-752; no epsilon, like the reference)
-__global__ void row_normalize_kernel(float* __restrict__ z, int M, int Z) {
+__device__ __forceinline__ float lo_of(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+__global__ void row_normalize_kernel(float* __restrict__ z, float* __restrict__ zlo, int M, int Z) {
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -82,12 +88,19 @@ __global__ void row_normalize_kernel(float* __restrict__ z, int M, int Z) {
   for (int c = lane; c < Z; c += 32) { const float v = z[(size_t)m * Z + c]; s = fmaf(v, v, s); }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float nrm = sqrtf(s);
-  for (int c = lane; c < Z; c += 32) z[(size_t)m * Z + c] = z[(size_t)m * Z + c] / nrm;
+  for (int c = lane; c < Z; c += 32) {
+    const float v = z[(size_t)m * Z + c] / nrm;
+    z[(size_t)m * Z + c] = v;
+    if (zlo) zlo[(size_t)m * Z + c] = lo_of(v);
+  }
 }
 
-__global__ void shrink_kernel(const float* __restrict__ c, float* __restrict__ z, long long n, float thr) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    z[i] = epilogue_apply(c[i], EPI_SHRINK, thr);
+__global__ void shrink_kernel(const float* __restrict__ c, float* __restrict__ z, float* __restrict__ zlo, long long n, float thr) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = epilogue_apply(c[i], EPI_SHRINK, thr);
+    z[i] = v;
+    zlo[i] = lo_of(v);
+  }
 }
 
 __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
@@ -98,7 +111,7 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
 static int act_to_epi(int act) { return act == KMPC_ACT_RELU ? EPI_RELU : (act == KMPC_ACT_TANH ? EPI_TANH : EPI_GELU); }
 
 struct AView {            // how the rows of the first GEMM are addressed
-  const float* A; long long group_stride; int rows_per_group; int lda; int K; bool window;
+  const float* A; const float* A_lo; long long group_stride; int rows_per_group; int lda; int K; bool window;
 };
 
 static GemmArgs base_args() {
@@ -116,13 +129,17 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
   int maxw = Z;
   for (int v : m->enc_dims) if (v > maxw) maxw = v;
   for (int v : m->dec_dims) if (v > maxw) maxw = v;
-  // chunk rows so that the ping-pong activations (~4 buffers) stay inside the 126 MB L2
-  long long ch = (96ll << 20) / (4ll * 4 * maxw);
-  ch = (ch / 128) * 128;
-  if (ch < 128) ch = 128;
+  // Row chunks: 4 ping-pong activation buffers + their residual twins.  The chain is compute bound (activation
+  // traffic is ~16 KB per row and layer against ~2 MFLOP), so the chunk is sized for full waves of 128-row tiles,
+  // not for L2 residency; window views are chunked in whole paths so that tiles never straddle two paths.
+  long long ch = 32768;
+  if (av.window && av.rows_per_group < M) {
+    ch = (ch / av.rows_per_group) * av.rows_per_group;
+    if (ch < av.rows_per_group) ch = av.rows_per_group;
+  }
   if (ch > M) ch = M;
   const int CH = (int)ch;
-  const size_t need = (size_t)CH * maxw * 4 * sizeof(float) + 256;
+  const size_t need = (size_t)CH * maxw * 8 * sizeof(float) + 256;
   if (h->scratch_bytes < need) {
     if (h->scratch) cudaFree(h->scratch);
     h->scratch = nullptr; h->scratch_bytes = 0;
@@ -131,7 +148,15 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
     h->scratch_bytes = need;
   }
   float* buf[4];
-  for (int i = 0; i < 4; ++i) buf[i] = (float*)h->scratch + (size_t)i * CH * maxw;
+  float* lob[4];
+  for (int i = 0; i < 4; ++i) {
+    buf[i] = (float*)h->scratch + (size_t)i * CH * maxw;
+    lob[i] = (float*)h->scratch + (size_t)(4 + i) * CH * maxw;
+  }
+  auto lo_of_buf = [&](const float* p) -> float* {
+    for (int i = 0; i < 4; ++i) if (p == buf[i]) return lob[i];
+    return nullptr;
+  };
   int rc;
   for (int r0 = 0; r0 < M; r0 += CH) {
     const int rows = (M - r0 < CH) ? (M - r0) : CH;
@@ -145,45 +170,45 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
         GemmArgs g = base_args();
         const bool last = (li == m->n_enc - 1);
         if (li == 0) {
-          g.A = av.A; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda;
+          g.A = av.A; g.A_lo = av.A_lo; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda;
           g.row0 = r0; g.K = av.K;
-          g.W = av.window ? m->enc_w0_win : m->enc_w[0]; g.ldw = av.K;
+          g.W = av.window ? m->enc_w0_win : m->enc_w[0]; g.W_lo = av.window ? m->enc_w0_win_lo : m->enc_w_lo[0]; g.ldw = av.K;
         } else {
-          g.A = x; g.a_group_stride = 0; g.a_rows_per_group = rows; g.lda = xld; g.row0 = 0; g.K = m->enc_dims[li];
-          g.W = m->enc_w[li]; g.ldw = m->enc_dims[li];
+          g.A = x; g.A_lo = lo_of_buf(x); g.a_group_stride = 0; g.a_rows_per_group = rows; g.lda = xld; g.row0 = 0; g.K = m->enc_dims[li];
+          g.W = m->enc_w[li]; g.W_lo = m->enc_w_lo[li]; g.ldw = m->enc_dims[li];
         }
         g.M = rows; g.Nout = m->enc_dims[li + 1]; g.n_store = g.Nout;
         g.bias = m->enc_b[li];
         g.act = last ? (m->enc_last_relu ? EPI_RELU : EPI_NONE) : act_to_epi(m->enc_act);
         float* o = last ? ((m->kind == KMPC_MODEL_LISTA) ? cbuf : zcur) : buf[li & 1];
-        g.C = o; g.ldc = g.Nout;
+        g.C = o; g.C_lo = lo_of_buf(o); g.ldc = g.Nout;
         if ((rc = launch_gemm(g, st, &h->launches))) return rc;
         x = o; xld = g.Nout;
       }
     } else {   // LISTA linear encoder: c = x @ We^T
       GemmArgs g = base_args();
-      g.A = av.A; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda; g.row0 = r0;
-      g.K = av.K; g.W = av.window ? m->enc_w0_win : m->enc_w[0]; g.ldw = av.K;
+      g.A = av.A; g.A_lo = av.A_lo; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda; g.row0 = r0;
+      g.K = av.K; g.W = av.window ? m->enc_w0_win : m->enc_w[0]; g.W_lo = av.window ? m->enc_w0_win_lo : m->enc_w_lo[0]; g.ldw = av.K;
       g.M = rows; g.Nout = Z; g.n_store = Z; g.C = cbuf; g.ldc = Z;
       if ((rc = launch_gemm(g, st, &h->launches))) return rc;
     }
     if (m->kind == KMPC_MODEL_LISTA) {
       const long long n = (long long)rows * Z;
       int blocks = (int)((n + 255) / 256); if (blocks > h->sm_count * 8) blocks = h->sm_count * 8;
-      shrink_kernel<<<blocks, 256, 0, st>>>(cbuf, zcur, n, m->lista_thr); h->launches++;
+      shrink_kernel<<<blocks, 256, 0, st>>>(cbuf, zcur, lo_of_buf(zcur), n, m->lista_thr); h->launches++;
       float* zalt = buf[0];
       for (int it = 0; it < m->lista_loops; ++it) {          // z = shrink(z @ S + c)
         GemmArgs g = base_args();
-        g.A = zcur; g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->lista_ST; g.ldw = Z;
+        g.A = zcur; g.A_lo = lo_of_buf(zcur); g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->lista_ST; g.W_lo = m->lista_ST_lo; g.ldw = Z;
         g.M = rows; g.Nout = Z; g.n_store = Z; g.addend = cbuf; g.ld_add = Z; g.act = EPI_SHRINK; g.shrink_thr = m->lista_thr;
-        g.C = zalt; g.ldc = Z;
+        g.C = zalt; g.C_lo = lo_of_buf(zalt); g.ldc = Z;
         if ((rc = launch_gemm(g, st, &h->launches))) return rc;
         float* t = zcur; zcur = zalt; zalt = t;
       }
       if (zcur != buf[2]) {   // keep the convention zcur == buf[2] or buf[0]; both are fine below
       }
     } else if (m->norm_fn == KMPC_NORM_BALL) {
-      row_normalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(zcur, rows, Z); h->launches++;
+      row_normalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(zcur, lo_of_buf(zcur), rows, Z); h->launches++;
     }
     if (out_mode == 0) {
       cudaError_t e = cudaMemcpyAsync(out + (size_t)r0 * Z, zcur, (size_t)rows * Z * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -195,12 +220,12 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
     float* hbuf[2] = {buf[1], buf[3]};
     for (int k = 0; k < H; ++k) {
       GemmArgs g = base_args();
-      g.A = zcur; g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->kmatT; g.ldw = Z;
-      g.M = rows; g.Nout = Z; g.n_store = Z; g.C = znext; g.ldc = Z;
+      g.A = zcur; g.A_lo = lo_of_buf(zcur); g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->kmatT; g.W_lo = m->kmatT_lo; g.ldw = Z;
+      g.M = rows; g.Nout = Z; g.n_store = Z; g.C = znext; g.C_lo = lo_of_buf(znext); g.ldc = Z;
       if ((rc = launch_gemm(g, st, &h->launches))) return rc;
       { float* t = zcur; zcur = znext; znext = t; }
       if (m->kind == KMPC_MODEL_GENERIC && m->norm_fn == KMPC_NORM_BALL) {
-        row_normalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(zcur, rows, Z); h->launches++;
+        row_normalize_kernel<<<(rows + 7) / 8, 256, 0, st>>>(zcur, lo_of_buf(zcur), rows, Z); h->launches++;
       }
       const int ncol = (out_mode == 1) ? m->N : n_cols;
       float* dst = out + ((size_t)r0 * H + k) * ncol;
@@ -209,13 +234,13 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
         for (int li = 0; li < m->n_dec; ++li) {
           GemmArgs d = base_args();
           const bool last = (li == m->n_dec - 1);
-          d.A = xx; d.a_rows_per_group = rows; d.lda = xl; d.K = m->dec_dims[li]; d.W = m->dec_w[li]; d.ldw = m->dec_dims[li];
+          d.A = xx; d.A_lo = lo_of_buf(xx); d.a_rows_per_group = rows; d.lda = xl; d.K = m->dec_dims[li]; d.W = m->dec_w[li]; d.W_lo = m->dec_w_lo[li]; d.ldw = m->dec_dims[li];
           d.M = rows; d.bias = m->dec_b[li];
           if (last) {
             d.Nout = ncol; d.n_store = ncol; d.C = dst; d.ldc = (long long)H * ncol;
             if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.row0 = r0; }
           } else {
-            d.Nout = m->dec_dims[li + 1]; d.n_store = d.Nout; d.act = act_to_epi(m->dec_act); d.C = hbuf[li & 1]; d.ldc = d.Nout;
+            d.Nout = m->dec_dims[li + 1]; d.n_store = d.Nout; d.act = act_to_epi(m->dec_act); d.C = hbuf[li & 1]; d.C_lo = lo_of_buf(d.C); d.ldc = d.Nout;
           }
           if ((rc = launch_gemm(d, st, &h->launches))) return rc;
           xx = d.C; xl = d.Nout;
@@ -249,12 +274,21 @@ static int dev_copy(kmpc_model* m, const float* src, size_t n, float** out) {
   return 0;
 }
 
+static int make_lo(kmpc_model* m, const float* src, size_t n, float** out) {
+  int rc = dev_copy(m, nullptr, n, out);
+  if (rc) return rc;
+  rc = kmpc::launch_split_lo(src, *out, (long long)n, 0);
+  if (rc) return kmpc_fail_cuda((cudaError_t)rc, "split_lo");
+  return 0;
+}
+
 extern "C" {
 
 int kmpc_model_free(kmpc_model* m) {
   if (!m) return KMPC_OK;
   cudaSetDevice(m->h->device);
   for (void* p : m->owned) cudaFree(p);
+  if (m->z_lo) cudaFree(m->z_lo);
   delete m;
   return KMPC_OK;
 }
@@ -270,7 +304,8 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
   m->n_enc = 0; m->enc_act = D->enc_act; m->enc_last_relu = D->enc_last_relu; m->enc_w0_win = nullptr;
   m->n_dec = 0; m->dec_act = D->dec_act; m->kmatT = nullptr;
   m->lista_linear = D->lista_linear_encoder; m->lista_loops = D->lista_loops; m->lista_thr = D->lista_threshold;
-  m->lista_ST = nullptr; m->lista_wdT = nullptr;
+  m->lista_ST = nullptr; m->lista_wdT = nullptr; m->lista_ST_lo = nullptr; m->kmatT_lo = nullptr; m->enc_w0_win_lo = nullptr;
+  m->z_lo = nullptr; m->z_lo_cap = 0;
   int rc = 0;
   auto bail = [&](int code) { kmpc_model_free(m); return code; };
   const bool mlp_enc = (D->kind == KMPC_MODEL_GENERIC) || !D->lista_linear_encoder;
@@ -284,26 +319,32 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
       float *w = nullptr, *b = nullptr;
       if ((rc = dev_copy(m, D->enc_w_host[i], (size_t)m->enc_dims[i] * m->enc_dims[i + 1], &w))) return bail(rc);
       if (D->enc_b_host && D->enc_b_host[i]) { if ((rc = dev_copy(m, D->enc_b_host[i], m->enc_dims[i + 1], &b))) return bail(rc); }
-      m->enc_w.push_back(w); m->enc_b.push_back(b);
+      float* wl = nullptr;
+      if ((rc = make_lo(m, w, (size_t)m->enc_dims[i] * m->enc_dims[i + 1], &wl))) return bail(rc);
+      m->enc_w.push_back(w); m->enc_b.push_back(b); m->enc_w_lo.push_back(wl);
     }
     first_w = m->enc_w[0]; first_out = m->enc_dims[1];
   } else {
     if (!D->lista_We) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: lista_We missing"));
     float* w = nullptr;
     if ((rc = dev_copy(m, D->lista_We, (size_t)D->latent * D->obs, &w))) return bail(rc);
-    m->enc_w.push_back(w); m->enc_b.push_back(nullptr);
+    float* wl = nullptr;
+    if ((rc = make_lo(m, w, (size_t)D->latent * D->obs, &wl))) return bail(rc);
+    m->enc_w.push_back(w); m->enc_b.push_back(nullptr); m->enc_w_lo.push_back(wl);
     m->enc_dims = {D->obs, D->latent};
     first_w = w; first_out = D->latent;
   }
   {  // first layer re-laid for the window read
     if ((rc = dev_copy(m, nullptr, (size_t)first_out * m->d * m->ld, &m->enc_w0_win))) return bail(rc);
     kmpc::window_permute_kernel<<<h->sm_count * 4, 256>>>(first_w, first_out, m->N, m->d, m->ld, m->enc_w0_win);
+    if ((rc = make_lo(m, m->enc_w0_win, (size_t)first_out * m->d * m->ld, &m->enc_w0_win_lo))) return bail(rc);
   }
   if (!D->kmat) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: kmat missing"));
   if ((rc = dev_copy(m, nullptr, (size_t)m->Z * m->Z, &m->kmatT))) return bail(rc);
   {
     dim3 grid((m->Z + 31) / 32, (m->Z + 31) / 32), blk(32, 8);
     kmpc::transpose_kernel<<<grid, blk>>>(D->kmat, m->Z, m->Z, m->kmatT);
+    if ((rc = make_lo(m, m->kmatT, (size_t)m->Z * m->Z, &m->kmatT_lo))) return bail(rc);
   }
   if (D->kind == KMPC_MODEL_GENERIC) {
     if (D->n_dec <= 0 || !D->dec_dims_host || !D->dec_w_host) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: decoder layers missing"));
@@ -314,13 +355,16 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
       float *w = nullptr, *b = nullptr;
       if ((rc = dev_copy(m, D->dec_w_host[i], (size_t)m->dec_dims[i] * m->dec_dims[i + 1], &w))) return bail(rc);
       if (D->dec_b_host && D->dec_b_host[i]) { if ((rc = dev_copy(m, D->dec_b_host[i], m->dec_dims[i + 1], &b))) return bail(rc); }
-      m->dec_w.push_back(w); m->dec_b.push_back(b);
+      float* wl = nullptr;
+      if ((rc = make_lo(m, w, (size_t)m->dec_dims[i] * m->dec_dims[i + 1], &wl))) return bail(rc);
+      m->dec_w.push_back(w); m->dec_b.push_back(b); m->dec_w_lo.push_back(wl);
     }
   } else {
     if (!D->lista_S || !D->lista_dict) return bail(kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: lista_S / lista_dict missing"));
     if ((rc = dev_copy(m, nullptr, (size_t)m->Z * m->Z, &m->lista_ST))) return bail(rc);
     dim3 grid((m->Z + 31) / 32, (m->Z + 31) / 32), blk(32, 8);
     kmpc::transpose_kernel<<<grid, blk>>>(D->lista_S, m->Z, m->Z, m->lista_ST);
+    if ((rc = make_lo(m, m->lista_ST, (size_t)m->Z * m->Z, &m->lista_ST_lo))) return bail(rc);
     if ((rc = dev_copy(m, nullptr, (size_t)m->obs * m->Z, &m->lista_wdT))) return bail(rc);
     kmpc::dict_normalize_transpose_kernel<<<(m->Z + 7) / 8, 256>>>(D->lista_dict, m->Z, m->obs, m->lista_wdT);
   }
@@ -360,8 +404,22 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
   int rc = stats_to_f32(h, mean, std, (stats_per_path ? B : 1) * m->N, &std32, &mean32, st);
   if (rc) return rc;
   const int rpp = t1 - t0;
+  // residual twin of the series for the 3xTF32 operand split of the first layer
+  kmpc_model* mm = const_cast<kmpc_model*>(m);
+  const size_t zn = (size_t)B * T * ld_z;
+  if (mm->z_lo_cap < zn) {
+    if (mm->z_lo) cudaFree(mm->z_lo);
+    mm->z_lo = nullptr; mm->z_lo_cap = 0;
+    cudaError_t e = cudaMalloc(&mm->z_lo, zn * sizeof(float));
+    if (e != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(z_lo)");
+    mm->z_lo_cap = zn;
+  }
+  rc = kmpc::launch_split_lo(z, mm->z_lo, (long long)zn, st);
+  h->launches++;
+  if (rc) return kmpc_fail_cuda((cudaError_t)rc, "split_lo(series)");
   kmpc::AView av;
-  av.A = z + (size_t)(row0 + t0) * ld_z; av.group_stride = (long long)T * ld_z; av.rows_per_group = rpp; av.lda = ld_z;
+  av.A = z + (size_t)(row0 + t0) * ld_z; av.A_lo = mm->z_lo + (size_t)(row0 + t0) * ld_z;
+  av.group_stride = (long long)T * ld_z; av.rows_per_group = rpp; av.lda = ld_z;
   av.K = m->d * ld_z; av.window = true;
   return kmpc::run_chain(h, m, av, B * rpp, H, 1, m->N, std32, mean32, stats_per_path ? rpp : 0, yhat, st);
 }
@@ -369,7 +427,7 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
 int kmpc_encode(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, float* latent, void* stream) {
   if (!h || !m || !obs || !latent || M <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_encode: bad argument");
   FCK(cudaSetDevice(h->device));
-  kmpc::AView av; av.A = obs; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
+  kmpc::AView av; av.A = obs; av.A_lo = nullptr; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
   return kmpc::run_chain(h, m, av, M, 0, 0, 0, nullptr, nullptr, 0, latent, (cudaStream_t)stream);
 }
 
@@ -377,7 +435,7 @@ int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, i
   if (!h || !m || !obs || !pred || M <= 0 || H <= 0 || obs_cols <= 0 || obs_cols > m->obs)
     return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_rollout: bad argument");
   FCK(cudaSetDevice(h->device));
-  kmpc::AView av; av.A = obs; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
+  kmpc::AView av; av.A = obs; av.A_lo = nullptr; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
   return kmpc::run_chain(h, m, av, M, H, 2, obs_cols, nullptr, nullptr, 0, pred, (cudaStream_t)stream);
 }
 
@@ -392,7 +450,7 @@ int kmpc_step_latent(kmpc_handle* h, const kmpc_model* m, const float* z, int M,
   int rc = kmpc::launch_gemm(g, st, &h->launches);
   if (rc) return rc;
   if (m->kind == KMPC_MODEL_GENERIC && m->norm_fn == KMPC_NORM_BALL) {
-    kmpc::row_normalize_kernel<<<(M + 7) / 8, 256, 0, st>>>(out, M, m->Z); h->launches++;
+    kmpc::row_normalize_kernel<<<(M + 7) / 8, 256, 0, st>>>(out, nullptr, M, m->Z); h->launches++;
   }
   return KMPC_OK;
 }
@@ -430,6 +488,34 @@ int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, floa
     if ((rc = kmpc::launch_gemm(d, st, &h->launches))) return rc;
     xx = d.C; xl = d.Nout;
   }
+  return KMPC_OK;
+}
+
+// ---- diagnostics -------------------------------------------------------------------------------------------
+// 1 = tcgen05 3xTF32 GEMM where eligible (default), 0 = fp32 SIMT GEMM everywhere.  Process-wide.
+int kmpc_set_gemm_mode(int use_tensor_cores) { kmpc::set_gemm_tc_mode(use_tensor_cores); return KMPC_OK; }
+
+// C[M,Nout] = A[M,K] . W[Nout,K]^T through one chosen kernel: mode 0 = SIMT fp32, 1 = tcgen05 3xTF32 (returns
+// KMPC_E_UNSUPPORTED if the shape is not eligible).  Allocates the residual twins internally; synchronous.
+int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode) {
+  if (!h || !A || !W || !C || M <= 0 || Nout <= 0 || K <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_debug_gemm: bad argument");
+  FCK(cudaSetDevice(h->device));
+  float *Alo = nullptr, *Wlo = nullptr;
+  FCK(cudaMalloc(&Alo, (size_t)M * K * sizeof(float)));
+  cudaError_t e = cudaMalloc(&Wlo, (size_t)Nout * K * sizeof(float));
+  if (e != cudaSuccess) { cudaFree(Alo); return kmpc_fail_cuda(e, "cudaMalloc"); }
+  kmpc::launch_split_lo(A, Alo, (long long)M * K, 0);
+  kmpc::launch_split_lo(W, Wlo, (long long)Nout * K, 0);
+  kmpc::GemmArgs g = kmpc::base_args();
+  g.A = A; g.A_lo = Alo; g.a_rows_per_group = M; g.lda = K; g.K = K; g.W = W; g.W_lo = Wlo; g.ldw = K;
+  g.M = M; g.Nout = Nout; g.n_store = Nout; g.C = C; g.ldc = Nout;
+  int rc = mode ? kmpc::launch_gemm_tc(g, 0) : kmpc::launch_gemm_simt(g, 0);
+  h->launches += 3;
+  e = cudaDeviceSynchronize();
+  cudaFree(Alo); cudaFree(Wlo);
+  if (rc == -100) return kmpc_fail_cuda(cudaErrorNotSupported, "kmpc_debug_gemm: shape not eligible for the tcgen05 kernel");
+  if (rc) return kmpc_fail_cuda((cudaError_t)rc, "kmpc_debug_gemm launch");
+  if (e != cudaSuccess) return kmpc_fail_cuda(e, "kmpc_debug_gemm kernel");
   return KMPC_OK;
 }
 

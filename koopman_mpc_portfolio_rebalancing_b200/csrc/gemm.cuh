@@ -14,11 +14,13 @@ struct GemmArgs {
   // [B,T,ld] uses rows_per_group = rows per path, group_stride = T*ld, lda = ld, K = d*ld: consecutive rows
   // overlap and the embedded matrix is never materialised.
   const float* A;
+  const float* A_lo;   // fp32 residual twin of A (x - top19bits(x)); null -> the tcgen05 path is not eligible
   long long a_group_stride;
   int a_rows_per_group;
   int lda;
   int row0;            // logical index of row 0 of this launch (chunked launches over a grouped view)
   const float* W;      // [Nout, K], row stride ldw
+  const float* W_lo;   // residual twin of W
   int ldw;
   int M, Nout, K;
   const float* bias;   // [Nout] or null
@@ -41,6 +43,11 @@ struct GemmArgs {
 
 // fp32 SIMT path (exact fp32 FMA accumulation; any shape / alignment)
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
+// tcgen05 3xTF32 path; returns -100 when the launch is not eligible (shape, alignment, missing twins)
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+void set_gemm_tc_mode(int on);
+int launch_split_lo(const float* x, float* lo, long long n, cudaStream_t st);
+int launch_gemm(const GemmArgs& g, cudaStream_t st, long long* launches);
 
 __device__ __forceinline__ float epilogue_apply(float x, int act, float thr) {
   switch (act) {

@@ -3,7 +3,6 @@
 #include "gemm.cuh"
 int kmpc_fail_cuda(cudaError_t e, const char* what);
 namespace kmpc {
-int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);   // returns -100 when the shape is not eligible
 int launch_gemm(const GemmArgs& g, cudaStream_t st, long long* launches) {
   int rc = launch_gemm_tc(g, st);
   if (rc == -100) rc = launch_gemm_simt(g, st);

@@ -14,8 +14,11 @@
 //     whose SPD Schur complement K is assembled with warp reductions and factorised by the warp.
 // The numpy twin of this file, iteration for iteration, is oracle/mpc_oracle.py::solve_structured.
 //
-// Lane l owns assets l, l+32, ... (APT per lane); H is a compile-time constant so that every
-// per-stage array lives in registers (or compiler-managed local memory when it does not fit).
+// Memory placement (the solver is latency/issue bound, not HBM bound): lane l owns assets l, l+32, ...
+// (APT per lane).  The iterate (w, slacks, duals, R) lives in registers; the factorisation of the current
+// iterate (Green factors, barrier weights) and the search directions live in the warp's private slice of
+// shared memory, laid out [array][stage][slot] so that every access is conflict free.  H is a compile-time
+// constant: every loop over stages is unrolled and every register array is statically indexed.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -53,17 +56,6 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
   return v;
 }
-// min / max of non-negative values through the integer REDUX unit (fp32 precision, rounded safely)
-__device__ __forceinline__ double warp_min_pos(double v) {
-  float f = __double2float_rd(v);
-  unsigned u = __reduce_min_sync(kFull, __float_as_uint(f));
-  return (double)__uint_as_float(u);
-}
-__device__ __forceinline__ double warp_max_pos(double v) {
-  float f = __double2float_ru(v);
-  unsigned u = __reduce_max_sync(kFull, __float_as_uint(f));
-  return (double)__uint_as_float(u);
-}
 
 // Reduce NV (<= 32) per-lane values across the warp; the total of entry e lands in lane e.
 // 31 double shuffles for 32 entries instead of 160.
@@ -75,13 +67,11 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[32], int lan
       const bool up = (lane & o) != 0;
 #pragma unroll
       for (int i = 0; i < o; ++i) {
-        if (i + o < NV || i < NV) {
-          double lo = (i < NV) ? v[i] : 0.0;
-          double hi = (i + o < NV) ? v[i + o] : 0.0;
-          double send = up ? lo : hi;
-          double keep = up ? hi : lo;
-          v[i] = keep + shfl_xor_d(send, o);
-        }
+        double lo = (i < NV) ? v[i] : 0.0;
+        double hi = (i + o < NV) ? v[i + o] : 0.0;
+        double send = up ? lo : hi;
+        double keep = up ? hi : lo;
+        v[i] = keep + shfl_xor_d(send, o);
       }
     } else {
 #pragma unroll
@@ -94,21 +84,67 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[32], int lan
 template <int H, int APT>
 struct WarpIpm {
   static constexpr int NB = 3 * H;          // border size (R-rows, budget rows, cap rows)
-  static constexpr int SMEM_DOUBLES = NB * NB + NB;
+  static constexpr int SLOTS = 32 * APT;
+  // shared-memory arrays, each [H][SLOTS]: Green factors, barrier weights, search direction, iterate
+  enum : int { QL, TL, QR, TR, GJJ, VD, FL, FR, IE, DP, DQ, DW0, DW, DSP, DSQ, DZW, DZP, DZQ,
+               RR, ZW, WW, SP, SQ, ZP, ZQ, IW, ISP, ISQ, NARR };
+  // warp-uniform per-stage scalars, also in shared memory (broadcast reads; every lane writes the same value)
+  enum : int { NU, SC, ZC, DNU, DSC, DZC, IRHO, ISC, RHO, RP, CC, YR, YN, YC, NUNI };
+  static constexpr int SMEM_DOUBLES = NARR * H * SLOTS + NB * NB + NB + NUNI * H;
   static_assert(NB <= 32, "border must fit one entry per lane");
+  static_assert(2 * H + 1 <= 32, "H too large for the residual batch");
 
-  // ---- per-lane state -------------------------------------------------------------------------
-  double R[APT][H], w[APT][H], sp[APT][H], sq[APT][H], zw[APT][H], zp[APT][H], zq[APT][H];
-  double nu[H], sc[H], zc[H];               // warp-uniform
-  bool valid[APT];
-  // ---- factorisation of the current iterate -----------------------------------------------------
-  double qL[APT][H], tL[APT][H], qR[APT][H], tR[APT][H], gjj[APT][H], Vd[APT][H], fL[APT][H], fR[APT][H];
-  double phi[APT][H], iE[APT][H], Dp[APT][H], Dq[APT][H], Dw0[APT][H];
+  double* sm;                               // this warp's shared-memory slice
   double* Ksm;                              // [NB*NB] lower Cholesky factor (row-major), then [NB] 1/diag
-  int lane;
+  int lane, nassets;
   bool has_w, has_u, has_c;
   double lam, tau, delta;
   int nb;                                   // active border size: 2H or 3H
+
+  __device__ __forceinline__ void bind(double* smem_slice, int lane_, int n_assets) {
+    sm = smem_slice; Ksm = smem_slice + NARR * H * SLOTS; lane = lane_; nassets = n_assets;
+  }
+  __device__ __forceinline__ double& U(int arr, int k) const { return Ksm[NB * NB + NB + arr * H + k]; }
+  __device__ __forceinline__ bool ok(int a) const { return lane + 32 * a < nassets; }
+  __device__ __forceinline__ double& F(int arr, int k, int a) const { return sm[(arr * H + k) * SLOTS + a * 32 + lane]; }
+  __device__ __forceinline__ double phi(int k, int a) const { return (F(DQ, k, a) - F(DP, k, a)) * F(IE, k, a); }
+
+  // Green's function column j (runtime) of asset a: G[l] = potential of node l, D[l] = drop across edge l, for
+  // a unit current injected at node j.  Register arrays are indexed statically; j only enters predicates.
+  __device__ __forceinline__ void green_col(int a, int j, double (&G)[H], double (&D)[H]) const {
+    const double gjj = F(GJJ, j, a);
+    double v = gjj;
+#pragma unroll
+    for (int l = 0; l < H; ++l) {
+      G[l] = 0.0; D[l] = 0.0;
+      if (l == j) G[l] = gjj;
+      if (l > j) { D[l] = -v * F(QR, l, a); v *= F(TR, l, a); G[l] = v; }
+    }
+    v = gjj;
+#pragma unroll
+    for (int l = H - 1; l >= 0; --l) {
+      if (l <= j) {
+        D[l] = v * F(QL, l, a); v *= F(TL, l, a);
+        if (l >= 1) G[(l >= 1) ? l - 1 : 0] = v;
+      }
+    }
+  }
+  // DD[l]: drop across edge l for a unit dipole across edge k (+1 at node k, -1 at node k-1), k runtime
+  __device__ __forceinline__ void dipole_col(int a, int k, double (&DD)[H]) const {
+    const double V = F(VD, k, a);
+    double v = V * F(FL, k, a);
+#pragma unroll
+    for (int l = 0; l < H; ++l) {
+      DD[l] = 0.0;
+      if (l == k) DD[l] = V;
+      if (l > k) { DD[l] = -v * F(QR, l, a); v *= F(TR, l, a); }
+    }
+    v = -V * F(FR, k, a);
+#pragma unroll
+    for (int l = H - 1; l >= 0; --l) {
+      if (l < k) { DD[l] = v * F(QL, l, a); v *= F(TL, l, a); }
+    }
+  }
 
   // M0^{-1} (g_w, g_u): dw, dd through the Green's functions; pg = phi * g_u (dipole strengths)
   __device__ __forceinline__ void m0_apply(int a, const double (&gwv)[H], const double (&pg)[H],
@@ -117,148 +153,177 @@ struct WarpIpm {
     for (int k = 0; k < H; ++k) { dw[k] = 0.0; dd[k] = 0.0; }
 #pragma unroll
     for (int j = 0; j < H; ++j) {
+      double G[H], D[H];
+      green_col(a, j, G, D);
       const double g = gwv[j];
       double acc = 0.0;                     // sum_k D[k,j] * pg[k]  (potential of node j from the dipoles)
-      double v = gjj[a][j];
-      dw[j] += v * g;
 #pragma unroll
-      for (int l = j + 1; l < H; ++l) {     // propagate right
-        const double Dlj = -v * qR[a][l];
-        v *= tR[a][l];
-        dw[l] += v * g;
-        dd[l] += Dlj * g;
-        acc += Dlj * pg[l];
-      }
-      v = gjj[a][j];
-#pragma unroll
-      for (int l = j; l >= 0; --l) {        // propagate left
-        const double Dlj = v * qL[a][l];
-        dd[l] += Dlj * g;
-        acc += Dlj * pg[l];
-        v *= tL[a][l];
-        if (l >= 1) dw[l - 1] += v * g;
+      for (int l = 0; l < H; ++l) {
+        dw[l] += G[l] * g;
+        dd[l] += D[l] * g;
+        acc += D[l] * pg[l];
       }
       dw[j] -= acc;
     }
     if (has_u) {
 #pragma unroll
-      for (int k = 0; k < H; ++k) {         // dipole across edge k
-        const double p = pg[k];
-        const double V = Vd[a][k];
-        dd[k] -= V * p;
-        double v = V * fL[a][k];
+      for (int k = 0; k < H; ++k) {
+        double DD[H];
+        dipole_col(a, k, DD);
 #pragma unroll
-        for (int l = k + 1; l < H; ++l) {
-          dd[l] += v * qR[a][l] * p;        // DD[l,k] = -v*qR
-          v *= tR[a][l];
-        }
-        v = -V * fR[a][k];
-#pragma unroll
-        for (int l = k - 1; l >= 0; --l) {
-          dd[l] -= v * qL[a][l] * p;        // DD[l,k] = v*qL
-          v *= tL[a][l];
-        }
+        for (int l = 0; l < H; ++l) dd[l] -= DD[l] * pg[k];
       }
     }
   }
 
-  // Build the Green's-function factors of every owned asset and the border matrix K; Cholesky.
+  // Build the Green factors of every owned asset (to shared memory) and the border matrix K; Cholesky.
   // Returns false on a non-positive pivot.
-  __device__ bool factorize(const double (&rho)[H]) {
-    double c[32];
-    // K entry numbering (lower triangle incl. diagonal, row-major over the active nb x nb border)
-    // is processed in batches of 32 partial sums.
-    const int ntri = nb * (nb + 1) / 2;
-    // per-asset Green factors
-#pragma unroll
+  __device__ __forceinline__ bool factorize() {
+#pragma unroll 1
     for (int a = 0; a < APT; ++a) {
+      const bool va = ok(a);
       double e[H], hLv[H], hRv[H], ad[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) {
-        const double dw0 = (has_w && valid[a]) ? zw[a][k] / w[a][k] : 0.0;
-        Dw0[a][k] = dw0;
+        const double iw = 1.0 / F(WW, k, a);
+        F(IW, k, a) = iw;
+        const double dw0 = (has_w && va) ? F(ZW, k, a) * iw : 0.0;
+        F(DW0, k, a) = dw0;
         ad[k] = dw0 + delta;
         if (has_u) {
-          const double dp = zp[a][k] / sp[a][k], dq = zq[a][k] / sq[a][k];
+          const double isp = 1.0 / F(SP, k, a), isq = 1.0 / F(SQ, k, a);
+          F(ISP, k, a) = isp; F(ISQ, k, a) = isq;
+          const double dp = F(ZP, k, a) * isp, dq = F(ZQ, k, a) * isq;
           const double E = dp + dq + delta;
           const double ie = 1.0 / E;
-          Dp[a][k] = dp; Dq[a][k] = dq; iE[a][k] = ie;
-          phi[a][k] = (dq - dp) * ie;
+          F(DP, k, a) = dp; F(DQ, k, a) = dq; F(IE, k, a) = ie;
           e[k] = (4.0 * dp * dq + 2.0 * delta * (dp + dq) + delta * delta) * ie;
         } else {
-          Dp[a][k] = 0.0; Dq[a][k] = 0.0; iE[a][k] = 1.0; phi[a][k] = 0.0; e[k] = 0.0;
+          F(DP, k, a) = 0.0; F(DQ, k, a) = 0.0; F(IE, k, a) = 1.0; e[k] = 0.0;
         }
       }
       // left sweep: hL[k] = conductance to ground seen at node k leftwards incl. ad[k]
 #pragma unroll
       for (int l = 0; l < H; ++l) {
-        if (l == 0) { qL[a][0] = 1.0; tL[a][0] = 0.0; }
-        else {
-          const double inv = 1.0 / (e[l] + hLv[l - 1]);
-          qL[a][l] = hLv[l - 1] * inv; tL[a][l] = e[l] * inv;
+        double ql = 1.0, tl = 0.0;
+        if (l > 0) {
+          const double inv = 1.0 / (e[l] + hLv[(l > 0) ? l - 1 : 0]);
+          ql = hLv[(l > 0) ? l - 1 : 0] * inv; tl = e[l] * inv;
         }
-        hLv[l] = ad[l] + e[l] * qL[a][l];
+        F(QL, l, a) = ql; F(TL, l, a) = tl;
+        hLv[l] = ad[l] + e[l] * ql;
       }
       // right sweep: hR[k] incl. ad[k]; qR/tR indexed by the edge entering node l from the left
       hRv[H - 1] = ad[H - 1];
+      double qr[H];
+      qr[0] = 0.0;
+      F(QR, 0, a) = 0.0; F(TR, 0, a) = 0.0;
 #pragma unroll
       for (int l = H - 1; l >= 1; --l) {
         const double inv = 1.0 / (e[l] + hRv[l]);
-        qR[a][l] = hRv[l] * inv; tR[a][l] = e[l] * inv;
-        hRv[l - 1] = ad[l - 1] + e[l] * qR[a][l];
+        qr[l] = hRv[l] * inv;
+        F(QR, l, a) = qr[l]; F(TR, l, a) = e[l] * inv;
+        hRv[l - 1] = ad[l - 1] + e[l] * qr[l];
       }
-      qR[a][0] = 0.0; tR[a][0] = 0.0;
 #pragma unroll
       for (int j = 0; j < H; ++j) {
-        const double gR = (j + 1 < H) ? e[j + 1] * qR[a][j + 1] : 0.0;
-        gjj[a][j] = 1.0 / (hLv[j] + gR);
+        const int jn = (j + 1 < H) ? j + 1 : 0;
+        const double gR = (j + 1 < H) ? e[jn] * qr[jn] : 0.0;
+        F(GJJ, j, a) = 1.0 / (hLv[j] + gR);
         double fl = 1.0, fr = 0.0;
         if (j > 0) {
-          const double inv = 1.0 / (hLv[j - 1] + hRv[j]);
-          fl = hLv[j - 1] * inv; fr = hRv[j] * inv;
+          const double inv = 1.0 / (hLv[(j > 0) ? j - 1 : 0] + hRv[j]);
+          fl = hLv[(j > 0) ? j - 1 : 0] * inv; fr = hRv[j] * inv;
         }
-        fL[a][j] = fl; fR[a][j] = fr;
-        Vd[a][j] = 1.0 / (e[j] + hRv[j] * fl);
+        F(FL, j, a) = fl; F(FR, j, a) = fr;
+        F(VD, j, a) = 1.0 / (e[j] + hRv[j] * fl);
       }
-    }
-    // K assembly: entries in batches of 32; entry (r, cidx) with r >= cidx (lower triangle).
-    // Border rows: [0,H) = Rt_k, [H,2H) = 1t_k, [2H,3H) = et_k.
-    int r0 = 0, c0 = 0;                                // (row, col) of entry `base`
-    for (int base = 0; base < ntri; base += 32) {
-      int r = r0, cc = c0;
-      int myr = 0, myc = 0;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        double s = 0.0;
-        if (base + i < ntri) {
-          const int rt = r / H, rl = r - rt * H;       // type and stage of the row / column
-          const int ct = cc / H, cl = cc - ct * H;
-#pragma unroll
-          for (int a = 0; a < APT; ++a)
-            if (valid[a]) s += k_entry(a, rt, rl, ct, cl);
-        }
-        c[i] = s;
-        if (i == lane) { myr = r; myc = cc; }
-        if (++cc > r) { ++r; cc = 0; }
-      }
-      r0 = r; c0 = cc;
-      const double tot = warp_transpose_reduce<32>(c, lane);
-      if (base + lane < ntri) Ksm[myr * NB + myc] = tot;
     }
     __syncwarp();
-    if (lane < H) {
-      double rk = 0.0, sk = 0.0;
+    // K assembly, one batch per column stage j.  Border rows: [0,H) = Rt, [H,2H) = 1t, [2H,3H) = et.
+    // Batch j holds, for all row stages l:  (1t_l,Rt_j) [H]  and for l >= j: (Rt_l,Rt_j) [H]  (1t_l,1t_j) [H]
+    //                then the cap entries:  (et_l,Rt_j) [H]  (et_l,1t_j) [H]  and for l >= j: (et_l,et_j) [H]
+    // For H > 5 the batch is split in two halves of <= 32 entries.
+    constexpr bool kSplit = (6 * H > 32);
+    constexpr int kHalves = kSplit ? 2 : 1;
+#pragma unroll 1
+    for (int jh = 0; jh < H * kHalves; ++jh) {
+      const int j = jh / kHalves, half = jh - j * kHalves;
+      double c[32];
 #pragma unroll
-      for (int k = 0; k < H; ++k) if (lane == k) { rk = rho[k]; sk = has_c ? sc[k] / zc[k] : 0.0; }
-      Ksm[lane * NB + lane] += rk * rk;                                     // 1/beta_k
-      if (has_c) Ksm[(2 * H + lane) * NB + 2 * H + lane] += sk;
+      for (int i = 0; i < 32; ++i) c[i] = 0.0;
+      const bool doG = !kSplit || half == 0;       // entries built from G: 1R, RR, 11
+      const bool doE = (!kSplit || half == 1) && has_c;   // entries involving cap rows: eR, e1, ee
+      constexpr int offE = kSplit ? 0 : 3 * H;     // position of the cap entries inside c[]
+#pragma unroll 1
+      for (int a = 0; a < APT; ++a) {
+        if (!ok(a)) continue;
+        double G[H], D[H];
+        green_col(a, j, G, D);
+        const double Rj = F(RR, j, a);
+        if (doG) {
+#pragma unroll
+          for (int l = 0; l < H; ++l) {
+            c[l] += Rj * G[l];                                   // (1t_l, Rt_j)
+            if (l >= j) {
+              c[H + l] += F(RR, l, a) * Rj * G[l];               // (Rt_l, Rt_j)
+              c[2 * H + l] += G[l];                              // (1t_l, 1t_j)
+            }
+          }
+        }
+        if (doE) {
+          double DD[H];
+          dipole_col(a, j, DD);
+          const double phj = phi(j, a);
+#pragma unroll
+          for (int l = 0; l < H; ++l) {
+            const double phl = phi(l, a);
+            const double dm = -phl * D[l];
+            c[offE + l] += dm * Rj;                              // (et_l, Rt_j)
+            c[offE + H + l] += dm;                               // (et_l, 1t_j)
+            if (l >= j) {
+              double v = phl * phj * DD[l];
+              if (l == j) v += F(IE, l, a);
+              c[offE + 2 * H + l] += v;                          // (et_l, et_j)
+            }
+          }
+        }
+      }
+      const double tot = warp_transpose_reduce<(kSplit ? 3 * H : 6 * H)>(c, lane);
+      // scatter: lane e holds entry e of this batch
+      int t = lane;
+      bool capPart = kSplit ? (half == 1) : false;
+      if (!kSplit && t >= 3 * H) { t -= 3 * H; capPart = true; }
+      if (lane < (kSplit ? 3 * H : 6 * H)) {
+        const int grp = t / H, l = t - grp * H;
+        int r = -1, cc = -1;
+        if (!capPart) {
+          if (grp == 0) { r = H + l; cc = j; }
+          else if (grp == 1 && l >= j) { r = l; cc = j; }
+          else if (grp == 2 && l >= j) { r = H + l; cc = H + j; }
+        } else if (has_c) {
+          if (grp == 0) { r = 2 * H + l; cc = j; }
+          else if (grp == 1) { r = 2 * H + l; cc = H + j; }
+          else if (grp == 2 && l >= j) { r = 2 * H + l; cc = 2 * H + j; }
+        }
+        if (r >= 0) Ksm[r * NB + cc] = tot;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {          // static indices only: a lane-indexed pick would push rho/sc/zc to local memory
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        Ksm[k * NB + k] += U(RHO, k) * U(RHO, k);                                   // 1/beta_k
+        if (has_c) Ksm[(2 * H + k) * NB + 2 * H + k] += U(SC, k) / U(ZC, k);
+      }
     }
     __syncwarp();
     // warp Cholesky (lower, in place); lane i owns row i
-    bool ok = true;
+    bool pd = true;
+#pragma unroll 1
     for (int j = 0; j < nb; ++j) {
       const double djj = Ksm[j * NB + j];
-      if (!(djj > 0.0)) { ok = false; break; }
+      if (!(djj > 0.0)) { pd = false; break; }
       const double inv = 1.0 / sqrt(djj);
       if (lane > j && lane < nb) Ksm[lane * NB + j] *= inv;
       if (lane == j) { Ksm[j * NB + j] = djj * inv; Ksm[NB * NB + j] = inv; }
@@ -269,55 +334,18 @@ struct WarpIpm {
       }
       __syncwarp();
     }
-    return ok;
-  }
-
-  // Green's function value needed by one K entry for asset slot a.
-  // G[l,j]: node l potential for unit injection at j;  D[l,j]: drop across edge l;  DD[l,k].
-  __device__ __forceinline__ double green_G(int a, int l, int j) const {
-    double v = gjj[a][j];
-    if (l > j) { for (int m = j + 1; m <= l; ++m) v *= tR[a][m]; }
-    else { for (int m = j; m > l; --m) v *= tL[a][m]; }
-    return v;
-  }
-  __device__ __forceinline__ double green_D(int a, int l, int j) const {
-    if (l <= j) return green_G(a, l, j) * qL[a][l];
-    return -green_G(a, l - 1, j) * qR[a][l];
-  }
-  __device__ __forceinline__ double green_DD(int a, int l, int k) const {
-    const double V = Vd[a][k];
-    if (l == k) return V;
-    if (l > k) {
-      double v = V * fL[a][k];
-      for (int m = k + 1; m < l; ++m) v *= tR[a][m];
-      return -v * qR[a][l];
-    }
-    double v = -V * fR[a][k];
-    for (int m = k - 1; m > l; --m) v *= tL[a][m];
-    return v * qL[a][l];
-  }
-  __device__ __forceinline__ double k_entry(int a, int rt, int rl, int ct, int cl) const {
-    // row type rt in {0:R,1:one,2:cap}, col type ct <= rt ordering not guaranteed; handle all pairs
-    if (rt < 2 && ct < 2) {
-      const double g = green_G(a, rl, cl);
-      return g * (rt == 0 ? R[a][rl] : 1.0) * (ct == 0 ? R[a][cl] : 1.0);
-    }
-    if (rt == 2 && ct < 2) {   // S[et_l, Rt_j or 1t_j] = sum -phi_l D[l,j] * (R_j or 1)
-      return -phi[a][rl] * green_D(a, rl, cl) * (ct == 0 ? R[a][cl] : 1.0);
-    }
-    // rt == 2 && ct == 2
-    double v = phi[a][rl] * phi[a][cl] * green_DD(a, rl, cl);
-    if (rl == cl) v += iE[a][rl];
-    return v;
+    return pd;
   }
 
   // y <- K^{-1} t ; lane i holds t_i on entry and y_i on exit (i < nb)
   __device__ __forceinline__ double k_solve(double t) const {
+#pragma unroll 1
     for (int j = 0; j < nb; ++j) {                 // forward: L y = t
       const double yj = shfl_d(t, j) * Ksm[NB * NB + j];
       if (lane == j) t = yj;
       if (lane > j && lane < nb) t -= Ksm[lane * NB + j] * yj;
     }
+#pragma unroll 1
     for (int j = nb - 1; j >= 0; --j) {            // backward: L' x = y
       const double xj = shfl_d(t, j) * Ksm[NB * NB + j];
       if (lane == j) t = xj;
@@ -326,154 +354,152 @@ struct WarpIpm {
     return t;
   }
 
-  struct Dir {
-    double dw[APT][H], dsp[APT][H], dsq[APT][H], dzw[APT][H], dzp[APT][H], dzq[APT][H];
-    double dnu[H], dsc[H], dzc[H];
-  };
+  // right-hand side of one asset:  rhs_x = -grad f - A' nu - G'(c/s);  c-terms come from shared memory
+  // (they alias the DZ* arrays, see solve()) when use_c, else they are zero (predictor).
+  __device__ __forceinline__ void build_rhs(int a, bool use_c, double (&g_w)[H], double (&g_u)[H]) const {
+    double tq[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      double gwk = F(RR, k, a) * U(IRHO, k) - U(NU, k);              // -grad_w f - nu
+      if (has_w && use_c) gwk += F(DZW, k, a) * F(IW, k, a);
+      double guk = 0.0;
+      tq[k] = 0.0;
+      if (has_u) {
+        double a1 = 0.0, a2 = 0.0;
+        if (use_c) { a1 = F(DZP, k, a) * F(ISP, k, a); a2 = F(DZQ, k, a) * F(ISQ, k, a); }
+        tq[k] = a1 - a2;
+        guk = -lam + a1 + a2;
+        if (has_c) guk -= U(CC, k) * U(ISC, k);
+      }
+      g_w[k] = gwk; g_u[k] = guk;
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      g_w[k] -= tq[k];
+      if (k + 1 < H) g_w[k] += tq[(k + 1 < H) ? k + 1 : 0];
+    }
+  }
 
-  // One Newton solve with complementarity targets c* (c = sigma*mu - corrector products).
-  __device__ void newton(const double (&gw)[APT][H], const double (&rp)[H],
-                         const double (&cw)[APT][H], const double (&cp)[APT][H], const double (&cq)[APT][H],
-                         const double (&cc)[H], Dir& d) const {
-    double g_w[APT][H], g_u[APT][H];
+  // One Newton solve with complementarity targets c (sigma*mu - corrector products; zero when !use_c).
+  // Writes the direction to shared memory (DW, DSP, DSQ, DZW, DZP, DZQ) and dnu/dsc/dzc.
+  // Two passes over the assets share one code instance: pass 0 accumulates t = V' M0^{-1} g, pass 1 applies
+  // dx = M0^{-1}(g - V y).
+  __device__ __forceinline__ void newton(bool use_c) {
     double tv[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) tv[i] = 0.0;
-    // right-hand side  rhs_x = -grad f - A' nu - G'(c/s)
 #pragma unroll
-    for (int a = 0; a < APT; ++a) {
-      double tq[H];
+    for (int k = 0; k < H; ++k) { U(YR, k) = 0.0; U(YN, k) = 0.0; U(YC, k) = 0.0; }
+    __syncwarp();
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) {
+        if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < H; ++k) {
-        double gwk = -gw[a][k] - nu[k];
-        if (has_w) gwk += cw[a][k] / w[a][k];
-        double guk = 0.0;
-        tq[k] = 0.0;
-        if (has_u) {
-          const double a1 = cp[a][k] / sp[a][k], a2 = cq[a][k] / sq[a][k];
-          tq[k] = a1 - a2;
-          guk = -lam + a1 + a2;
-          if (has_c) guk -= cc[k] / sc[k];
+          for (int k = 0; k < H; ++k) tv[H + k] += U(RP, k);            // t[H+k] = sum dw0 - q, q = -rp
         }
-        g_w[a][k] = gwk; g_u[a][k] = guk;
-      }
+        const double t = warp_transpose_reduce<NB>(tv, lane);
+        const double y = k_solve(t);
 #pragma unroll
-      for (int k = 0; k < H; ++k) {
-        g_w[a][k] -= tq[k];
-        if (k + 1 < H) g_w[a][k] += tq[k + 1];
-      }
-      if (!valid[a]) {
-#pragma unroll
-        for (int k = 0; k < H; ++k) { g_w[a][k] = 0.0; g_u[a][k] = 0.0; }
-      }
-    }
-    // first pass: t = V' M0^{-1} g
-#pragma unroll
-    for (int a = 0; a < APT; ++a) {
-      if (!valid[a]) continue;
-      double pg[H], dw0[H], dd0[H];
-#pragma unroll
-      for (int k = 0; k < H; ++k) pg[k] = phi[a][k] * g_u[a][k];
-      m0_apply(a, g_w[a], pg, dw0, dd0);
-#pragma unroll
-      for (int k = 0; k < H; ++k) {
-        tv[k] += R[a][k] * dw0[k];
-        tv[H + k] += dw0[k];
-        if (has_c) tv[2 * H + k] += g_u[a][k] * iE[a][k] - phi[a][k] * dd0[k];   // du0
-      }
-    }
-    double t = warp_transpose_reduce<NB>(tv, lane);
-#pragma unroll
-    for (int k = 0; k < H; ++k) if (lane == H + k) t += rp[k];   // t[H+k] = sum dw0 - q, q = -rp
-    const double y = k_solve(t);
-    // second pass: dx = M0^{-1}(g - V y)
-    double yR[H], yN[H], yC[H];
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-      yR[k] = shfl_d(y, k);
-      yN[k] = shfl_d(y, H + k);
-      yC[k] = has_c ? shfl_d(y, 2 * H + k) : 0.0;
-      d.dnu[k] = yN[k];
-      if (has_c) {
-        d.dsc[k] = -yC[k] * sc[k] / zc[k];
-        d.dzc[k] = (cc[k] / sc[k] - zc[k]) + yC[k];
-      } else { d.dsc[k] = 0.0; d.dzc[k] = 0.0; }
-    }
-#pragma unroll
-    for (int a = 0; a < APT; ++a) {
-      double gw2[H], geff[H], pg[H], dw[H], dd[H];
-#pragma unroll
-      for (int k = 0; k < H; ++k) {
-        gw2[k] = g_w[a][k] - yR[k] * R[a][k] - yN[k];
-        geff[k] = g_u[a][k] - yC[k];
-        pg[k] = phi[a][k] * geff[k];
-      }
-      if (valid[a]) m0_apply(a, gw2, pg, dw, dd);
-#pragma unroll
-      for (int k = 0; k < H; ++k) {
-        if (!valid[a]) {
-          d.dw[a][k] = 0.0; d.dsp[a][k] = 0.0; d.dsq[a][k] = 0.0; d.dzw[a][k] = 0.0; d.dzp[a][k] = 0.0; d.dzq[a][k] = 0.0;
-          continue;
+        for (int k = 0; k < H; ++k) {
+          U(YR, k) = shfl_d(y, k);
+          U(YN, k) = shfl_d(y, H + k);
+          U(YC, k) = has_c ? shfl_d(y, 2 * H + k) : 0.0;
+          U(DNU, k) = U(YN, k);
+          if (has_c) {
+            U(DSC, k) = -U(YC, k) * U(SC, k) / U(ZC, k);
+            U(DZC, k) = (U(CC, k) * U(ISC, k) - U(ZC, k)) + U(YC, k);
+          } else { U(DSC, k) = 0.0; U(DZC, k) = 0.0; }
         }
-        d.dw[a][k] = dw[k];
-        d.dzw[a][k] = has_w ? (cw[a][k] / w[a][k] - zw[a][k]) - Dw0[a][k] * dw[k] : 0.0;
-        if (has_u) {
-          const double dsp_ = (geff[k] - (2.0 * Dq[a][k] + delta) * dd[k]) * iE[a][k];
-          const double dsq_ = (geff[k] + (2.0 * Dp[a][k] + delta) * dd[k]) * iE[a][k];
-          d.dsp[a][k] = dsp_; d.dsq[a][k] = dsq_;
-          d.dzp[a][k] = (cp[a][k] / sp[a][k] - zp[a][k]) - Dp[a][k] * dsp_;
-          d.dzq[a][k] = (cq[a][k] / sq[a][k] - zq[a][k]) - Dq[a][k] * dsq_;
+      }
+#pragma unroll 1
+      for (int a = 0; a < APT; ++a) {
+        if (!ok(a)) continue;
+        double g_w[H], g_u[H], pg[H], dw[H], dd[H];
+        build_rhs(a, use_c, g_w, g_u);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          g_w[k] -= U(YR, k) * F(RR, k, a) + U(YN, k);                // zeros in pass 0
+          g_u[k] -= U(YC, k);                                      // geff
+          pg[k] = phi(k, a) * g_u[k];
+        }
+        m0_apply(a, g_w, pg, dw, dd);
+        if (pass == 0) {
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            tv[k] += F(RR, k, a) * dw[k];
+            tv[H + k] += dw[k];
+            if (has_c) tv[2 * H + k] += g_u[k] * F(IE, k, a) - phi(k, a) * dd[k];   // du0
+          }
         } else {
-          d.dsp[a][k] = 0.0; d.dsq[a][k] = 0.0; d.dzp[a][k] = 0.0; d.dzq[a][k] = 0.0;
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            const double cwv = (use_c && has_w) ? F(DZW, k, a) : 0.0;
+            const double cpv = (use_c && has_u) ? F(DZP, k, a) : 0.0;
+            const double cqv = (use_c && has_u) ? F(DZQ, k, a) : 0.0;
+            F(DW, k, a) = dw[k];
+            F(DZW, k, a) = has_w ? (cwv * F(IW, k, a) - F(ZW, k, a)) - F(DW0, k, a) * dw[k] : 0.0;
+            if (has_u) {
+              const double dp = F(DP, k, a), dq = F(DQ, k, a), ie = F(IE, k, a);
+              const double dsp_ = (g_u[k] - (2.0 * dq + delta) * dd[k]) * ie;
+              const double dsq_ = (g_u[k] + (2.0 * dp + delta) * dd[k]) * ie;
+              F(DSP, k, a) = dsp_; F(DSQ, k, a) = dsq_;
+              F(DZP, k, a) = (cpv * F(ISP, k, a) - F(ZP, k, a)) - dp * dsp_;
+              F(DZQ, k, a) = (cqv * F(ISQ, k, a) - F(ZQ, k, a)) - dq * dsq_;
+            } else {
+              F(DSP, k, a) = 0.0; F(DSQ, k, a) = 0.0; F(DZP, k, a) = 0.0; F(DZQ, k, a) = 0.0;
+            }
+          }
         }
       }
     }
   }
 
   // largest steps keeping slacks (ap) and duals (ad) positive
-  __device__ void max_step(const Dir& d, const double (&rho)[H], bool allow_short, double& ap, double& ad) const {
+  __device__ __forceinline__ void max_step(bool allow_short, double& ap, double& ad) const {
     double p = 1.0, q = 1.0;
-    auto lim = [](double v, double dv, double a0) { return (dv < 0.0) ? fmin(a0, -v / dv) : a0; };
+    // a0 <- min(a0, -v/dv) for dv < 0; the division is executed only when it lowers the bound
+    auto lim = [](double v, double dv, double a0) {
+      if (dv < 0.0 && fma(a0, dv, v) < 0.0) a0 = fmin(a0, -v / dv);
+      return a0;
+    };
+    double dr[32];
+    if (allow_short) {
 #pragma unroll
+      for (int i = 0; i < 32; ++i) dr[i] = 0.0;
+    }
+#pragma unroll 1
     for (int a = 0; a < APT; ++a) {
-      if (!valid[a]) continue;
+      if (!ok(a)) continue;
 #pragma unroll
       for (int k = 0; k < H; ++k) {
-        if (has_w) { p = lim(w[a][k], d.dw[a][k], p); q = lim(zw[a][k], d.dzw[a][k], q); }
+        if (has_w) { p = lim(F(WW, k, a), F(DW, k, a), p); q = lim(F(ZW, k, a), F(DZW, k, a), q); }
         if (has_u) {
-          p = lim(sp[a][k], d.dsp[a][k], p); p = lim(sq[a][k], d.dsq[a][k], p);
-          q = lim(zp[a][k], d.dzp[a][k], q); q = lim(zq[a][k], d.dzq[a][k], q);
+          p = lim(F(SP, k, a), F(DSP, k, a), p); p = lim(F(SQ, k, a), F(DSQ, k, a), p);
+          q = lim(F(ZP, k, a), F(DZP, k, a), q); q = lim(F(ZQ, k, a), F(DZQ, k, a), q);
         }
+        if (allow_short) dr[k] += F(DW, k, a) * F(RR, k, a);
       }
     }
     if (allow_short) {       // keep the log argument positive
-      double dr[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) dr[i] = 0.0;
-#pragma unroll
-      for (int a = 0; a < APT; ++a)
-        if (valid[a]) {
-#pragma unroll
-          for (int k = 0; k < H; ++k) dr[k] += d.dw[a][k] * R[a][k];
-        }
       const double tot = warp_transpose_reduce<H>(dr, lane);
 #pragma unroll
-      for (int k = 0; k < H; ++k) p = lim(rho[k], shfl_d(tot, k), p);
+      for (int k = 0; k < H; ++k) p = lim(U(RHO, k), shfl_d(tot, k), p);
     }
     if (has_c) {
 #pragma unroll
-      for (int k = 0; k < H; ++k) { p = lim(sc[k], d.dsc[k], p); q = lim(zc[k], d.dzc[k], q); }
+      for (int k = 0; k < H; ++k) { p = lim(U(SC, k), U(DSC, k), p); q = lim(U(ZC, k), U(DZC, k), q); }
     }
-    // exact fp64 min over the warp (the fp32 REDUX shortcut would perturb the iterates w.r.t. the oracle)
+    // exact fp64 min over the warp (keeps the iterates identical to the oracle's)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { p = fmin(p, shfl_xor_d(p, o)); q = fmin(q, shfl_xor_d(q, o)); }
     ap = p; ad = q;
   }
 
-  // Solve.  On entry R, valid, lane, Ksm are set.  w0[a] = current weights of the owned assets.
-  // Returns status; w[][] holds the plan (or tile(w0) on failure), kkt = (pres, dres, gap).
-  __device__ int solve(const double (&w0)[APT], int N, double lam_, double tau_, bool allow_short,
-                       const IpmOptions& opt, int& iters, double (&kkt)[3]) {
+  // Solve.  On entry the RR array (gross returns) is filled and bind() was called.  w0[a] = current weights of
+  // the owned assets.  Returns status; the WW array holds the plan (or tile(w0) on failure), kkt = (pres, dres, gap).
+  __device__ __forceinline__ int solve(const double (&w0)[APT], int N, double lam_, double tau_, bool allow_short,
+                                       const IpmOptions& opt, int& iters, double (&kkt)[3]) {
     lam = lam_; tau = tau_; delta = opt.delta;
     has_u = (lam > 0.0) || (tau > 0.0);
     has_c = has_u && (tau > 0.0);
@@ -485,17 +511,17 @@ struct WarpIpm {
     int bad = 0;
 #pragma unroll
     for (int a = 0; a < APT; ++a)
-      if (valid[a]) {
+      if (ok(a)) {
         if (!isfinite(w0[a])) bad = 1;
 #pragma unroll
-        for (int k = 0; k < H; ++k) if (!(isfinite(R[a][k]) && R[a][k] > 0.0)) bad = 1;
+        for (int k = 0; k < H; ++k) if (!(isfinite(F(RR, k, a)) && F(RR, k, a) > 0.0)) bad = 1;
       }
     if (__any_sync(kFull, bad)) { hold(w0); return ST_NONFINITE; }
     // ---- initial point (oracle/mpc_oracle.py::_initial_point) ----------------------------------------
     double base[APT], sb = 0.0;
 #pragma unroll
     for (int a = 0; a < APT; ++a) {
-      base[a] = valid[a] ? (allow_short ? w0[a] : fmax(w0[a], 0.0)) : 0.0;
+      base[a] = ok(a) ? (allow_short ? w0[a] : fmax(w0[a], 0.0)) : 0.0;
       sb += base[a];
     }
     sb = warp_sum(sb);
@@ -505,10 +531,10 @@ struct WarpIpm {
 #pragma unroll
     for (int a = 0; a < APT; ++a) {
       const double b = (sb > 0.0) ? base[a] / sb : invN;
-      const double w1 = valid[a] ? (1.0 - eps) * b + eps * invN : 1.0;
+      const double w1 = ok(a) ? (1.0 - eps) * b + eps * invN : 1.0;
 #pragma unroll
-      for (int k = 0; k < H; ++k) w[a][k] = w1;
-      if (valid[a]) absd0 += fabs(w1 - w0[a]);
+      for (int k = 0; k < H; ++k) F(WW, k, a) = w1;
+      if (ok(a)) absd0 += fabs(w1 - w0[a]);
     }
     absd0 = warp_sum(absd0);
     if (has_u) {
@@ -521,41 +547,40 @@ struct WarpIpm {
       double su0 = 0.0;
 #pragma unroll
       for (int a = 0; a < APT; ++a) {
-        const double d0 = valid[a] ? w[a][0] - w0[a] : 0.0;
+        const double d0 = ok(a) ? F(WW, 0, a) - w0[a] : 0.0;
         const double u0 = fabs(d0) + dl0;
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           const double dk = (k == 0) ? d0 : 0.0;
           const double uk = (k == 0) ? u0 : dlk;
-          sp[a][k] = uk - dk; sq[a][k] = uk + dk;
+          F(SP, k, a) = uk - dk; F(SQ, k, a) = uk + dk;
         }
-        if (valid[a]) su0 += u0;
+        if (ok(a)) su0 += u0;
       }
       su0 = warp_sum(su0);
 #pragma unroll
-      for (int k = 0; k < H; ++k) sc[k] = has_c ? (tau - ((k == 0) ? su0 : dlk * N)) : 1.0;
+      for (int k = 0; k < H; ++k) U(SC, k) = has_c ? (tau - ((k == 0) ? su0 : dlk * N)) : 1.0;
     } else {
 #pragma unroll
       for (int a = 0; a < APT; ++a)
 #pragma unroll
-        for (int k = 0; k < H; ++k) { sp[a][k] = 1.0; sq[a][k] = 1.0; }
+        for (int k = 0; k < H; ++k) { F(SP, k, a) = 1.0; F(SQ, k, a) = 1.0; }
 #pragma unroll
-      for (int k = 0; k < H; ++k) sc[k] = 1.0;
+      for (int k = 0; k < H; ++k) U(SC, k) = 1.0;
     }
-    double rho[H];
     {
       double rs[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) rs[i] = 0.0;
 #pragma unroll
       for (int a = 0; a < APT; ++a)
-        if (valid[a]) {
+        if (ok(a)) {
 #pragma unroll
-          for (int k = 0; k < H; ++k) rs[k] += w[a][k] * R[a][k];
+          for (int k = 0; k < H; ++k) rs[k] += F(WW, k, a) * F(RR, k, a);
         }
       const double tot = warp_transpose_reduce<H>(rs, lane);
 #pragma unroll
-      for (int k = 0; k < H; ++k) rho[k] = shfl_d(tot, k);
+      for (int k = 0; k < H; ++k) U(RHO, k) = shfl_d(tot, k);
     }
     const bool dual_start = has_w && (opt.dual_init > 0.0);
     if (dual_start) {
@@ -564,78 +589,79 @@ struct WarpIpm {
       for (int k = 0; k < H; ++k) {
         double mx = 0.0;
 #pragma unroll
-        for (int a = 0; a < APT; ++a) if (valid[a]) mx = fmax(mx, R[a][k] / rho[k]);
+        for (int a = 0; a < APT; ++a) if (ok(a)) mx = fmax(mx, F(RR, k, a) / U(RHO, k));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, shfl_xor_d(mx, o));
-        nu[k] = mx + opt.dual_init;
-        zc[k] = has_c ? zeta0 : 0.0;
+        U(NU, k) = mx + opt.dual_init;
+        U(ZC, k) = has_c ? zeta0 : 0.0;
       }
 #pragma unroll
       for (int a = 0; a < APT; ++a)
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-          zw[a][k] = valid[a] ? (-R[a][k] / rho[k] + nu[k]) : 0.0;
-          zp[a][k] = has_u ? 0.5 * (lam + zeta0) : 0.0;
-          zq[a][k] = zp[a][k];
+          F(ZW, k, a) = ok(a) ? (-F(RR, k, a) / U(RHO, k) + U(NU, k)) : 0.0;
+          F(ZP, k, a) = has_u ? 0.5 * (lam + zeta0) : 0.0;
+          F(ZQ, k, a) = F(ZP, k, a);
         }
     } else {
 #pragma unroll
-      for (int k = 0; k < H; ++k) { nu[k] = 1.0; zc[k] = has_c ? opt.mu0 / sc[k] : 0.0; }
+      for (int k = 0; k < H; ++k) { U(NU, k) = 1.0; U(ZC, k) = has_c ? opt.mu0 / U(SC, k) : 0.0; }
 #pragma unroll
       for (int a = 0; a < APT; ++a)
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-          zw[a][k] = (has_w && valid[a]) ? opt.mu0 / w[a][k] : 0.0;
-          zp[a][k] = has_u ? opt.mu0 / sp[a][k] : 0.0;
-          zq[a][k] = has_u ? opt.mu0 / sq[a][k] : 0.0;
+          F(ZW, k, a) = (has_w && ok(a)) ? opt.mu0 / F(WW, k, a) : 0.0;
+          F(ZP, k, a) = has_u ? opt.mu0 / F(SP, k, a) : 0.0;
+          F(ZQ, k, a) = has_u ? opt.mu0 / F(SQ, k, a) : 0.0;
         }
     }
     const double mcount = (has_w ? (double)H * N : 0.0) + (has_u ? 2.0 * H * N : 0.0) + (has_c ? (double)H : 0.0);
     int status = ST_FAILED;
-    double gw[APT][H];
-    double rp[H];
+#pragma unroll 1
     for (int it = 1; it <= opt.max_iter + 1; ++it) {
       iters = it;
       // ---- residuals --------------------------------------------------------------------------------
       double rs[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) rs[i] = 0.0;
+#pragma unroll 1
+      for (int a = 0; a < APT; ++a) {
+        if (!ok(a)) continue;
 #pragma unroll
-      for (int a = 0; a < APT; ++a)
-        if (valid[a]) {
-#pragma unroll
-          for (int k = 0; k < H; ++k) {
-            rs[k] += w[a][k] * R[a][k];
-            rs[H + k] += w[a][k];
-            double g = 0.0;
-            if (has_w) g += w[a][k] * zw[a][k];
-            if (has_u) g += sp[a][k] * zp[a][k] + sq[a][k] * zq[a][k];
-            rs[2 * H] += g;
-          }
+        for (int k = 0; k < H; ++k) {
+          const double wk = F(WW, k, a);
+          rs[k] += wk * F(RR, k, a);
+          rs[H + k] += wk;
+          double g = 0.0;
+          if (has_w) g += wk * F(ZW, k, a);
+          if (has_u) g += F(SP, k, a) * F(ZP, k, a) + F(SQ, k, a) * F(ZQ, k, a);
+          rs[2 * H] += g;
         }
-      static_assert(2 * H + 1 <= 32, "H too large for the residual batch");
+      }
       const double tot = warp_transpose_reduce<2 * H + 1>(rs, lane);
       double pres = 0.0, gap = shfl_d(tot, 2 * H);
 #pragma unroll
       for (int k = 0; k < H; ++k) {
-        rho[k] = shfl_d(tot, k);
-        rp[k] = shfl_d(tot, H + k) - 1.0;
-        pres = fmax(pres, fabs(rp[k]));
-        if (has_c) gap += sc[k] * zc[k];
+        U(RHO, k) = shfl_d(tot, k);
+        U(IRHO, k) = 1.0 / U(RHO, k);
+        U(ISC, k) = has_c ? 1.0 / U(SC, k) : 0.0;
+        U(RP, k) = shfl_d(tot, H + k) - 1.0;
+        pres = fmax(pres, fabs(U(RP, k)));
+        if (has_c) gap += U(SC, k) * U(ZC, k);
       }
       double dres = 0.0;
-#pragma unroll
+#pragma unroll 1
       for (int a = 0; a < APT; ++a) {
+        if (!ok(a)) continue;
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-          gw[a][k] = -R[a][k] / rho[k];
-          if (!valid[a]) continue;
-          const double yk = zp[a][k] - zq[a][k];
-          const double yn = (k + 1 < H) ? zp[a][k + 1] - zq[a][k + 1] : 0.0;
-          const double rdw = gw[a][k] - zw[a][k] + yk - yn + nu[k];
+          const int kn = (k + 1 < H) ? k + 1 : 0;
+          const double yk = F(ZP, k, a) - F(ZQ, k, a);
+          const double yn = (k + 1 < H) ? F(ZP, kn, a) - F(ZQ, kn, a) : 0.0;
+          const double rdw = -F(RR, k, a) * U(IRHO, k) - F(ZW, k, a) + yk - yn + U(NU, k);
           dres = fmax(dres, fabs(rdw));
           if (has_u) {
-            const double rdu = lam - zp[a][k] - zq[a][k] + (has_c ? zc[k] : 0.0);
+            const double rdu = lam - F(ZP, k, a) - F(ZQ, k, a) + (has_c ? U(ZC, k) : 0.0);
             dres = fmax(dres, fabs(rdu));
           }
         }
@@ -647,75 +673,73 @@ struct WarpIpm {
       if (pres < opt.tol && dres < opt.tol_dual && gap < opt.tol) { status = ST_OPTIMAL; break; }
       if (it == opt.max_iter + 1) break;
       const double mu = gap / fmax(mcount, 1.0);
-      if (!factorize(rho)) break;
-      // ---- predictor ------------------------------------------------------------------------------------
-      Dir d;
-      double cw[APT][H], cp[APT][H], cq[APT][H], cc[H];
+      __syncwarp();
+      if (!factorize()) break;
+      // ---- predictor (phase 0) and corrector (phase 1) share one code instance ---------------------------
 #pragma unroll
-      for (int a = 0; a < APT; ++a)
-#pragma unroll
-        for (int k = 0; k < H; ++k) { cw[a][k] = 0.0; cp[a][k] = 0.0; cq[a][k] = 0.0; }
-#pragma unroll
-      for (int k = 0; k < H; ++k) cc[k] = 0.0;
-      double sigma = 0.0;
-      if (mcount > 0.0) {
-        newton(gw, rp, cw, cp, cq, cc, d);
-        double aa, ab;
-        max_step(d, rho, allow_short, aa, ab);
-        double g2 = 0.0;
-#pragma unroll
-        for (int a = 0; a < APT; ++a)
-          if (valid[a]) {
+      for (int k = 0; k < H; ++k) U(CC, k) = 0.0;
+#pragma unroll 1
+      for (int phase = (mcount > 0.0 ? 0 : 1); phase < 2; ++phase) {
+        const bool use_c = (phase == 1) && (mcount > 0.0);
+        __syncwarp();
+        newton(use_c);
+        double aa = 1.0, ab = 1.0;
+        if (mcount > 0.0 || allow_short) max_step(allow_short, aa, ab);
+        if (phase == 0) {
+          double g2 = 0.0;
+#pragma unroll 1
+          for (int a = 0; a < APT; ++a) {
+            if (!ok(a)) continue;
 #pragma unroll
             for (int k = 0; k < H; ++k) {
-              if (has_w) g2 += (w[a][k] + aa * d.dw[a][k]) * (zw[a][k] + ab * d.dzw[a][k]);
-              if (has_u) g2 += (sp[a][k] + aa * d.dsp[a][k]) * (zp[a][k] + ab * d.dzp[a][k]) +
-                               (sq[a][k] + aa * d.dsq[a][k]) * (zq[a][k] + ab * d.dzq[a][k]);
+              if (has_w) g2 += (F(WW, k, a) + aa * F(DW, k, a)) * (F(ZW, k, a) + ab * F(DZW, k, a));
+              if (has_u) g2 += (F(SP, k, a) + aa * F(DSP, k, a)) * (F(ZP, k, a) + ab * F(DZP, k, a)) +
+                               (F(SQ, k, a) + aa * F(DSQ, k, a)) * (F(ZQ, k, a) + ab * F(DZQ, k, a));
             }
           }
-        g2 = warp_sum(g2);
-        if (has_c) {
+          g2 = warp_sum(g2);
+          if (has_c) {
 #pragma unroll
-          for (int k = 0; k < H; ++k) g2 += (sc[k] + aa * d.dsc[k]) * (zc[k] + ab * d.dzc[k]);
-        }
-        const double ratio = (gap > 0.0) ? fmin(1.0, fmax(g2 / gap, 0.0)) : 0.0;
-        sigma = ratio * ratio * ratio;
-        const double sm = sigma * mu;
-#pragma unroll
-        for (int a = 0; a < APT; ++a)
-#pragma unroll
-          for (int k = 0; k < H; ++k) {
-            cw[a][k] = has_w ? sm - d.dw[a][k] * d.dzw[a][k] : 0.0;
-            cp[a][k] = has_u ? sm - d.dsp[a][k] * d.dzp[a][k] : 0.0;
-            cq[a][k] = has_u ? sm - d.dsq[a][k] * d.dzq[a][k] : 0.0;
+            for (int k = 0; k < H; ++k) g2 += (U(SC, k) + aa * U(DSC, k)) * (U(ZC, k) + ab * U(DZC, k));
           }
+          const double ratio = (gap > 0.0) ? fmin(1.0, fmax(g2 / gap, 0.0)) : 0.0;
+          const double sigma = ratio * ratio * ratio;
+          const double smu = sigma * mu;
+          // complementarity targets of the corrector, stored in place of the affine dual steps
+#pragma unroll 1
+          for (int a = 0; a < APT; ++a) {
+            if (!ok(a)) continue;
 #pragma unroll
-        for (int k = 0; k < H; ++k) cc[k] = has_c ? sm - d.dsc[k] * d.dzc[k] : 0.0;
-      }
-      // ---- corrector ------------------------------------------------------------------------------------
-      newton(gw, rp, cw, cp, cq, cc, d);
-      double a_ = 1.0, b_ = 1.0;
-      if (mcount > 0.0 || allow_short) {
-        max_step(d, rho, allow_short, a_, b_);
-        a_ = fmin(1.0, opt.step_frac * a_); b_ = fmin(1.0, opt.step_frac * b_);
-      }
-#pragma unroll
-      for (int a = 0; a < APT; ++a)
-        if (valid[a]) {
-#pragma unroll
-          for (int k = 0; k < H; ++k) {
-            w[a][k] += a_ * d.dw[a][k];
-            if (has_w) zw[a][k] += b_ * d.dzw[a][k];
-            if (has_u) {
-              sp[a][k] += a_ * d.dsp[a][k]; sq[a][k] += a_ * d.dsq[a][k];
-              zp[a][k] += b_ * d.dzp[a][k]; zq[a][k] += b_ * d.dzq[a][k];
+            for (int k = 0; k < H; ++k) {
+              F(DZW, k, a) = has_w ? smu - F(DW, k, a) * F(DZW, k, a) : 0.0;
+              F(DZP, k, a) = has_u ? smu - F(DSP, k, a) * F(DZP, k, a) : 0.0;
+              F(DZQ, k, a) = has_u ? smu - F(DSQ, k, a) * F(DZQ, k, a) : 0.0;
             }
           }
-        }
 #pragma unroll
-      for (int k = 0; k < H; ++k) {
-        nu[k] += b_ * d.dnu[k];
-        if (has_c) { sc[k] += a_ * d.dsc[k]; zc[k] += b_ * d.dzc[k]; }
+          for (int k = 0; k < H; ++k) U(CC, k) = has_c ? smu - U(DSC, k) * U(DZC, k) : 0.0;
+        } else {
+          const double a_ = fmin(1.0, opt.step_frac * aa), b_ = fmin(1.0, opt.step_frac * ab);
+          const double pa = (mcount > 0.0 || allow_short) ? a_ : 1.0, pb = (mcount > 0.0 || allow_short) ? b_ : 1.0;
+#pragma unroll 1
+          for (int a = 0; a < APT; ++a) {
+            if (!ok(a)) continue;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              F(WW, k, a) += pa * F(DW, k, a);
+              if (has_w) F(ZW, k, a) += pb * F(DZW, k, a);
+              if (has_u) {
+                F(SP, k, a) += pa * F(DSP, k, a); F(SQ, k, a) += pa * F(DSQ, k, a);
+                F(ZP, k, a) += pb * F(DZP, k, a); F(ZQ, k, a) += pb * F(DZQ, k, a);
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            U(NU, k) += pb * U(DNU, k);
+            if (has_c) { U(SC, k) += pa * U(DSC, k); U(ZC, k) += pb * U(DZC, k); }
+          }
+        }
       }
     }
     if (status != ST_OPTIMAL && isfinite(kkt[1] + kkt[2]) && kkt[0] < 1e-8 && kkt[1] < 1e-6 && kkt[2] < 1e-8)
@@ -728,21 +752,21 @@ struct WarpIpm {
 #pragma unroll
     for (int a = 0; a < APT; ++a)
 #pragma unroll
-      for (int k = 0; k < H; ++k) w[a][k] = w0[a];
+      for (int k = 0; k < H; ++k) F(WW, k, a) = w0[a];
   }
 
-  // maximised objective of mpc.py:104 for the plan in w[][] (fp64)
-  __device__ double objective(const double (&w0)[APT]) const {
+  // maximised objective of mpc.py:104 for the plan in the WW array (fp64)
+  __device__ __forceinline__ double objective(const double (&w0)[APT]) const {
     double rs[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) rs[i] = 0.0;
 #pragma unroll
     for (int a = 0; a < APT; ++a)
-      if (valid[a]) {
+      if (ok(a)) {
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-          rs[k] += w[a][k] * R[a][k];
-          rs[H] += fabs(w[a][k] - ((k == 0) ? w0[a] : w[a][k - 1]));
+          rs[k] += F(WW, k, a) * F(RR, k, a);
+          rs[H] += fabs(F(WW, k, a) - ((k == 0) ? w0[a] : F(WW, (k == 0) ? 0 : k - 1, a)));
         }
       }
     const double tot = warp_transpose_reduce<H + 1>(rs, lane);

@@ -14,18 +14,17 @@ namespace kmpc {
 // round_f32(exp_f64(y)): the platform-independent stand-in for numpy's fp32 exp (mpc.py:55, backtest.py:193)
 __device__ __forceinline__ float exp_cr32(float y) { return __double2float_rn(exp((double)y)); }
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 1;   // one problem per warp; ~50 KB of shared memory per warp at H=5, N<=64
 
 template <int H, int APT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 mpc_solve_kernel(MpcSolveArgs A) {
   using Ipm = WarpIpm<H, APT>;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wid = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   Ipm s;
-  s.Ksm = smem + (size_t)wib * Ipm::SMEM_DOUBLES;
-  s.lane = lane;
+  s.bind(smem + (size_t)wib * Ipm::SMEM_DOUBLES, lane, A.N);
   const int N = A.N;
   const IpmOptions opt = A.opt;
   for (int p = wid; p < A.P; p += nwarps) {
@@ -33,16 +32,15 @@ mpc_solve_kernel(MpcSolveArgs A) {
 #pragma unroll
     for (int a = 0; a < APT; ++a) {
       const int i = lane + 32 * a;
-      s.valid[a] = i < N;
-      w0[a] = s.valid[a] ? A.w_cur[(size_t)p * N + i] : 0.0;
+            w0[a] = s.ok(a) ? A.w_cur[(size_t)p * N + i] : 0.0;
 #pragma unroll
       for (int k = 0; k < H; ++k) {
         double r = 1.0;
-        if (s.valid[a]) {
+        if (s.ok(a)) {
           if (A.yhat) r = (double)exp_cr32(A.yhat[((size_t)p * H + k) * N + i]);
           else r = exp(A.yhat64[((size_t)p * H + k) * N + i]);
         }
-        s.R[a][k] = r;
+        s.F(Ipm::RR, k, a) = r;
       }
     }
     const double lam = A.lam ? A.lam[p] : A.lam0;
@@ -52,9 +50,9 @@ mpc_solve_kernel(MpcSolveArgs A) {
     const double val = (st <= ST_INACCURATE) ? s.objective(w0) : CUDART_NAN;
 #pragma unroll
     for (int a = 0; a < APT; ++a)
-      if (s.valid[a]) {
+      if (s.ok(a)) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) A.w_out[((size_t)p * H + k) * N + lane + 32 * a] = s.w[a][k];
+        for (int k = 0; k < H; ++k) A.w_out[((size_t)p * H + k) * N + lane + 32 * a] = s.F(Ipm::WW, k, a);
       }
     if (lane == 0) {
       if (A.obj) A.obj[p] = val;
@@ -67,14 +65,13 @@ mpc_solve_kernel(MpcSolveArgs A) {
 }
 
 template <int H, int APT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 backtest_kernel(BacktestArgs A) {
   using Ipm = WarpIpm<H, APT>;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   Ipm s;
-  s.Ksm = smem + (size_t)wib * Ipm::SMEM_DOUBLES;
-  s.lane = lane;
+  s.bind(smem + (size_t)wib * Ipm::SMEM_DOUBLES, lane, A.N);
   const int N = A.N;
   const IpmOptions opt = A.opt;
   __shared__ int next_b[kWarpsPerBlock];
@@ -94,8 +91,7 @@ backtest_kernel(BacktestArgs A) {
     double wc[APT];
 #pragma unroll
     for (int a = 0; a < APT; ++a) {
-      s.valid[a] = (lane + 32 * a) < N;
-      wc[a] = s.valid[a] ? 1.0 / (double)N : 0.0;          // backtest.py:161
+            wc[a] = s.ok(a) ? 1.0 / (double)N : 0.0;          // backtest.py:161
     }
     // running metric state (backtest.py:221-249)
     double mean = 0.0, m2 = 0.0, cum = 1.0, peak = -CUDART_INF, maxdd = CUDART_INF, sum_turn = 0.0, v_first = 0.0;
@@ -108,7 +104,7 @@ backtest_kernel(BacktestArgs A) {
       for (int a = 0; a < APT; ++a)
 #pragma unroll
         for (int k = 0; k < H; ++k)
-          s.R[a][k] = s.valid[a] ? (double)exp_cr32(yh[k * N + lane + 32 * a]) : 1.0;
+          s.F(Ipm::RR, k, a) = s.ok(a) ? (double)exp_cr32(yh[k * N + lane + 32 * a]) : 1.0;
       int iters; double kkt[3];
       const int st = s.solve(wc, N, lam, tau, A.allow_short != 0, opt, iters, kkt);
       it_total += iters;
@@ -117,7 +113,7 @@ backtest_kernel(BacktestArgs A) {
       double tn = 0.0;
 #pragma unroll
       for (int a = 0; a < APT; ++a)
-        if (s.valid[a]) tn += fabs(s.w[a][0] - wc[a]);
+        if (s.ok(a)) tn += fabs(s.F(Ipm::WW, 0, a) - wc[a]);
       const double turnover = warp_sum(tn);
       const double cost = ccoef * turnover * V;
       V -= cost;
@@ -129,8 +125,8 @@ backtest_kernel(BacktestArgs A) {
         double pr = 0.0;
 #pragma unroll
         for (int a = 0; a < APT; ++a) {
-          r32[a] = s.valid[a] ? __fsub_rn(exp_cr32(rr[lane + 32 * a]), 1.0f) : 0.0f;   // f32, backtest.py:193
-          if (s.valid[a]) pr += s.w[a][0] * (double)r32[a];
+          r32[a] = s.ok(a) ? __fsub_rn(exp_cr32(rr[lane + 32 * a]), 1.0f) : 0.0f;   // f32, backtest.py:193
+          if (s.ok(a)) pr += s.F(Ipm::WW, 0, a) * (double)r32[a];
         }
         port_ret = warp_sum(pr);
         V *= (1.0 + port_ret);
@@ -138,10 +134,10 @@ backtest_kernel(BacktestArgs A) {
         if (fabs(denom) < 1e-8) denom = 1e-8;
 #pragma unroll
         for (int a = 0; a < APT; ++a)
-          wc[a] = s.valid[a] ? s.w[a][0] * (double)__fadd_rn(1.0f, r32[a]) / denom : 0.0;   // (1.0 + f32) stays f32
+          wc[a] = s.ok(a) ? s.F(Ipm::WW, 0, a) * (double)__fadd_rn(1.0f, r32[a]) / denom : 0.0;   // (1.0 + f32) stays f32
       } else {
 #pragma unroll
-        for (int a = 0; a < APT; ++a) wc[a] = s.valid[a] ? s.w[a][0] : 0.0;
+        for (int a = 0; a < APT; ++a) wc[a] = s.ok(a) ? s.F(Ipm::WW, 0, a) : 0.0;
       }
       // ---- history row + metric accumulators ----
       if (A.history && lane == 0) {
@@ -176,16 +172,25 @@ backtest_kernel(BacktestArgs A) {
     if (A.final_weights) {
 #pragma unroll
       for (int a = 0; a < APT; ++a)
-        if (s.valid[a]) A.final_weights[(size_t)b * N + lane + 32 * a] = wc[a];
+        if (s.ok(a)) A.final_weights[(size_t)b * N + lane + 32 * a] = wc[a];
     }
   }
+}
+
+template <typename K>
+static int blocks_per_sm_for(K kernel, size_t smem) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kWarpsPerBlock * 32, smem);
+  return nb < 1 ? 1 : nb;
 }
 
 template <int H, int APT>
 static int launch_mpc(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
   const size_t smem = (size_t)kWarpsPerBlock * WarpIpm<H, APT>::SMEM_DOUBLES * sizeof(double);
+  static int bps = blocks_per_sm_for(mpc_solve_kernel<H, APT>, smem);
   int blocks = (A.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int cap = sm_count * 2;
+  const int cap = sm_count * bps;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   mpc_solve_kernel<H, APT><<<blocks, kWarpsPerBlock * 32, smem, st>>>(A);
@@ -194,8 +199,9 @@ static int launch_mpc(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
 template <int H, int APT>
 static int launch_bt(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   const size_t smem = (size_t)kWarpsPerBlock * WarpIpm<H, APT>::SMEM_DOUBLES * sizeof(double);
+  static int bps = blocks_per_sm_for(backtest_kernel<H, APT>, smem);
   int blocks = (A.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int cap = sm_count * 2;
+  const int cap = sm_count * bps;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   backtest_kernel<H, APT><<<blocks, kWarpsPerBlock * 32, smem, st>>>(A);
