@@ -33,6 +33,7 @@ struct kmpc_model {
   float* lista_ST;             // S^T
   float* lista_ST_lo;
   float* lista_wdT;            // [obs, Z]: (dict / ||dict||_row.clamp(1e-4))^T
+  float* lista_wdT_lo;
   float* z_lo;                 // residual twin of the standardised series of the current forecast call
   size_t z_lo_cap;
   std::vector<void*> owned;
@@ -238,7 +239,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
           d.M = rows; d.bias = m->dec_b[li];
           if (last) {
             d.Nout = ncol; d.n_store = ncol; d.C = dst; d.ldc = (long long)H * ncol;
-            if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.row0 = r0; }
+            if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.stat_row0 = r0; }
           } else {
             d.Nout = m->dec_dims[li + 1]; d.n_store = d.Nout; d.act = act_to_epi(m->dec_act); d.C = hbuf[li & 1]; d.C_lo = lo_of_buf(d.C); d.ldc = d.Nout;
           }
@@ -247,9 +248,9 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
         }
       } else {
         GemmArgs d = base_args();
-        d.A = zcur; d.a_rows_per_group = rows; d.lda = Z; d.K = Z; d.W = m->lista_wdT; d.ldw = Z;
+        d.A = zcur; d.A_lo = lo_of_buf(zcur); d.a_rows_per_group = rows; d.lda = Z; d.K = Z; d.W = m->lista_wdT; d.W_lo = m->lista_wdT_lo; d.ldw = Z;
         d.M = rows; d.Nout = ncol; d.n_store = ncol; d.C = dst; d.ldc = (long long)H * ncol;
-        if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.row0 = r0; }
+        if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.stat_row0 = r0; }
         if ((rc = launch_gemm(d, st, &h->launches))) return rc;
       }
     }
@@ -304,7 +305,7 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
   m->n_enc = 0; m->enc_act = D->enc_act; m->enc_last_relu = D->enc_last_relu; m->enc_w0_win = nullptr;
   m->n_dec = 0; m->dec_act = D->dec_act; m->kmatT = nullptr;
   m->lista_linear = D->lista_linear_encoder; m->lista_loops = D->lista_loops; m->lista_thr = D->lista_threshold;
-  m->lista_ST = nullptr; m->lista_wdT = nullptr; m->lista_ST_lo = nullptr; m->kmatT_lo = nullptr; m->enc_w0_win_lo = nullptr;
+  m->lista_ST = nullptr; m->lista_wdT = nullptr; m->lista_ST_lo = nullptr; m->lista_wdT_lo = nullptr; m->kmatT_lo = nullptr; m->enc_w0_win_lo = nullptr;
   m->z_lo = nullptr; m->z_lo_cap = 0;
   int rc = 0;
   auto bail = [&](int code) { kmpc_model_free(m); return code; };
@@ -367,6 +368,7 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
     if ((rc = make_lo(m, m->lista_ST, (size_t)m->Z * m->Z, &m->lista_ST_lo))) return bail(rc);
     if ((rc = dev_copy(m, nullptr, (size_t)m->obs * m->Z, &m->lista_wdT))) return bail(rc);
     kmpc::dict_normalize_transpose_kernel<<<(m->Z + 7) / 8, 256>>>(D->lista_dict, m->Z, m->obs, m->lista_wdT);
+    if ((rc = make_lo(m, m->lista_wdT, (size_t)m->obs * m->Z, &m->lista_wdT_lo))) return bail(rc);
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return bail(kmpc_fail_cuda(e, "kmpc_model_load kernels"));

@@ -34,6 +34,7 @@ struct GemmArgs {
   const float* mean32;
   int stat_rows_per_group;
   int stat_ld;
+  int stat_row0;       // logical index of row 0 of this launch for the statistics lookup
   float* C;            // output, row stride ldc, only columns < n_store are written
   long long ldc;
   int n_store;

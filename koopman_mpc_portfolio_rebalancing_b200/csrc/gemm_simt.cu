@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * 4 + (i >> 2) * 64 + (i & 3);
     if (m >= g.M) continue;
-    const int sg = (g.std32 && g.stat_rows_per_group > 0) ? (m + g.row0) / g.stat_rows_per_group : 0;
+    const int sg = (g.std32 && g.stat_rows_per_group > 0) ? (m + g.stat_row0) / g.stat_rows_per_group : 0;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * 4 + (j >> 2) * 64 + (j & 3);

@@ -47,6 +47,7 @@ struct Params {
   const float* bias;
   const float* addend; int ld_add;
   int act; float shrink_thr;
+  const float* std32; const float* mean32; int stat_rows_per_group; int stat_ld; int row0;   // de-standardise epilogue
   float* C; float* C_lo; long long ldc; int n_store;
 };
 
@@ -250,6 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float* crow = p.C + m * p.ldc + n0;
           float* lrow = p.C_lo ? p.C_lo + m * p.ldc + n0 : nullptr;
           const float* arow = p.addend ? p.addend + m * p.ld_add + n0 : nullptr;
+          const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (m + p.row0) / p.stat_rows_per_group : 0;
           const bool full = (n0 + 16 <= p.n_store) && ((((uintptr_t)crow) & 15) == 0);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -263,6 +265,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (arow) t += arow[j4 * 4 + j];
               }
               t = epilogue_apply(t, p.act, p.shrink_thr);
+              if (p.std32 && n < p.n_store)
+                t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + n]), p.mean32[sg * p.stat_ld + n]);
               x[j] = t;
               lo[j] = t - __uint_as_float(__float_as_uint(t) & 0xffffe000u);
             }
@@ -328,9 +332,9 @@ void set_gemm_tc_mode(int on) { g_tc_mode = on; }
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   using namespace tc;
   if (!g_tc_mode) return -100;
-  if (!g.A_lo || !g.W_lo || g.std32) return -100;
-  if (g.Nout < 64 || g.K < BK || g.M < BM) return -100;
-  if ((g.lda % 4) || (g.ldw % 4) || (g.a_group_stride % 4) || (g.ldc % 4)) return -100;
+  if (!g.A_lo || !g.W_lo) return -100;
+  if (g.Nout < 16 || g.K < BK || g.M < BM) return -100;
+  if ((g.lda % 4) || (g.ldw % 4) || (g.a_group_stride % 4)) return -100;
   if (((uintptr_t)g.A & 15) || ((uintptr_t)g.A_lo & 15) || ((uintptr_t)g.W & 15) || ((uintptr_t)g.W_lo & 15)) return -100;
   Params p;
   const bool flat = g.a_rows_per_group >= g.M + g.row0;
@@ -347,6 +351,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.k_blocks = (g.K + BK - 1) / BK;
   p.bias = g.bias; p.addend = g.addend; p.ld_add = g.ld_add; p.act = g.act; p.shrink_thr = g.shrink_thr;
   p.C = g.C; p.C_lo = g.C_lo; p.ldc = g.ldc; p.n_store = g.n_store < g.Nout ? g.n_store : g.Nout;
+  p.std32 = g.std32; p.mean32 = g.mean32; p.stat_rows_per_group = g.stat_rows_per_group; p.stat_ld = g.stat_ld; p.row0 = g.stat_row0;
 
   const long long a_off = flat ? (long long)g.row0 * g.lda
                                : (long long)(g.row0 / g.a_rows_per_group) * g.a_group_stride;

@@ -81,12 +81,14 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[32], int lan
   return v[0];
 }
 
-template <int H, int APT>
+template <int H, int APT, int NS>
 struct WarpIpm {
   static constexpr int NB = 3 * H;          // border size (R-rows, budget rows, cap rows)
-  static constexpr int SLOTS = 32 * APT;
+  static constexpr int SLOTS = NS;          // slots per row: N <= NS <= 32*APT (compile-time so that every
+                                            // shared-memory access has an immediate offset)
+  static_assert(NS <= 32 * APT && NS > 32 * (APT - 1), "slot stride does not match assets-per-lane");
   // shared-memory arrays, each [H][SLOTS]: Green factors, barrier weights, search direction, iterate
-  enum : int { QL, TL, QR, TR, GJJ, VD, FL, FR, IE, DP, DQ, DW0, DW, DSP, DSQ, DZW, DZP, DZQ,
+  enum : int { QL, TL, QR, TR, GJJ, VD, FL, FR, IE, DW, DSP, DSQ, DZW, DZP, DZQ,
                RR, ZW, WW, SP, SQ, ZP, ZQ, IW, ISP, ISQ, NARR };
   // warp-uniform per-stage scalars, also in shared memory (broadcast reads; every lane writes the same value)
   enum : int { NU, SC, ZC, DNU, DSC, DZC, IRHO, ISC, RHO, RP, CC, YR, YN, YC, NUNI };
@@ -106,8 +108,12 @@ struct WarpIpm {
   }
   __device__ __forceinline__ double& U(int arr, int k) const { return Ksm[NB * NB + NB + arr * H + k]; }
   __device__ __forceinline__ bool ok(int a) const { return lane + 32 * a < nassets; }
+  // Only lanes that own asset (a) may touch F(.,.,a): slots >= NS do not exist.  Every use is guarded by ok(a).
   __device__ __forceinline__ double& F(int arr, int k, int a) const { return sm[(arr * H + k) * SLOTS + a * 32 + lane]; }
-  __device__ __forceinline__ double phi(int k, int a) const { return (F(DQ, k, a) - F(DP, k, a)) * F(IE, k, a); }
+  __device__ __forceinline__ double dP(int k, int a) const { return F(ZP, k, a) * F(ISP, k, a); }
+  __device__ __forceinline__ double dQ(int k, int a) const { return F(ZQ, k, a) * F(ISQ, k, a); }
+  __device__ __forceinline__ double dW0(int k, int a) const { return (has_w && ok(a)) ? F(ZW, k, a) * F(IW, k, a) : 0.0; }
+  __device__ __forceinline__ double phi(int k, int a) const { return has_u ? (dQ(k, a) - dP(k, a)) * F(IE, k, a) : 0.0; }
 
   // Green's function column j (runtime) of asset a: G[l] = potential of node l, D[l] = drop across edge l, for
   // a unit current injected at node j.  Register arrays are indexed statically; j only enters predicates.
@@ -181,14 +187,14 @@ struct WarpIpm {
   __device__ __forceinline__ bool factorize() {
 #pragma unroll 1
     for (int a = 0; a < APT; ++a) {
-      const bool va = ok(a);
+      if (!ok(a)) continue;
+      const bool va = true;
       double e[H], hLv[H], hRv[H], ad[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) {
         const double iw = 1.0 / F(WW, k, a);
         F(IW, k, a) = iw;
         const double dw0 = (has_w && va) ? F(ZW, k, a) * iw : 0.0;
-        F(DW0, k, a) = dw0;
         ad[k] = dw0 + delta;
         if (has_u) {
           const double isp = 1.0 / F(SP, k, a), isq = 1.0 / F(SQ, k, a);
@@ -196,10 +202,10 @@ struct WarpIpm {
           const double dp = F(ZP, k, a) * isp, dq = F(ZQ, k, a) * isq;
           const double E = dp + dq + delta;
           const double ie = 1.0 / E;
-          F(DP, k, a) = dp; F(DQ, k, a) = dq; F(IE, k, a) = ie;
+          F(IE, k, a) = ie;
           e[k] = (4.0 * dp * dq + 2.0 * delta * (dp + dq) + delta * delta) * ie;
         } else {
-          F(DP, k, a) = 0.0; F(DQ, k, a) = 0.0; F(IE, k, a) = 1.0; e[k] = 0.0;
+          F(IE, k, a) = 1.0; e[k] = 0.0;
         }
       }
       // left sweep: hL[k] = conductance to ground seen at node k leftwards incl. ad[k]
@@ -438,9 +444,9 @@ struct WarpIpm {
             const double cpv = (use_c && has_u) ? F(DZP, k, a) : 0.0;
             const double cqv = (use_c && has_u) ? F(DZQ, k, a) : 0.0;
             F(DW, k, a) = dw[k];
-            F(DZW, k, a) = has_w ? (cwv * F(IW, k, a) - F(ZW, k, a)) - F(DW0, k, a) * dw[k] : 0.0;
+            F(DZW, k, a) = has_w ? (cwv * F(IW, k, a) - F(ZW, k, a)) - dW0(k, a) * dw[k] : 0.0;
             if (has_u) {
-              const double dp = F(DP, k, a), dq = F(DQ, k, a), ie = F(IE, k, a);
+              const double dp = dP(k, a), dq = dQ(k, a), ie = F(IE, k, a);
               const double dsp_ = (g_u[k] - (2.0 * dq + delta) * dd[k]) * ie;
               const double dsq_ = (g_u[k] + (2.0 * dp + delta) * dd[k]) * ie;
               F(DSP, k, a) = dsp_; F(DSQ, k, a) = dsq_;
@@ -531,10 +537,12 @@ struct WarpIpm {
 #pragma unroll
     for (int a = 0; a < APT; ++a) {
       const double b = (sb > 0.0) ? base[a] / sb : invN;
-      const double w1 = ok(a) ? (1.0 - eps) * b + eps * invN : 1.0;
+      const double w1 = (1.0 - eps) * b + eps * invN;
+      if (ok(a)) {
 #pragma unroll
-      for (int k = 0; k < H; ++k) F(WW, k, a) = w1;
-      if (ok(a)) absd0 += fabs(w1 - w0[a]);
+        for (int k = 0; k < H; ++k) F(WW, k, a) = w1;
+        absd0 += fabs(w1 - w0[a]);
+      }
     }
     absd0 = warp_sum(absd0);
     if (has_u) {
@@ -547,7 +555,8 @@ struct WarpIpm {
       double su0 = 0.0;
 #pragma unroll
       for (int a = 0; a < APT; ++a) {
-        const double d0 = ok(a) ? F(WW, 0, a) - w0[a] : 0.0;
+        if (!ok(a)) continue;
+        const double d0 = F(WW, 0, a) - w0[a];
         const double u0 = fabs(d0) + dl0;
 #pragma unroll
         for (int k = 0; k < H; ++k) {
@@ -555,7 +564,7 @@ struct WarpIpm {
           const double uk = (k == 0) ? u0 : dlk;
           F(SP, k, a) = uk - dk; F(SQ, k, a) = uk + dk;
         }
-        if (ok(a)) su0 += u0;
+        su0 += u0;
       }
       su0 = warp_sum(su0);
 #pragma unroll
@@ -563,8 +572,10 @@ struct WarpIpm {
     } else {
 #pragma unroll
       for (int a = 0; a < APT; ++a)
+        if (ok(a)) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) { F(SP, k, a) = 1.0; F(SQ, k, a) = 1.0; }
+          for (int k = 0; k < H; ++k) { F(SP, k, a) = 1.0; F(SQ, k, a) = 1.0; }
+        }
 #pragma unroll
       for (int k = 0; k < H; ++k) U(SC, k) = 1.0;
     }
@@ -597,22 +608,26 @@ struct WarpIpm {
       }
 #pragma unroll
       for (int a = 0; a < APT; ++a)
+        if (ok(a)) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-          F(ZW, k, a) = ok(a) ? (-F(RR, k, a) / U(RHO, k) + U(NU, k)) : 0.0;
-          F(ZP, k, a) = has_u ? 0.5 * (lam + zeta0) : 0.0;
-          F(ZQ, k, a) = F(ZP, k, a);
+          for (int k = 0; k < H; ++k) {
+            F(ZW, k, a) = -F(RR, k, a) / U(RHO, k) + U(NU, k);
+            F(ZP, k, a) = has_u ? 0.5 * (lam + zeta0) : 0.0;
+            F(ZQ, k, a) = F(ZP, k, a);
+          }
         }
     } else {
 #pragma unroll
       for (int k = 0; k < H; ++k) { U(NU, k) = 1.0; U(ZC, k) = has_c ? opt.mu0 / U(SC, k) : 0.0; }
 #pragma unroll
       for (int a = 0; a < APT; ++a)
+        if (ok(a)) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-          F(ZW, k, a) = (has_w && ok(a)) ? opt.mu0 / F(WW, k, a) : 0.0;
-          F(ZP, k, a) = has_u ? opt.mu0 / F(SP, k, a) : 0.0;
-          F(ZQ, k, a) = has_u ? opt.mu0 / F(SQ, k, a) : 0.0;
+          for (int k = 0; k < H; ++k) {
+            F(ZW, k, a) = has_w ? opt.mu0 / F(WW, k, a) : 0.0;
+            F(ZP, k, a) = has_u ? opt.mu0 / F(SP, k, a) : 0.0;
+            F(ZQ, k, a) = has_u ? opt.mu0 / F(SQ, k, a) : 0.0;
+          }
         }
     }
     const double mcount = (has_w ? (double)H * N : 0.0) + (has_u ? 2.0 * H * N : 0.0) + (has_c ? (double)H : 0.0);
@@ -671,8 +686,14 @@ struct WarpIpm {
       kkt[0] = pres; kkt[1] = dres; kkt[2] = gap;
       if (!isfinite(dres + gap)) break;
       if (pres < opt.tol && dres < opt.tol_dual && gap < opt.tol) { status = ST_OPTIMAL; break; }
+      // flat directions (curvature << delta): the dual residual crawls at ~delta*|dx| while the gap has long
+      // collapsed; the objective is converged -> "optimal_inaccurate" instead of iterating into round-off
+      if (pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6) { status = ST_INACCURATE; break; }
       if (it == opt.max_iter + 1) break;
       const double mu = gap / fmax(mcount, 1.0);
+      // endgame: primal residual and gap converged, only the dual residual along flat directions is left ->
+      // shrink the proximal term so the Newton step is no longer damped there
+      if (pres < opt.tol && gap < opt.tol) delta = fmax(0.3 * delta, 1e-9);
       __syncwarp();
       if (!factorize()) break;
       // ---- predictor (phase 0) and corrector (phase 1) share one code instance ---------------------------
@@ -751,8 +772,10 @@ struct WarpIpm {
   __device__ __forceinline__ void hold(const double (&w0)[APT]) {
 #pragma unroll
     for (int a = 0; a < APT; ++a)
+      if (ok(a)) {
 #pragma unroll
-      for (int k = 0; k < H; ++k) F(WW, k, a) = w0[a];
+        for (int k = 0; k < H; ++k) F(WW, k, a) = w0[a];
+      }
   }
 
   // maximised objective of mpc.py:104 for the plan in the WW array (fp64)

@@ -16,10 +16,10 @@ __device__ __forceinline__ float exp_cr32(float y) { return __double2float_rn(ex
 
 constexpr int kWarpsPerBlock = 1;   // one problem per warp; ~50 KB of shared memory per warp at H=5, N<=64
 
-template <int H, int APT>
+template <int H, int APT, int NS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 mpc_solve_kernel(MpcSolveArgs A) {
-  using Ipm = WarpIpm<H, APT>;
+  using Ipm = WarpIpm<H, APT, NS>;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wid = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
@@ -40,7 +40,7 @@ mpc_solve_kernel(MpcSolveArgs A) {
           if (A.yhat) r = (double)exp_cr32(A.yhat[((size_t)p * H + k) * N + i]);
           else r = exp(A.yhat64[((size_t)p * H + k) * N + i]);
         }
-        s.F(Ipm::RR, k, a) = r;
+        if (s.ok(a)) s.F(Ipm::RR, k, a) = r;
       }
     }
     const double lam = A.lam ? A.lam[p] : A.lam0;
@@ -64,10 +64,10 @@ mpc_solve_kernel(MpcSolveArgs A) {
   }
 }
 
-template <int H, int APT>
+template <int H, int APT, int NS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 backtest_kernel(BacktestArgs A) {
-  using Ipm = WarpIpm<H, APT>;
+  using Ipm = WarpIpm<H, APT, NS>;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   Ipm s;
@@ -104,7 +104,7 @@ backtest_kernel(BacktestArgs A) {
       for (int a = 0; a < APT; ++a)
 #pragma unroll
         for (int k = 0; k < H; ++k)
-          s.F(Ipm::RR, k, a) = s.ok(a) ? (double)exp_cr32(yh[k * N + lane + 32 * a]) : 1.0;
+          if (s.ok(a)) s.F(Ipm::RR, k, a) = (double)exp_cr32(yh[k * N + lane + 32 * a]);
       int iters; double kkt[3];
       const int st = s.solve(wc, N, lam, tau, A.allow_short != 0, opt, iters, kkt);
       it_total += iters;
@@ -133,11 +133,13 @@ backtest_kernel(BacktestArgs A) {
         double denom = 1.0 + port_ret;
         if (fabs(denom) < 1e-8) denom = 1e-8;
 #pragma unroll
-        for (int a = 0; a < APT; ++a)
-          wc[a] = s.ok(a) ? s.F(Ipm::WW, 0, a) * (double)__fadd_rn(1.0f, r32[a]) / denom : 0.0;   // (1.0 + f32) stays f32
+        for (int a = 0; a < APT; ++a) {
+          wc[a] = 0.0;
+          if (s.ok(a)) wc[a] = s.F(Ipm::WW, 0, a) * (double)__fadd_rn(1.0f, r32[a]) / denom;   // (1.0 + f32) stays f32
+        }
       } else {
 #pragma unroll
-        for (int a = 0; a < APT; ++a) wc[a] = s.ok(a) ? s.F(Ipm::WW, 0, a) : 0.0;
+        for (int a = 0; a < APT; ++a) { wc[a] = 0.0; if (s.ok(a)) wc[a] = s.F(Ipm::WW, 0, a); }
       }
       // ---- history row + metric accumulators ----
       if (A.history && lane == 0) {
@@ -185,26 +187,26 @@ static int blocks_per_sm_for(K kernel, size_t smem) {
   return nb < 1 ? 1 : nb;
 }
 
-template <int H, int APT>
+template <int H, int APT, int NS>
 static int launch_mpc(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
-  const size_t smem = (size_t)kWarpsPerBlock * WarpIpm<H, APT>::SMEM_DOUBLES * sizeof(double);
-  static int bps = blocks_per_sm_for(mpc_solve_kernel<H, APT>, smem);
+  const size_t smem = (size_t)kWarpsPerBlock * WarpIpm<H, APT, NS>::SMEM_DOUBLES * sizeof(double);
+  static const int bps = blocks_per_sm_for(mpc_solve_kernel<H, APT, NS>, smem);
   int blocks = (A.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = sm_count * bps;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  mpc_solve_kernel<H, APT><<<blocks, kWarpsPerBlock * 32, smem, st>>>(A);
+  mpc_solve_kernel<H, APT, NS><<<blocks, kWarpsPerBlock * 32, smem, st>>>(A);
   return (int)cudaGetLastError();
 }
-template <int H, int APT>
+template <int H, int APT, int NS>
 static int launch_bt(const BacktestArgs& A, int sm_count, cudaStream_t st) {
-  const size_t smem = (size_t)kWarpsPerBlock * WarpIpm<H, APT>::SMEM_DOUBLES * sizeof(double);
-  static int bps = blocks_per_sm_for(backtest_kernel<H, APT>, smem);
+  const size_t smem = (size_t)kWarpsPerBlock * WarpIpm<H, APT, NS>::SMEM_DOUBLES * sizeof(double);
+  static const int bps = blocks_per_sm_for(backtest_kernel<H, APT, NS>, smem);
   int blocks = (A.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int cap = sm_count * bps;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  backtest_kernel<H, APT><<<blocks, kWarpsPerBlock * 32, smem, st>>>(A);
+  backtest_kernel<H, APT, NS><<<blocks, kWarpsPerBlock * 32, smem, st>>>(A);
   return (int)cudaGetLastError();
 }
 

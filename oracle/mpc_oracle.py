@@ -398,9 +398,19 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
         if res[0] < tol and res[1] < tol_dual and gap < tol:
             status = STATUS_OPTIMAL
             break
+        # flat directions (curvature << delta): the proximal term makes the dual residual crawl at ~delta*|dx|
+        # while the gap has long collapsed; the objective is converged, so stop as "optimal_inaccurate" instead
+        # of iterating into round-off (mpc.py:113 accepts that status)
+        if res[0] < tol and gap < 1e-6 * tol and res[1] < 1e-6:
+            status = STATUS_INACCURATE
+            break
         if it == max_iter + 1:
             break
         mu = gap / max(m, 1)
+        if res[0] < tol and gap < tol:
+            # endgame: primal residual and gap have converged, only the dual residual along flat directions is
+            # left; shrink the proximal term so that the Newton step is no longer damped there
+            delta = max(0.3 * delta, 1e-9)
 
         Dw0 = zw / w if has_w else zHN
         beta = 1.0 / rho ** 2

@@ -122,3 +122,30 @@ def test_lista_window_forecast_large_latent():
     spec = fo.ModelSpec(kind="lista", linear_encoder=True, alpha=5e-3, L=L, loops=10, act="relu", last_relu=False)
     want = fo.forecast(do.time_delay_embedding(do.standardize(lr, mean, std), d), sd, spec, H, N, mean, std)
     assert rowwise_rel(y, want) < FORECAST_RTOL
+
+
+def test_multi_chunk_forecast_with_partial_last_chunk():
+    """More rows than one activation chunk (32768) and a partial last chunk, per-path statistics, tensor-core
+    eligible widths: every row must still match the oracle (guards the chunk / group addressing)."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df, model as km, synthetic
+    from oracle import forecast_oracle as fo, data_oracle as do
+    rng = np.random.default_rng(11)
+    B, N, d, H, Z = 181, 12, 8, 3, 64
+    rpp = 190
+    T = rpp + d - 1
+    lr = rng.standard_normal((B, T, N)) * 0.012
+    mean = rng.normal(3e-4, 1e-4, (B, N)); std = rng.uniform(0.008, 0.02, (B, N))
+    sd = synthetic.generic_km_weights(9, N * d, [128, 128], Z)
+    m = km.make_model(km.model_config("GenericKM", Z, [128, 128], enc_bias=True), N * d)
+    m.load_state_dict(sd)
+    z = df.standardize_device(lr, mean, std)
+    y = m.forecast_series(z, torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda(), N, d, 0, 0, rpp, H).cpu().numpy()
+    assert B * rpp > 32768
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    worst = 0.0
+    for b in [0, 1, 90, 171, 172, 173, 179, 180]:          # paths on both sides of the chunk boundary
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)[:rpp]
+        want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
+        worst = max(worst, rowwise_rel(y[b], want))
+    assert worst < FORECAST_RTOL, worst
