@@ -47,6 +47,8 @@ int dispatch_backtest(const BacktestArgs& A, int H, int sm_count, cudaStream_t s
 
 namespace kmpc {
 int mpc_variant_supported(int H, int N);
+void set_mpc_mode(int mode);
+int get_mpc_mode();
 int launch_standardize(const double* y, const double* mean, const double* sd, int spp, int B, int T, int N, float* out,
                        int ld, int sm_count, cudaStream_t st);
 int launch_embed_gather(const float* data, int ld, int B, int T, int N, int d, float* out, int sm_count, cudaStream_t st);

@@ -6,6 +6,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["cta", "warp"], autouse=True)
+def mpc_kernel_layout(request):
+    """every test runs against both kernel layouts: one thread block per problem (default) and one warp per problem"""
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    _capi.lib().kmpc_set_mpc_kernel(1 if request.param == "cta" else 0)
+    yield request.param
+    _capi.lib().kmpc_set_mpc_kernel(1)
+
+
 def _mods():
     import torch
     from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt

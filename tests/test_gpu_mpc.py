@@ -7,6 +7,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["cta", "warp"], autouse=True)
+def mpc_kernel_layout(request):
+    """every test runs against both kernel layouts: one thread block per problem (default) and one warp per problem"""
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    _capi.lib().kmpc_set_mpc_kernel(1 if request.param == "cta" else 0)
+    yield request.param
+    _capi.lib().kmpc_set_mpc_kernel(1)
+
 OBJ_RTOL = 1e-6      # |obj_gpu - obj_oracle| <= OBJ_RTOL * max(|obj_oracle|, OBJ_FLOOR)
 OBJ_FLOOR = 1e-3     # objectives are sums of daily log-growth; below 1e-3 the bar is absolute 1e-9
 W_ATOL = 1e-4
