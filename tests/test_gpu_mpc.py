@@ -111,3 +111,22 @@ def test_unsupported_shape_fails_loudly():
     from koopman_mpc_portfolio_rebalancing_b200 import _capi
     with pytest.raises(_capi.KmpcError):
         mpc.solve_mpc_log_utility(np.ones(700) / 700, np.zeros((5, 700), np.float32), mpc.MPCConfig())
+
+
+def test_config5_shape_100_assets():
+    """N = 100, H = 5 (Monte-Carlo stress-test shape, BASELINE config 5): CTA layout with four lane groups"""
+    torch, mpc, mo = _mods()
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    if _capi.lib().kmpc_mpc_supported(5, 100) != 1:
+        pytest.skip("no kernel variant for N=100 in this layout")
+    rng = np.random.default_rng(77)
+    P, N, H = 12, 100, 5
+    w0 = np.stack([rng.dirichlet(np.ones(N) * 0.5) for _ in range(P)])
+    y = (3e-4 + rng.standard_normal((P, H, N)) * 0.01).astype(np.float32)
+    out = mpc.solve_mpc_batch(torch.from_numpy(w0).cuda(), torch.from_numpy(y).cuda())
+    W = out["w"].cpu().numpy(); val = out["value"].cpu().numpy(); st = out["status"].cpu().numpy()
+    for p in range(P):
+        ref = mo.solve_structured(w0[p], y[p], 1e-3, 0.2)
+        assert st[p] == 0 and ref.status == 0
+        assert abs(val[p] - ref.value) <= OBJ_RTOL * max(abs(ref.value), OBJ_FLOOR)
+        assert np.abs(W[p] - ref.w).max() < W_ATOL
