@@ -195,7 +195,7 @@ def run_gpu_arm(args):
     lr_h = torch.from_numpy(lr).pin_memory(); mean_h = torch.from_numpy(mean).pin_memory(); std_h = torch.from_numpy(std).pin_memory()
     lr_d, mean_d, std_d = lr_h.to(dev), mean_h.to(dev), std_h.to(dev)
     handle = _capi.Handle.get(local)
-    _capi.lib().kmpc_set_mpc_kernel(1 if args.mpc_kernel == "cta" else 0)
+    _capi.lib().kmpc_set_mpc_kernel({"lane": 2, "cta": 1, "warp": 0}[args.mpc_kernel])
     B_total = B * world
 
     def step_device(timings=None):
@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--paths", type=int, default=0, help="backtests per GPU (default: the workload's)")
     ap.add_argument("--cpu-decisions", type=int, default=96, help="decisions in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mpc-kernel", default="cta", choices=["cta", "warp"], help="MPC kernel layout (diagnostics)")
+    ap.add_argument("--mpc-kernel", default="lane", choices=["lane", "cta", "warp"], help="MPC kernel layout (diagnostics)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -62,8 +62,9 @@ int kmpc_destroy(kmpc_handle* h);
 int64_t kmpc_launch_count(const kmpc_handle* h);
 /* 1 if an MPC kernel variant for (H, N) is compiled in */
 int kmpc_mpc_supported(int H, int N);
-/* diagnostics: MPC kernel layout, process-wide: 1 = one thread block per problem, thread = (stage, asset)
- * [default], 0 = one warp per problem.  Same algorithm and results. */
+/* diagnostics: MPC kernel layout, process-wide: 2 = one block per problem, thread = asset, stages in registers
+ * [default]; 1 = one block per problem, thread = (stage, asset); 0 = one warp per problem.  Same central path and
+ * results within the parity tolerances in all three. */
 int kmpc_set_mpc_kernel(int mode);
 
 /* ---------------------------------------------------------------------------------------------

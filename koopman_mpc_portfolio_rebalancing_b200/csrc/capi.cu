@@ -65,7 +65,11 @@ int kmpc_destroy(kmpc_handle* h) {
 
 int64_t kmpc_launch_count(const kmpc_handle* h) { return h ? h->launches : 0; }
 int kmpc_mpc_supported(int H, int N) { return kmpc::mpc_variant_supported(H, N); }
-int kmpc_set_mpc_kernel(int mode) { kmpc::set_mpc_mode(mode ? 1 : 0); return KMPC_OK; }
+int kmpc_set_mpc_kernel(int mode) {
+  if (mode < 0 || mode > 2) return fail(KMPC_E_INVALID, "kmpc_set_mpc_kernel: mode must be 0, 1 or 2");
+  kmpc::set_mpc_mode(mode);
+  return KMPC_OK;
+}
 
 int kmpc_standardize(kmpc_handle* h, const double* logret, const double* mean, const double* std, int stats_per_path,
                      int B, int T, int N, float* out, int ld_out, void* stream) {

@@ -1,0 +1,737 @@
+// Lane-per-asset layout of the fp64 interior-point MPC solver (same central path and Newton system as
+// mpc_ipm.cuh / oracle/mpc_oracle.py::solve_structured(apply="sweep"); see mpc_ipm.cuh for the program).
+//
+// Why a third layout (profiles/r1_backtest_cta_kernel.txt): the warp- and CTA-per-problem kernels execute
+// ~350 k warp instructions per decision of which 17 % are fp64 math; the rest is predication on a runtime stage
+// index, O(H^2) Green's-function columns rebuilt for every matrix-vector product, full-precision divisions, a
+// Cholesky that makes ~105 dependent shared-memory round trips, and block-wide barriers (48 % of all stalls).
+//
+//   thread i  = asset i; block = G warps = one problem (N <= 32 G).  Every loop over the H stages is unrolled:
+//               the iterate (R, w, sp, sq, zw, zp, zq), the element-wise barrier factors and the search direction
+//               of all stages of one asset are statically indexed REGISTERS of its thread; H independent
+//               dependency chains per thread give the ILP that the low occupancy needs.
+//   M0^{-1}   = the per-asset SPD tridiagonal (path network) is applied in O(H) by two Norton-equivalent sweeps
+//               (left sources JL, right sources JR) and a two-sided split at every edge: node potentials AND the
+//               drops across the edges come out of products of factors in [0,1] without differencing potentials
+//               (oracle: _path_sweep; as accurate as the explicit Green's functions, 9 H flops instead of ~7 H^2).
+//   border K  = the <= 3H x 3H Schur complement needs the explicit entries sum_i c_i G_i[l,j]: every thread
+//               emits its <= 3H^2 + 3H(H+1)/2 products into a [entry][thread] shared-memory tile (conflict free),
+//               lane e of every warp adds up row e over its 32 columns (16 LDS.128 + 32 DADD for 32 entries; a
+//               shuffle butterfly costs ~8 instructions per entry), warp 0 combines the G partials.
+//   Cholesky  = warp 0, lane = row, the row lives in registers, columns are exchanged by shuffles: 15 dependent
+//               steps instead of 105 dependent shared-memory round trips; the factor goes back to shared memory
+//               for the two triangular solves of each Newton system.
+//   division  = MUFU.RCP64H + one third-order Newton step (4 instructions, <= 2 ulp) for the ~40 reciprocals
+//               per asset and iteration; the step-length ratio tests multiply by reciprocals and keep a running
+//               maximum (no divergent division).
+#pragma once
+#include "mpc_ipm.cuh"
+
+namespace kmpc {
+
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // ~20 correct bits
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);                            // relative error ~e^3
+}
+
+// Position r * NB + c (lower triangle) of the K entries in the order LaneIpm::assemble_K emits them.
+template <int H>
+struct KMap {
+  static constexpr int NB = 3 * H;
+  static constexpr int N1 = H * H + H * (H + 1);                 // entries without the cap rows
+  static constexpr int NK = 3 * H * H + 3 * H * (H + 1) / 2;
+  int rc[NK];
+  constexpr KMap() : rc() {
+    int e = 0;
+    for (int j = 0; j < H; ++j)
+      for (int l = j; l < H; ++l) {
+        rc[e++] = (H + l) * NB + j;                              // (1t_l, Rt_j)
+        if (l != j) rc[e++] = (H + j) * NB + l;                  // (1t_j, Rt_l)
+        rc[e++] = l * NB + j;                                    // (Rt_l, Rt_j)
+        rc[e++] = (H + l) * NB + H + j;                          // (1t_l, 1t_j)
+      }
+    for (int l = 0; l < H; ++l)
+      for (int j = 0; j < H; ++j) {
+        rc[e++] = (2 * H + l) * NB + j;                          // (et_l, Rt_j)
+        rc[e++] = (2 * H + l) * NB + H + j;                      // (et_l, 1t_j)
+      }
+    for (int j = 0; j < H; ++j)
+      for (int l = j; l < H; ++l) rc[e++] = (2 * H + l) * NB + 2 * H + j;   // (et_l, et_j)
+  }
+};
+template <int H>
+__device__ __constant__ KMap<H> g_kmap{};
+
+template <int H, int G>
+struct LaneIpm {
+  static constexpr int NT = 32 * G;                 // threads per problem
+  static constexpr int NB = 3 * H;
+  static constexpr int LD = NT + 2;                 // row stride of the reduction tile: 16-byte rows, LD/2 odd
+  static constexpr int KB = (NB + 1 > 30) ? 32 : 30;   // entries per K-assembly batch (<= 32)
+  static constexpr int NK = KMap<H>::NK, N1 = KMap<H>::N1;
+  static_assert(NB + 1 <= 32, "H too large: the border must fit one row per lane");
+
+  // ---- shared memory of one problem (doubles) -------------------------------------------------------------------
+  enum : int { F_QL, F_TL, F_QR, F_TR, F_GJJ, F_VD, F_FL, F_FR, NFAC };    // sweep factors [H][NT]
+  enum : int { T_CW, T_CP, T_CQ, NTGT };                                    // complementarity targets [H][NT]
+  enum : int { U_NU, U_SC, U_ZC, U_RHO, U_IRHO, U_ISC, U_RP, U_CC, NUNI };
+  static constexpr int OFF_FAC = 0;
+  static constexpr int OFF_TILE = OFF_FAC + NFAC * H * NT;                  // reduction tile, rows of LD doubles
+  static constexpr int SMALL_ROWS = NB + 1;                                 // rows usable while the targets are live
+  static constexpr int TILE_A = KB * LD;
+  static constexpr int TILE_B = SMALL_ROWS * LD + NTGT * H * NT;
+  static constexpr int TILE_DOUBLES = ((TILE_A > TILE_B ? TILE_A : TILE_B) + 1) & ~1;
+  static constexpr int OFF_TGT = OFF_TILE + TILE_DOUBLES - NTGT * H * NT;  // targets = tail of the tile
+  static constexpr int OFF_K = OFF_TILE + TILE_DOUBLES;                     // [NB*NB] K / Cholesky factor, [NB] 1/diag
+  static constexpr int OFF_T = OFF_K + NB * NB + NB + ((NB * NB + NB) & 1); // [32] border right-hand side / solution
+  static constexpr int OFF_P = OFF_T + 32;                                  // [2][G][32] per-warp partials
+  static constexpr int OFF_U = OFF_P + 2 * G * 32;                          // [NUNI][H] stage scalars
+  static constexpr int OFF_FLAG = OFF_U + NUNI * H + ((NUNI * H) & 1);      // [2]
+  static constexpr int SMEM_DOUBLES = OFF_FLAG + 2;
+
+  // ---- registers of thread i (asset i) ----------------------------------------------------------------------------
+  double R[H], w[H], sp[H], sq[H], zw[H], zp[H], zq[H];      // iterate
+  double iw[H], isp[H], isq[H], ie[H], ph[H];                // element-wise factors of the current iterate
+  double* sm;
+  int tid, lane, warp, psel;
+  bool valid, has_w, has_u, has_c;
+  double lam, tau, delta;
+
+  __device__ __forceinline__ void bind(double* smem, int n_assets) {
+    sm = smem; tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; psel = 0;
+    valid = tid < n_assets;
+  }
+  __device__ __forceinline__ double& FAC(int arr, int k) const { return sm[OFF_FAC + (arr * H + k) * NT + tid]; }
+  __device__ __forceinline__ double& TGT(int arr, int k) const { return sm[OFF_TGT + (arr * H + k) * NT + tid]; }
+  __device__ __forceinline__ double& U(int arr, int k) const { return sm[OFF_U + arr * H + k]; }
+  __device__ __forceinline__ void sync() const {
+    if (G == 1) __syncwarp(); else __syncthreads();
+  }
+
+  // ---- reductions over the threads of the problem --------------------------------------------------------------
+  // Sum of row `lane` of the tile over this warp's 32 columns.
+  __device__ __forceinline__ double row_partial(int rows) const {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (lane < rows) {
+      const double2* p = reinterpret_cast<const double2*>(sm + OFF_TILE + lane * LD + 32 * warp);
+#pragma unroll
+      for (int m = 0; m < 16; m += 2) {
+        const double2 a = p[m], b = p[m + 1];
+        s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
+      }
+    }
+    return (s0 + s1) + (s2 + s3);
+  }
+  // NV per-thread values (0 in padding threads) -> per-warp partial sums in P; ptotal(e) then gives the total of
+  // entry e (same bits in every thread) until the next tile_reduce.
+  template <int NV>
+  __device__ __forceinline__ void tile_reduce(const double (&v)[NV]) {
+    static_assert(NV <= SMALL_ROWS, "tile too small");
+#pragma unroll
+    for (int e = 0; e < NV; ++e) sm[OFF_TILE + e * LD + tid] = v[e];
+    sync();
+    const double s = row_partial(NV);
+    psel ^= 1;
+    sm[OFF_P + psel * G * 32 + warp * 32 + lane] = s;
+    sync();
+  }
+  __device__ __forceinline__ double ptotal(int e) const {
+    const double* P = sm + OFF_P + psel * G * 32;
+    double t = P[e];
+#pragma unroll
+    for (int g = 1; g < G; ++g) t += P[g * 32 + e];
+    return t;
+  }
+  template <int NV>
+  __device__ __forceinline__ void block_sum(const double (&v)[NV], double (&out)[NV]) {
+    tile_reduce<NV>(v);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) out[e] = ptotal(e);
+  }
+  // one or two values per thread -> block-wide max (shuffle butterfly, then the G partials)
+  __device__ __forceinline__ void block_max2(double& a, double& b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fmax(a, shfl_xor_d(a, o));
+      b = fmax(b, shfl_xor_d(b, o));
+    }
+    if (G > 1) {
+      psel ^= 1;
+      double* P = sm + OFF_P + psel * G * 32;
+      if (lane == 0) { P[warp * 32] = a; P[warp * 32 + 1] = b; }
+      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < G; ++g) { a = fmax(a, P[g * 32]); b = fmax(b, P[g * 32 + 1]); }
+    }
+  }
+  __device__ __forceinline__ double block_sum1(double a) {
+    a = warp_sum(a);
+    if (G > 1) {
+      psel ^= 1;
+      double* P = sm + OFF_P + psel * G * 32;
+      if (lane == 0) P[warp * 32] = a;
+      __syncthreads();
+      a = P[0];
+#pragma unroll
+      for (int g = 1; g < G; ++g) a += P[g * 32];
+    }
+    return a;
+  }
+
+  // ---- M0^{-1}: two-sided sweeps (oracle: _path_sweep) ---------------------------------------------------------
+  __device__ __forceinline__ void m0_apply(const double (&gw)[H], const double (&pg)[H], double (&dw)[H],
+                                           double (&dd)[H]) const {
+    double JL[H], JR[H], inc[H];
+    JL[0] = gw[0] - pg[0];
+#pragma unroll
+    for (int k = 1; k < H; ++k) JL[k] = fma(FAC(F_TL, k), JL[k - 1], fma(-FAC(F_QL, k), pg[k], gw[k]));
+    JR[H - 1] = gw[H - 1]; inc[H - 1] = 0.0;
+#pragma unroll
+    for (int k = H - 1; k >= 1; --k) {
+      inc[k - 1] = fma(FAC(F_TR, k), JR[k], FAC(F_QR, k) * pg[k]);
+      JR[k - 1] = gw[k - 1] + inc[k - 1];
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      dw[k] = FAC(F_GJJ, k) * (JL[k] + inc[k]);
+      double t = fma(FAC(F_FL, k), JR[k], -pg[k]);
+      if (k > 0) t = fma(-FAC(F_FR, k), JL[(k > 0) ? k - 1 : 0], t);
+      dd[k] = FAC(F_VD, k) * t;
+    }
+  }
+
+  // ---- factorisation ---------------------------------------------------------------------------------------------
+  // One batch of the K assembly is complete in the tile: add up, combine the warps, scatter into K.
+  __device__ __forceinline__ void flush_batch(int first, int count) {
+    sync();
+    double s = row_partial(count);
+    if (G > 1) {
+      psel ^= 1;
+      double* P = sm + OFF_P + psel * G * 32;
+      if (warp > 0) P[warp * 32 + lane] = s;
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll
+        for (int g = 1; g < G; ++g) s += P[g * 32 + lane];
+      }
+    } else {
+      __syncwarp();
+    }
+    if (warp == 0 && lane < count) sm[OFF_K + g_kmap<H>.rc[first + lane]] = s;
+  }
+
+  __device__ __forceinline__ bool factorize() {
+    double ad[H], e[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      iw[k] = rcp_fast(w[k]);
+      ad[k] = (has_w ? zw[k] * iw[k] : 0.0) + delta;
+      if (has_u) {
+        isp[k] = rcp_fast(sp[k]); isq[k] = rcp_fast(sq[k]);
+        const double dp = zp[k] * isp[k], dq = zq[k] * isq[k];
+        const double s = dp + dq;
+        ie[k] = rcp_fast(s + delta);
+        ph[k] = (dq - dp) * ie[k];
+        e[k] = fma(4.0 * dp, dq, fma(2.0 * delta, s, delta * delta)) * ie[k];
+      } else { isp[k] = 1.0; isq[k] = 1.0; ie[k] = 1.0; ph[k] = 0.0; e[k] = 0.0; }
+    }
+    // conductance sweeps (per thread, sequential in the stage index by nature)
+    double hL[H], hR[H], qL[H], tL[H], qR[H], tR[H], gjj[H], vd[H], fL[H], fR[H];
+    qL[0] = 1.0; tL[0] = 0.0; hL[0] = ad[0] + e[0];
+#pragma unroll
+    for (int l = 1; l < H; ++l) {
+      const double inv = rcp_fast(e[l] + hL[l - 1]);
+      qL[l] = hL[l - 1] * inv; tL[l] = e[l] * inv;
+      hL[l] = fma(e[l], qL[l], ad[l]);
+    }
+    hR[H - 1] = ad[H - 1]; qR[0] = 0.0; tR[0] = 0.0;
+#pragma unroll
+    for (int l = H - 1; l >= 1; --l) {
+      const double inv = rcp_fast(e[l] + hR[l]);
+      qR[l] = hR[l] * inv; tR[l] = e[l] * inv;
+      hR[l - 1] = fma(e[l], qR[l], ad[l - 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const double gR = (k + 1 < H) ? e[(k + 1 < H) ? k + 1 : 0] * qR[(k + 1 < H) ? k + 1 : 0] : 0.0;
+      gjj[k] = rcp_fast(hL[k] + gR);
+      fL[k] = 1.0; fR[k] = 0.0;
+      if (k > 0) {
+        const double inv = rcp_fast(hL[(k > 0) ? k - 1 : 0] + hR[k]);
+        fL[k] = hL[(k > 0) ? k - 1 : 0] * inv; fR[k] = hR[k] * inv;
+      }
+      vd[k] = rcp_fast(fma(hR[k], fL[k], e[k]));
+      if (!valid) { gjj[k] = 0.0; vd[k] = 0.0; ie[k] = 0.0; }     // padding lanes contribute exact zeros everywhere
+      FAC(F_QL, k) = qL[k]; FAC(F_TL, k) = tL[k]; FAC(F_QR, k) = qR[k]; FAC(F_TR, k) = tR[k];
+      FAC(F_GJJ, k) = gjj[k]; FAC(F_VD, k) = vd[k]; FAC(F_FL, k) = fL[k]; FAC(F_FR, k) = fR[k];
+    }
+    // ---- border matrix: emit the entries in KMap order, KB at a time --------------------------------------------
+    if (warp == 0) {                                 // clear K (rows >= 2H stay identity when there is no cap)
+      for (int q = lane; q < NB * NB; q += 32) sm[OFF_K + q] = (q / NB == q % NB) ? 1.0 : 0.0;
+    }
+    double* tile = sm + OFF_TILE + tid;
+    int en = 0;                                      // compile-time after unrolling
+    auto emit = [&](double val) {
+      tile[(en % KB) * LD] = val;
+      ++en;
+    };
+#define KMPC_FLUSH_IF_FULL()                                             \
+    if (en % KB == 0) flush_batch(en - KB, KB);
+    double Gm[H][H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      double g = gjj[j];
+#pragma unroll
+      for (int l = j; l < H; ++l) {
+        if (l > j) g *= tR[l];
+        Gm[l][j] = g;
+        emit(R[j] * g); KMPC_FLUSH_IF_FULL();
+        if (l != j) { emit(R[l] * g); KMPC_FLUSH_IF_FULL(); }
+        emit(R[l] * R[j] * g); KMPC_FLUSH_IF_FULL();
+        emit(g); KMPC_FLUSH_IF_FULL();
+      }
+    }
+    if (has_c) {
+#pragma unroll
+      for (int l = 0; l < H; ++l) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          // D[l][j]: drop across edge l for a unit injection at node j
+          const double D = (l <= j) ? Gm[j][l] * qL[l] : -Gm[(l > 0) ? l - 1 : 0][j] * qR[l];
+          const double dm = -ph[l] * D;
+          emit(dm * R[j]); KMPC_FLUSH_IF_FULL();
+          emit(dm); KMPC_FLUSH_IF_FULL();
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        double v = vd[j] * fL[j];
+#pragma unroll
+        for (int l = j; l < H; ++l) {
+          double ddv;
+          if (l == j) ddv = vd[j];
+          else { ddv = -v * qR[l]; v *= tR[l]; }
+          double val = ph[l] * ph[j] * ddv;
+          if (l == j) val += ie[l];
+          emit(val); KMPC_FLUSH_IF_FULL();
+        }
+      }
+      if (en % KB != 0) flush_batch(en - en % KB, en % KB);
+    } else {
+      if (en % KB != 0) flush_batch(en - en % KB, en % KB);
+    }
+#undef KMPC_FLUSH_IF_FULL
+    sync();
+    // ---- Cholesky by warp 0: lane = row, row in registers, columns exchanged by shuffles ----------------------
+    if (warp == 0) {
+      const int nb = has_c ? 3 * H : 2 * H;
+      double a[NB];
+      const int r = (lane < NB) ? lane : NB - 1;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) a[c] = (c <= lane) ? sm[OFF_K + r * NB + c] : 0.0;
+      {
+        double add = 0.0;
+        if (lane < H) { const double rho = U(U_RHO, lane); add = rho * rho; }                       // 1/beta_k
+        if (has_c && lane >= 2 * H && lane < NB) add = U(U_SC, lane - 2 * H) * rcp_fast(U(U_ZC, lane - 2 * H));
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (c == lane) a[c] += add;
+      }
+      bool pd = true;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const double djj = shfl_d(a[j], j);
+        if (!(djj > 0.0) && j < nb) pd = false;
+        const double inv = rsqrt(djj);
+        const double l = a[j] * inv;                         // L[lane][j] (lanes >= j)
+        a[j] = l;
+        if (lane == j) sm[OFF_K + NB * NB + j] = inv;
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c) a[c] = fma(-l, shfl_d(l, c), a[c]);
+      }
+      if (lane < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (c <= lane) sm[OFF_K + lane * NB + c] = a[c];
+      }
+      if (lane == 0) sm[OFF_FLAG] = pd ? 1.0 : 0.0;
+    }
+    sync();
+    return sm[OFF_FLAG] > 0.5;
+  }
+
+  // t (OFF_T) <- K^{-1} t by warp 0
+  __device__ __forceinline__ void k_solve_shared() {
+    if (warp == 0) {
+      const int r = (lane < NB) ? lane : NB - 1;
+      double Lr[NB], Lc[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        Lr[j] = (j < lane && lane < NB) ? sm[OFF_K + r * NB + j] : 0.0;          // L[lane][j]
+        Lc[j] = (j > lane && lane < NB) ? sm[OFF_K + j * NB + r] : 0.0;          // L[j][lane]
+      }
+      const double myinv = (lane < NB) ? sm[OFF_K + NB * NB + r] : 0.0;
+      double t = (lane < NB) ? sm[OFF_T + r] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {                       // forward: L y = t
+        const double yj = shfl_d(t * myinv, j);
+        t = (lane == j) ? yj : fma(-Lr[j], yj, t);
+      }
+#pragma unroll
+      for (int j = NB - 1; j >= 0; --j) {                  // backward: L' x = y
+        const double xj = shfl_d(t * myinv, j);
+        t = (lane == j) ? xj : fma(-Lc[j], xj, t);
+      }
+      if (lane < NB) sm[OFF_T + lane] = t;
+    }
+  }
+
+  // One Newton solve; on return dw/dsp/dsq/dzw/dzp/dzq hold the direction of my asset, the stage scalars
+  // (dnu, dsc, dzc) of stage tid are returned to the owner threads tid < H, and (rp_, rd_) are my largest primal / dual step ratios -dv/v.
+  __device__ __forceinline__ void newton(bool use_c, double (&dw)[H], double (&dsp)[H], double (&dsq)[H],
+                                         double (&dzw)[H], double (&dzp)[H], double (&dzq)[H], double& dnu, double& dsc,
+                                         double& dzc, double& rp_, double& rd_) {
+    double gw[H], gu[H], pg[H], tq[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      double gwk = fma(R[k], U(U_IRHO, k), -U(U_NU, k));
+      double guk = 0.0;
+      tq[k] = 0.0;
+      if (use_c && has_w) gwk = fma(TGT(T_CW, k), iw[k], gwk);
+      if (has_u) {
+        double a1 = 0.0, a2 = 0.0;
+        if (use_c) { a1 = TGT(T_CP, k) * isp[k]; a2 = TGT(T_CQ, k) * isq[k]; }
+        tq[k] = a1 - a2;
+        guk = -lam + a1 + a2;
+        if (has_c) guk = fma(-U(U_CC, k), U(U_ISC, k), guk);
+      }
+      gw[k] = gwk; gu[k] = guk;
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      gw[k] -= tq[k];
+      if (k + 1 < H) gw[k] += tq[(k + 1 < H) ? k + 1 : 0];
+      pg[k] = ph[k] * gu[k];
+    }
+    double dd[H];
+    m0_apply(gw, pg, dw, dd);
+    {
+      double v[NB];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        v[k] = R[k] * dw[k];                                 // padding lanes: dw = dd = ie = 0
+        v[H + k] = dw[k];
+        v[2 * H + k] = has_c ? fma(gu[k], ie[k], -ph[k] * dd[k]) : 0.0;
+      }
+      tile_reduce<NB>(v);
+      if (tid < NB) {
+        double t = ptotal(tid);
+        if (tid >= H && tid < 2 * H) t += U(U_RP, tid - H);  // t[H+k] = sum dw0 - q, q = -rp
+        sm[OFF_T + tid] = t;
+      }
+    }
+    sync();
+    k_solve_shared();
+    sync();
+    dnu = 0.0; dsc = 0.0; dzc = 0.0;
+    if (tid < H) {                                           // stage scalars stay with their owner threads
+      const double yC = has_c ? sm[OFF_T + 2 * H + tid] : 0.0;
+      dnu = sm[OFF_T + H + tid];
+      if (has_c) {
+        dsc = -yC * U(U_SC, tid) * rcp_fast(U(U_ZC, tid));
+        dzc = fma(U(U_CC, tid), U(U_ISC, tid), -U(U_ZC, tid)) + yC;
+      }
+    }
+    double geff[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      gw[k] -= fma(sm[OFF_T + k], R[k], sm[OFF_T + H + k]);
+      geff[k] = gu[k] - (has_c ? sm[OFF_T + 2 * H + k] : 0.0);
+      pg[k] = ph[k] * geff[k];
+    }
+    m0_apply(gw, pg, dw, dd);
+    double rp = 0.0, rd = 0.0;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        if (has_w) {
+          const double cw = use_c ? TGT(T_CW, k) : 0.0;
+          dzw[k] = fma(iw[k], fma(-zw[k], dw[k], cw), -zw[k]);
+          rp = fmax(rp, -dw[k] * iw[k]);
+          rd = fmax(rd, -dzw[k] * rcp_fast(zw[k]));
+        } else dzw[k] = 0.0;
+        if (has_u) {
+          const double cp = use_c ? TGT(T_CP, k) : 0.0, cq = use_c ? TGT(T_CQ, k) : 0.0;
+          const double dp = zp[k] * isp[k], dq = zq[k] * isq[k];
+          dsp[k] = fma(-fma(2.0, dq, delta), dd[k], geff[k]) * ie[k];
+          dsq[k] = fma(fma(2.0, dp, delta), dd[k], geff[k]) * ie[k];
+          dzp[k] = fma(isp[k], fma(-zp[k], dsp[k], cp), -zp[k]);
+          dzq[k] = fma(isq[k], fma(-zq[k], dsq[k], cq), -zq[k]);
+          rp = fmax(rp, fmax(-dsp[k] * isp[k], -dsq[k] * isq[k]));
+          rd = fmax(rd, fmax(-dzp[k] * rcp_fast(zp[k]), -dzq[k] * rcp_fast(zq[k])));
+        } else { dsp[k] = 0.0; dsq[k] = 0.0; dzp[k] = 0.0; dzq[k] = 0.0; }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < H; ++k) { dw[k] = 0.0; dsp[k] = 0.0; dsq[k] = 0.0; dzw[k] = 0.0; dzp[k] = 0.0; dzq[k] = 0.0; }
+    }
+    if (has_c && tid < H) {
+      rp = fmax(rp, -dsc * U(U_ISC, tid));
+      rd = fmax(rd, -dzc * rcp_fast(U(U_ZC, tid)));
+    }
+    rp_ = rp; rd_ = rd;
+  }
+
+  // Solve one problem.  R[] (gross returns of my asset, all stages) is set; w0 = my current weight.
+  // Returns the status; w[] holds my entries of the plan (w0 in every stage on failure).
+  __device__ __forceinline__ int solve(double w0, int N, double lam_, double tau_, bool allow_short,
+                                       const IpmOptions& opt, int& iters, double (&kkt)[3]) {
+    lam = lam_; tau = tau_; delta = opt.delta;
+    has_u = (lam > 0.0) || (tau > 0.0);
+    has_c = has_u && (tau > 0.0);
+    has_w = !allow_short;
+    iters = 0;
+    kkt[0] = kkt[1] = kkt[2] = CUDART_NAN;
+    if (!valid) {
+      w0 = 0.0;
+#pragma unroll
+      for (int k = 0; k < H; ++k) R[k] = 1.0;
+    }
+    // ---- screening, initial point (oracle/mpc_oracle.py::_initial_point) --------------------------------------
+    const double base = valid ? (allow_short ? w0 : fmax(w0, 0.0)) : 0.0;
+    double mxR[H];
+    {
+      bool okv = isfinite(w0);
+#pragma unroll
+      for (int k = 0; k < H; ++k) okv = okv && isfinite(R[k]) && (R[k] > 0.0);
+      double bad = okv ? 0.0 : 1.0, dummy = 0.0;
+      block_max2(bad, dummy);
+      if (bad > 0.0) {
+#pragma unroll
+        for (int k = 0; k < H; ++k) w[k] = w0;
+        return ST_NONFINITE;
+      }
+    }
+    const double sb = block_sum1(base);
+    const double invN = 1.0 / (double)N;
+    const double eps = (tau <= 0.0) ? 0.1 : fmin(0.1, tau / 8.0);
+    const double b0 = (sb > 0.0) ? base / sb : invN;
+    const double w1 = valid ? fma(1.0 - eps, b0, eps * invN) : 1.0;
+    double rho0[H];
+    double absd0;
+    {
+      double v[H + 1], tot[H + 1];
+#pragma unroll
+      for (int k = 0; k < H; ++k) v[k] = valid ? w1 * R[k] : 0.0;
+      v[H] = valid ? fabs(w1 - w0) : 0.0;
+      block_sum<H + 1>(v, tot);
+#pragma unroll
+      for (int k = 0; k < H; ++k) rho0[k] = tot[k];
+      absd0 = tot[H];
+    }
+    double sc0 = 1.0, sck = 1.0, dl0 = 0.0, dlk = 0.0;
+    if (has_u) {
+      if (tau > 0.0) {
+        const double room0 = tau - absd0;
+        if (!(room0 > 0.0)) {
+#pragma unroll
+          for (int k = 0; k < H; ++k) w[k] = w0;
+          kkt[0] = kkt[1] = kkt[2] = CUDART_INF;
+          return ST_FAILED;
+        }
+        dl0 = room0 / (2.0 * N); dlk = tau / (2.0 * N);
+      } else { dl0 = dlk = 0.05 * invN; }
+      if (has_c) { sc0 = tau - (absd0 + dl0 * N); sck = tau - dlk * N; }
+    }
+    const bool dual_start = has_w && (opt.dual_init > 0.0);
+    const double zeta0 = has_c ? opt.dual_init : 0.0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      mxR[k] = valid ? R[k] : 0.0;
+    }
+    if (dual_start) {
+      // stage maxima of R (two per butterfly)
+#pragma unroll
+      for (int k = 0; k < H; k += 2) {
+        double a = mxR[k], b = (k + 1 < H) ? mxR[(k + 1 < H) ? k + 1 : 0] : 0.0;
+        block_max2(a, b);
+        mxR[k] = a;
+        if (k + 1 < H) mxR[(k + 1 < H) ? k + 1 : 0] = b;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const double d0 = (k == 0 && valid) ? w1 - w0 : 0.0;
+      const double uk = has_u ? ((k == 0) ? fabs(d0) + dl0 : dlk) : 1.0;
+      w[k] = w1;
+      sp[k] = has_u ? uk - d0 : 1.0;
+      sq[k] = has_u ? uk + d0 : 1.0;
+      const double sck_ = (k == 0) ? sc0 : sck;
+      double nu_k;
+      if (dual_start) {
+        const double ir = 1.0 / rho0[k];
+        nu_k = mxR[k] * ir + opt.dual_init;
+        zw[k] = valid ? fma(-R[k], ir, nu_k) : 0.0;
+        zp[k] = has_u ? 0.5 * (lam + zeta0) : 0.0;
+        zq[k] = zp[k];
+        if (tid == 0) U(U_ZC, k) = has_c ? zeta0 : 0.0;
+      } else {
+        nu_k = 1.0;
+        zw[k] = (has_w && valid) ? opt.mu0 / w[k] : 0.0;
+        zp[k] = has_u ? opt.mu0 / sp[k] : 0.0;
+        zq[k] = has_u ? opt.mu0 / sq[k] : 0.0;
+        if (tid == 0) U(U_ZC, k) = has_c ? opt.mu0 / sck_ : 0.0;
+      }
+      if (tid == 0) { U(U_NU, k) = nu_k; U(U_SC, k) = sck_; U(U_CC, k) = 0.0; }
+      if (!valid) { zw[k] = 1.0; zp[k] = 1.0; zq[k] = 1.0; }      // benign padding (never updated, never summed)
+    }
+    sync();
+    const double mcount = (has_w ? (double)H * N : 0.0) + (has_u ? 2.0 * H * N : 0.0) + (has_c ? (double)H : 0.0);
+    int status = ST_FAILED;
+#pragma unroll 1
+    for (int it = 1; it <= opt.max_iter + 1; ++it) {
+      iters = it;
+      // ---- residuals ---------------------------------------------------------------------------------------------
+      double gap, pres;
+      {
+        double v[2 * H + 1];
+        double g = 0.0;
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          v[k] = valid ? w[k] * R[k] : 0.0;
+          v[H + k] = valid ? w[k] : 0.0;
+          if (has_w) g = fma(w[k], zw[k], g);
+          if (has_u) g = fma(sp[k], zp[k], fma(sq[k], zq[k], g));
+        }
+        if (!valid) g = 0.0;
+        if (has_c && tid < H) g = fma(U(U_SC, tid), U(U_ZC, tid), g);
+        v[2 * H] = g;
+        tile_reduce<2 * H + 1>(v);
+        gap = ptotal(2 * H);
+        pres = 0.0;
+#pragma unroll
+        for (int k = 0; k < H; ++k) pres = fmax(pres, fabs(ptotal(H + k) - 1.0));
+        if (tid < H) {
+          const double rho = ptotal(tid);
+          U(U_RHO, tid) = rho; U(U_IRHO, tid) = rcp_fast(rho);
+          U(U_RP, tid) = ptotal(H + tid) - 1.0;
+          U(U_ISC, tid) = has_c ? rcp_fast(U(U_SC, tid)) : 0.0;
+        }
+      }
+      sync();
+      double dres = 0.0;
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const double yk = zp[k] - zq[k];
+          const double yn = (k + 1 < H) ? zp[(k + 1 < H) ? k + 1 : 0] - zq[(k + 1 < H) ? k + 1 : 0] : 0.0;
+          const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (has_w ? zw[k] : 0.0) + (yk - yn);
+          dres = fmax(dres, fabs(rdw));
+          if (has_u) dres = fmax(dres, fabs(lam - zp[k] - zq[k] + (has_c ? U(U_ZC, k) : 0.0)));
+        }
+      }
+      {
+        double dummy = 0.0;
+        block_max2(dres, dummy);
+      }
+      kkt[0] = pres; kkt[1] = dres; kkt[2] = gap;
+      if (!isfinite(dres + gap)) break;
+      if (pres < opt.tol && dres < opt.tol_dual && gap < opt.tol) { status = ST_OPTIMAL; break; }
+      if (pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6) { status = ST_INACCURATE; break; }
+      if (it == opt.max_iter + 1) break;
+      const double mu = gap / fmax(mcount, 1.0);
+      if (pres < opt.tol && gap < opt.tol) delta = fmax(0.3 * delta, 1e-9);
+      if (!factorize()) break;
+      if (tid < H) U(U_CC, tid) = 0.0;
+      sync();
+      const bool stepped = (mcount > 0.0 || allow_short);
+#pragma unroll 1
+      for (int phase = (mcount > 0.0 ? 0 : 1); phase < 2; ++phase) {
+        const bool use_c = (phase == 1) && (mcount > 0.0);
+        double dw[H], dsp[H], dsq[H], dzw[H], dzp[H], dzq[H], dnu, dsc, dzc, rp, rd;
+        newton(use_c, dw, dsp, dsq, dzw, dzp, dzq, dnu, dsc, dzc, rp, rd);
+        if (allow_short) {            // keep the argument of the logarithm positive: rho_k + a * sum_i R dw > 0
+          double v[H], tot[H];
+#pragma unroll
+          for (int k = 0; k < H; ++k) v[k] = dw[k] * R[k];
+          block_sum<H>(v, tot);
+#pragma unroll
+          for (int k = 0; k < H; ++k) rp = fmax(rp, -tot[k] * U(U_IRHO, k));
+        }
+        block_max2(rp, rd);
+        // largest steps keeping slacks (aa) and duals (ab) non-negative: min(1, 1 / max ratio)
+        const double aa = (stepped && rp > 1.0) ? 1.0 / rp : 1.0;
+        const double ab = (stepped && rd > 1.0) ? 1.0 / rd : 1.0;
+        if (phase == 0) {
+          double g2 = 0.0;
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              if (has_w) g2 = fma(fma(aa, dw[k], w[k]), fma(ab, dzw[k], zw[k]), g2);
+              if (has_u) g2 = fma(fma(aa, dsp[k], sp[k]), fma(ab, dzp[k], zp[k]),
+                                  fma(fma(aa, dsq[k], sq[k]), fma(ab, dzq[k], zq[k]), g2));
+            }
+          }
+          if (has_c && tid < H) g2 = fma(fma(aa, dsc, U(U_SC, tid)), fma(ab, dzc, U(U_ZC, tid)), g2);
+          g2 = block_sum1(g2);
+          const double ratio = (gap > 0.0) ? fmin(1.0, fmax(g2 / gap, 0.0)) : 0.0;
+          const double smu = ratio * ratio * ratio * mu;
+#pragma unroll
+          for (int k = 0; k < H; ++k) {      // complementarity targets of the corrector
+            TGT(T_CW, k) = has_w ? fma(-dw[k], dzw[k], smu) : 0.0;
+            TGT(T_CP, k) = has_u ? fma(-dsp[k], dzp[k], smu) : 0.0;
+            TGT(T_CQ, k) = has_u ? fma(-dsq[k], dzq[k], smu) : 0.0;
+          }
+          if (tid < H) U(U_CC, tid) = has_c ? fma(-dsc, dzc, smu) : 0.0;
+          sync();
+        } else {
+          const double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;
+          const double pb = stepped ? fmin(1.0, opt.step_frac * ab) : 1.0;
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              w[k] = fma(pa, dw[k], w[k]);
+              if (has_w) zw[k] = fma(pb, dzw[k], zw[k]);
+              if (has_u) {
+                sp[k] = fma(pa, dsp[k], sp[k]); sq[k] = fma(pa, dsq[k], sq[k]);
+                zp[k] = fma(pb, dzp[k], zp[k]); zq[k] = fma(pb, dzq[k], zq[k]);
+              }
+            }
+          }
+          if (tid < H) {
+            U(U_NU, tid) = fma(pb, dnu, U(U_NU, tid));
+            if (has_c) { U(U_SC, tid) = fma(pa, dsc, U(U_SC, tid)); U(U_ZC, tid) = fma(pb, dzc, U(U_ZC, tid)); }
+          }
+          sync();
+        }
+      }
+    }
+    if (status != ST_OPTIMAL && isfinite(kkt[1] + kkt[2]) && kkt[0] < 1e-8 && kkt[1] < 1e-6 && kkt[2] < 1e-8)
+      status = ST_INACCURATE;
+    if (status == ST_FAILED) {
+#pragma unroll
+      for (int k = 0; k < H; ++k) w[k] = w0;
+    }
+    return status;
+  }
+
+  // maximised objective (mpc.py:104) of the plan held in w[]; same value in every thread
+  __device__ __forceinline__ double objective(double w0) {
+    double v[H + 1], tot[H + 1];
+    double ab = 0.0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      v[k] = valid ? w[k] * R[k] : 0.0;
+      ab += valid ? fabs(w[k] - ((k == 0) ? w0 : w[(k == 0) ? 0 : k - 1])) : 0.0;
+    }
+    v[H] = ab;
+    sync();
+    block_sum<H + 1>(v, tot);
+    double val = -lam * tot[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) val += log(tot[k]);
+    return val;
+  }
+};
+
+}  // namespace kmpc

@@ -1,0 +1,16 @@
+// One (H, G) instantiation of the lane-per-asset MPC / backtest kernels per translation unit.
+// Built with -DKMPC_H=<H> -DKMPC_G=<warps per problem>.
+#include "mpc_lane_kernels.cuh"
+#ifndef KMPC_H
+#error "compile with -DKMPC_H=<horizon> -DKMPC_G=<warps per problem>"
+#endif
+#define KMPC_CAT2(a, b, c, d) a##b##_##c##_##d
+#define KMPC_CAT(a, b, c) KMPC_CAT2(a, _lane, b, c)
+namespace kmpc {
+int KMPC_CAT(launch_mpc, KMPC_H, KMPC_G)(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
+  return launch_mpc_lane<KMPC_H, KMPC_G>(A, sm_count, st);
+}
+int KMPC_CAT(launch_bt, KMPC_H, KMPC_G)(const BacktestArgs& A, int sm_count, cudaStream_t st) {
+  return launch_bt_lane<KMPC_H, KMPC_G>(A, sm_count, st);
+}
+}  // namespace kmpc

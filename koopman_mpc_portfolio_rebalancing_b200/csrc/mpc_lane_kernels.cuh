@@ -1,0 +1,173 @@
+// Kernels around the lane-per-asset IPM solver (mpc_lane.cuh): same entry points and semantics as
+// mpc_kernels.cuh (mpc_solve = mpc.py:27-117, backtest = backtest.py:173-249); one block of G warps per problem /
+// per backtest, thread i = asset i, all stages of an asset in that thread's registers.
+#pragma once
+#include "kmpc_internal.cuh"
+#include "mpc_lane.cuh"
+
+#ifndef KMPC_LANE_MINB
+#define KMPC_LANE_MINB 1      // resident blocks per SM the register allocation is sized for (0/1 = no cap)
+#endif
+
+namespace kmpc {
+
+__device__ __forceinline__ float exp_cr32_lane(float y) { return __double2float_rn(exp((double)y)); }
+
+template <int H, int G>
+__global__ void __launch_bounds__(32 * G, KMPC_LANE_MINB)
+mpc_solve_lane_kernel(MpcSolveArgs A) {
+  using Ipm = LaneIpm<H, G>;
+  extern __shared__ double smem[];
+  Ipm s;
+  s.bind(smem, A.N);
+  const int N = A.N;
+  const IpmOptions opt = A.opt;
+  for (int p = blockIdx.x; p < A.P; p += gridDim.x) {
+    double w0 = 0.0;
+    if (s.valid) {
+      w0 = A.w_cur[(size_t)p * N + s.tid];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const size_t idx = ((size_t)p * H + k) * N + s.tid;
+        s.R[k] = A.yhat ? (double)exp_cr32_lane(A.yhat[idx]) : exp(A.yhat64[idx]);
+      }
+    }
+    const double lam = A.lam ? A.lam[p] : A.lam0;
+    const double tau = A.tau ? A.tau[p] : A.tau0;
+    int iters; double kkt[3];
+    const int st = s.solve(w0, N, lam, tau, A.allow_short != 0, opt, iters, kkt);
+    double val = CUDART_NAN;
+    if (st <= ST_INACCURATE) val = s.objective(w0);
+    if (s.valid) {
+#pragma unroll
+      for (int k = 0; k < H; ++k) A.w_out[((size_t)p * H + k) * N + s.tid] = s.w[k];
+    }
+    if (threadIdx.x == 0) {
+      if (A.obj) A.obj[p] = val;
+      if (A.kkt) { A.kkt[3 * p] = kkt[0]; A.kkt[3 * p + 1] = kkt[1]; A.kkt[3 * p + 2] = kkt[2]; }
+      if (A.status) A.status[p] = st;
+      if (A.iters) A.iters[p] = iters;
+    }
+    s.sync();
+  }
+}
+
+template <int H, int G>
+__global__ void __launch_bounds__(32 * G, KMPC_LANE_MINB)
+backtest_lane_kernel(BacktestArgs A) {
+  using Ipm = LaneIpm<H, G>;
+  extern __shared__ double smem[];
+  __shared__ int next_b;
+  Ipm s;
+  s.bind(smem, A.N);
+  const int N = A.N;
+  const IpmOptions opt = A.opt;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) next_b = atomicAdd(A.work_counter, 1);   // dynamic: backtests differ in iteration counts
+    __syncthreads();
+    const int b = next_b;
+    if (b >= A.B) break;
+    const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
+    const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
+    const double lam = A.lam ? A.lam[b] : A.lam0;
+    const double tau = A.tau ? A.tau[b] : A.tau0;
+    const double ccoef = A.cost_coeff ? A.cost_coeff[b] : A.cost_coeff0;
+    double V = A.capital ? A.capital[b] : A.capital0;
+    double wc = s.valid ? 1.0 / (double)N : 0.0;                                       // backtest.py:161
+    double mean = 0.0, m2 = 0.0, cum = 1.0, peak = -CUDART_INF, maxdd = CUDART_INF, sum_turn = 0.0, v_first = 0.0;
+    int n = 0, n_opt = 0, n_inacc = 0, n_fail = 0;
+    long long it_total = 0;
+    for (int t = 0; t < A.n_steps; t += A.rebalance_freq) {
+      if (s.valid) {
+#pragma unroll
+        for (int k = 0; k < H; ++k)
+          s.R[k] = (double)exp_cr32_lane(A.yhat[yb + ((size_t)t * H + k) * N + s.tid]);   // mpc.py:55
+      }
+      // realised return of the next day (independent of the solve: issue the load before it)
+      const bool market = (t + 1 < A.rows);
+      float y_next = 0.0f;
+      if (s.valid && market) y_next = A.realized[rb + (size_t)(t + 1) * N + s.tid];
+      int iters; double kkt[3];
+      const int st = s.solve(wc, N, lam, tau, A.allow_short != 0, opt, iters, kkt);
+      it_total += iters;
+      n_opt += (st == ST_OPTIMAL); n_inacc += (st == ST_INACCURATE); n_fail += (st >= ST_FAILED);
+      const double wn = s.valid ? s.w[0] : 0.0;                                          // backtest.py:131
+      float r32 = 0.0f;
+      if (s.valid && market) r32 = __fsub_rn(exp_cr32_lane(y_next), 1.0f);               // backtest.py:193
+      double v[2] = {fabs(wn - wc), wn * (double)r32}, T[2];
+      s.sync();
+      s.template block_sum<2>(v, T);
+      const double turnover = T[0];
+      const double cost = ccoef * turnover * V;
+      V -= cost;
+      double port_ret = 0.0;
+      wc = wn;
+      if (market) {
+        port_ret = T[1];
+        V *= (1.0 + port_ret);
+        double denom = 1.0 + port_ret;
+        if (fabs(denom) < 1e-8) denom = 1e-8;
+        wc = wn * (double)__fadd_rn(1.0f, r32) / denom;                                  // (1.0 + f32) stays f32
+      }
+      if (A.history && threadIdx.x == 0) {
+        double* hrow = A.history + ((size_t)b * A.n_hist + n) * 4;
+        hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
+      }
+      if (n == 0) v_first = V;
+      ++n;
+      const double dlt = port_ret - mean;
+      mean += dlt / (double)n;
+      m2 += dlt * (port_ret - mean);
+      cum *= (1.0 + port_ret);
+      peak = fmax(peak, cum);
+      maxdd = fmin(maxdd, (cum - peak) / peak);
+      sum_turn += turnover;
+    }
+    if (threadIdx.x == 0) {
+      double* m = A.metrics + (size_t)b * 5;
+      if (n > 0) {
+        const double sd = sqrt(m2 / (double)n);
+        m[0] = sqrt(252.0) * mean / (sd + 1e-8);
+        m[1] = maxdd;
+        m[2] = sum_turn / (double)n;
+        m[3] = V;
+        m[4] = V / v_first - 1.0;
+      } else { m[0] = m[1] = m[2] = m[3] = m[4] = CUDART_NAN; }
+      if (A.solve_stats) {
+        long long* ss = A.solve_stats + (size_t)b * 4;
+        ss[0] = n_opt; ss[1] = n_inacc; ss[2] = n_fail; ss[3] = it_total;
+      }
+    }
+    if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
+  }
+}
+
+template <typename K>
+static int lane_blocks_per_sm(K kernel, int threads, size_t smem) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
+  return nb < 1 ? 1 : nb;
+}
+
+template <int H, int G>
+static int launch_mpc_lane(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
+  const size_t smem = (size_t)LaneIpm<H, G>::SMEM_DOUBLES * sizeof(double);
+  static const int bps = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G>, 32 * G, smem);
+  int blocks = A.P < sm_count * bps ? A.P : sm_count * bps;
+  if (blocks < 1) blocks = 1;
+  mpc_solve_lane_kernel<H, G><<<blocks, 32 * G, smem, st>>>(A);
+  return (int)cudaGetLastError();
+}
+template <int H, int G>
+static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) {
+  const size_t smem = (size_t)LaneIpm<H, G>::SMEM_DOUBLES * sizeof(double);
+  static const int bps = lane_blocks_per_sm(backtest_lane_kernel<H, G>, 32 * G, smem);
+  int blocks = A.B < sm_count * bps ? A.B : sm_count * bps;
+  if (blocks < 1) blocks = 1;
+  backtest_lane_kernel<H, G><<<blocks, 32 * G, smem, st>>>(A);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace kmpc

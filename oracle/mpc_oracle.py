@@ -321,9 +321,52 @@ def _path_green(a, e):
     return G, D, DD
 
 
+def _path_factors(a, e):
+    """Sweep factors of the path networks of _path_green (same series/parallel recurrences), as arrays [H,N]:
+    qL,tL (left sweep), qR,tR (right sweep), gjj = T^{-1}[j,j], fL,fR,vd (two-sided split at an edge)."""
+    H, N = a.shape
+    hL = np.zeros((H, N)); qL = np.ones((H, N)); tL = np.zeros((H, N))
+    for k in range(H):
+        if k > 0:
+            inv = 1.0 / (e[k] + hL[k - 1]); qL[k] = hL[k - 1] * inv; tL[k] = e[k] * inv
+        hL[k] = a[k] + e[k] * qL[k]
+    hR = np.zeros((H, N)); qR = np.zeros((H, N)); tR = np.zeros((H, N))
+    hR[H - 1] = a[H - 1]
+    for k in range(H - 1, 0, -1):
+        inv = 1.0 / (e[k] + hR[k]); qR[k] = hR[k] * inv; tR[k] = e[k] * inv
+        hR[k - 1] = a[k - 1] + e[k] * qR[k]
+    gjj = np.zeros((H, N)); fL = np.ones((H, N)); fR = np.zeros((H, N)); vd = np.zeros((H, N))
+    for k in range(H):
+        gR = e[k + 1] * qR[k + 1] if k + 1 < H else 0.0
+        gjj[k] = 1.0 / (hL[k] + gR)
+        if k > 0:
+            inv = 1.0 / (hL[k - 1] + hR[k]); fL[k] = hL[k - 1] * inv; fR[k] = hR[k] * inv
+        vd[k] = 1.0 / (e[k] + hR[k] * fL[k])
+    return dict(qL=qL, tL=tL, qR=qR, tR=tR, gjj=gjj, fL=fL, fR=fR, vd=vd)
+
+
+def _path_sweep(F, gw, pg):
+    """(dw, dd) = (G gw - D^T pg, D gw - DD pg) in O(H) per asset instead of O(H^2): Norton equivalents of the
+    sources left (JL) and right (JR) of every node, swept once in each direction, then the node potential and the
+    drop across every edge from the two-sided split.  Same building blocks (factors in [0,1], no differencing of
+    potentials) as the Green's functions; this is what csrc/mpc_lane.cuh applies."""
+    H, N = gw.shape
+    JL = np.zeros((H, N)); JR = np.zeros((H, N)); inc = np.zeros((H, N))
+    for k in range(H):
+        JL[k] = gw[k] - F["qL"][k] * pg[k] + (F["tL"][k] * JL[k - 1] if k > 0 else 0.0)
+    JR[H - 1] = gw[H - 1]
+    for k in range(H - 1, 0, -1):
+        inc[k - 1] = F["tR"][k] * JR[k] + F["qR"][k] * pg[k]
+        JR[k - 1] = gw[k - 1] + inc[k - 1]
+    dw = F["gjj"] * (JL + inc)
+    t = F["fL"] * JR - pg
+    t[1:] -= F["fR"][1:] * JL[:-1]
+    return dw, F["vd"] * t
+
+
 def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e-10, tol_dual=1e-8,
                      max_iter=50, trace=None, delta=1e-5, split_steps=True, step_frac=0.995, mu0=1e-3,
-                     dual_init=3e-3):
+                     dual_init=3e-3, apply="green"):
     """Primal-dual IPM (Mehrotra); Newton step = per-asset path-network Green's functions + a (<=3H)
     dense border system.  This is the algorithm the CUDA kernel implements (csrc/mpc_ipm.cuh).
 
@@ -425,6 +468,7 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
             E = np.ones((H, N))
             e = zHN
         G, D, DD = _path_green(Dw0 + delta, e)
+        PF = _path_factors(Dw0 + delta, e) if apply == "sweep" else None
         # border matrix K = V^T M0^{-1} V + diag(1/beta, 0, sc/zc),  V = [Rt_j | 1t_j | et_j]
         K = np.zeros((nb, nb))
         for l in range(H):
@@ -454,6 +498,10 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
         def m0_solve(g_w, g_u):
             """(dw, dd, du) = M0^{-1} (g_w, g_u) through the Green's functions."""
             pg = phi * g_u                                   # dipole strengths (negated)
+            if PF is not None:
+                dw, dd = _path_sweep(PF, g_w, pg)
+                du = (g_u - F * dd) / E if has_u else zHN
+                return dw, dd, du
             dw = np.einsum('ljn,jn->ln', G, g_w) - np.einsum('kln,kn->ln', D, pg)
             dd = np.einsum('ljn,jn->ln', D, g_w) - np.einsum('lkn,kn->ln', DD, pg)
             du = (g_u - F * dd) / E if has_u else zHN

@@ -6,13 +6,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["cta", "warp"], autouse=True)
+@pytest.fixture(params=["lane", "cta", "warp"], autouse=True)
 def mpc_kernel_layout(request):
-    """every test runs against both kernel layouts: one thread block per problem (default) and one warp per problem"""
+    """every test runs against the three kernel layouts: thread = asset (default), thread = (stage, asset), and
+    one warp per problem"""
     from koopman_mpc_portfolio_rebalancing_b200 import _capi
-    _capi.lib().kmpc_set_mpc_kernel(1 if request.param == "cta" else 0)
+    _capi.lib().kmpc_set_mpc_kernel({"lane": 2, "cta": 1, "warp": 0}[request.param])
     yield request.param
-    _capi.lib().kmpc_set_mpc_kernel(1)
+    _capi.lib().kmpc_set_mpc_kernel(2)
 
 
 def _mods():

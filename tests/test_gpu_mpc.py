@@ -8,13 +8,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["cta", "warp"], autouse=True)
+@pytest.fixture(params=["lane", "cta", "warp"], autouse=True)
 def mpc_kernel_layout(request):
-    """every test runs against both kernel layouts: one thread block per problem (default) and one warp per problem"""
+    """every test runs against the three kernel layouts: thread = asset (default), thread = (stage, asset), and
+    one warp per problem"""
     from koopman_mpc_portfolio_rebalancing_b200 import _capi
-    _capi.lib().kmpc_set_mpc_kernel(1 if request.param == "cta" else 0)
+    _capi.lib().kmpc_set_mpc_kernel({"lane": 2, "cta": 1, "warp": 0}[request.param])
     yield request.param
-    _capi.lib().kmpc_set_mpc_kernel(1)
+    _capi.lib().kmpc_set_mpc_kernel(2)
 
 OBJ_RTOL = 1e-6      # |obj_gpu - obj_oracle| <= OBJ_RTOL * max(|obj_oracle|, OBJ_FLOOR)
 OBJ_FLOOR = 1e-3     # objectives are sums of daily log-growth; below 1e-3 the bar is absolute 1e-9
