@@ -29,6 +29,10 @@
 
 namespace kmpc {
 
+// Block-uniform conditions are evaluated from shared-memory values; the vote makes them provably warp-uniform so
+// that the shuffles downstream compile without divergence handling (WARPSYNC / ENDCOLLECTIVE per shuffle).
+__device__ __forceinline__ bool uni(bool c) { return __any_sync(kFull, c) != 0; }
+
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // ~20 correct bits
@@ -100,7 +104,8 @@ struct LaneIpm {
   double lam, tau, delta;
 
   __device__ __forceinline__ void bind(double* smem, int n_assets) {
-    sm = smem; tid = threadIdx.x; lane = tid & 31; warp = tid >> 5; psel = 0;
+    sm = smem; tid = threadIdx.x; lane = tid & 31; psel = 0;
+    warp = __shfl_sync(kFull, tid >> 5, 0);        // provably warp-uniform: branches on it need no reconvergence code
     valid = tid < n_assets;
   }
   __device__ __forceinline__ double& FAC(int arr, int k) const { return sm[OFF_FAC + (arr * H + k) * NT + tid]; }
@@ -357,7 +362,7 @@ struct LaneIpm {
       if (lane == 0) sm[OFF_FLAG] = pd ? 1.0 : 0.0;
     }
     sync();
-    return sm[OFF_FLAG] > 0.5;
+    return uni(sm[OFF_FLAG] > 0.5);
   }
 
   // t (OFF_T) <- K^{-1} t by warp 0
@@ -487,8 +492,8 @@ struct LaneIpm {
   __device__ __forceinline__ int solve(double w0, int N, double lam_, double tau_, bool allow_short,
                                        const IpmOptions& opt, int& iters, double (&kkt)[3]) {
     lam = lam_; tau = tau_; delta = opt.delta;
-    has_u = (lam > 0.0) || (tau > 0.0);
-    has_c = has_u && (tau > 0.0);
+    has_u = uni((lam > 0.0) || (tau > 0.0));
+    has_c = has_u && uni(tau > 0.0);
     has_w = !allow_short;
     iters = 0;
     kkt[0] = kkt[1] = kkt[2] = CUDART_NAN;
@@ -506,7 +511,7 @@ struct LaneIpm {
       for (int k = 0; k < H; ++k) okv = okv && isfinite(R[k]) && (R[k] > 0.0);
       double bad = okv ? 0.0 : 1.0, dummy = 0.0;
       block_max2(bad, dummy);
-      if (bad > 0.0) {
+      if (uni(bad > 0.0)) {
 #pragma unroll
         for (int k = 0; k < H; ++k) w[k] = w0;
         return ST_NONFINITE;
@@ -531,9 +536,9 @@ struct LaneIpm {
     }
     double sc0 = 1.0, sck = 1.0, dl0 = 0.0, dlk = 0.0;
     if (has_u) {
-      if (tau > 0.0) {
+      if (uni(tau > 0.0)) {
         const double room0 = tau - absd0;
-        if (!(room0 > 0.0)) {
+        if (uni(!(room0 > 0.0))) {
 #pragma unroll
           for (int k = 0; k < H; ++k) w[k] = w0;
           kkt[0] = kkt[1] = kkt[2] = CUDART_INF;
@@ -543,7 +548,7 @@ struct LaneIpm {
       } else { dl0 = dlk = 0.05 * invN; }
       if (has_c) { sc0 = tau - (absd0 + dl0 * N); sck = tau - dlk * N; }
     }
-    const bool dual_start = has_w && (opt.dual_init > 0.0);
+    const bool dual_start = has_w && uni(opt.dual_init > 0.0);
     const double zeta0 = has_c ? opt.dual_init : 0.0;
 #pragma unroll
     for (int k = 0; k < H; ++k) {
@@ -635,12 +640,12 @@ struct LaneIpm {
         block_max2(dres, dummy);
       }
       kkt[0] = pres; kkt[1] = dres; kkt[2] = gap;
-      if (!isfinite(dres + gap)) break;
-      if (pres < opt.tol && dres < opt.tol_dual && gap < opt.tol) { status = ST_OPTIMAL; break; }
-      if (pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6) { status = ST_INACCURATE; break; }
+      if (uni(!isfinite(dres + gap))) break;
+      if (uni(pres < opt.tol && dres < opt.tol_dual && gap < opt.tol)) { status = ST_OPTIMAL; break; }
+      if (uni(pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6)) { status = ST_INACCURATE; break; }
       if (it == opt.max_iter + 1) break;
       const double mu = gap / fmax(mcount, 1.0);
-      if (pres < opt.tol && gap < opt.tol) delta = fmax(0.3 * delta, 1e-9);
+      if (uni(pres < opt.tol && gap < opt.tol)) delta = fmax(0.3 * delta, 1e-9);
       if (!factorize()) break;
       if (tid < H) U(U_CC, tid) = 0.0;
       sync();

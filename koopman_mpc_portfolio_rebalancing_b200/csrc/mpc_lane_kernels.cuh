@@ -66,7 +66,7 @@ backtest_lane_kernel(BacktestArgs A) {
     __syncthreads();
     if (threadIdx.x == 0) next_b = atomicAdd(A.work_counter, 1);   // dynamic: backtests differ in iteration counts
     __syncthreads();
-    const int b = next_b;
+    const int b = __shfl_sync(kFull, next_b, 0);
     if (b >= A.B) break;
     const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
     const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
