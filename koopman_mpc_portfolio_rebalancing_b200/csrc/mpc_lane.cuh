@@ -99,20 +99,27 @@ struct LaneIpm {
   double R[H], w[H], sp[H], sq[H], zw[H], zp[H], zq[H];      // iterate
   double iw[H], isp[H], isq[H], ie[H], ph[H];                // element-wise factors of the current iterate
   double* sm;
-  int tid, lane, warp, psel;
-  bool valid, has_w, has_u, has_c;
+  int tid, lane, warp, psel, bar_id;
+  bool valid, has_w, has_u, has_c, allow_short_, fact_ok_;
   double lam, tau, delta;
+  // state of the solve in progress (begin / check / factor_a / factor_b / newton_phase)
+  double w0_, mu_, gap_, mcount_, kkt_[3];
+  int it_;
 
-  __device__ __forceinline__ void bind(double* smem, int n_assets) {
-    sm = smem; tid = threadIdx.x; lane = tid & 31; psel = 0;
+  // `slot`: which of the problems that share this thread block (its threads are [slot*NT, (slot+1)*NT), its
+  // named barrier is 1 + slot; barrier 0 stays free for block-wide lockstep points of the caller).
+  __device__ __forceinline__ void bind(double* smem_slice, int n_assets, int slot) {
+    sm = smem_slice; tid = (int)threadIdx.x - slot * NT; lane = tid & 31; psel = 0; bar_id = 1 + slot;
     warp = __shfl_sync(kFull, tid >> 5, 0);        // provably warp-uniform: branches on it need no reconvergence code
     valid = tid < n_assets;
+    fact_ok_ = true; it_ = 0;
   }
   __device__ __forceinline__ double& FAC(int arr, int k) const { return sm[OFF_FAC + (arr * H + k) * NT + tid]; }
   __device__ __forceinline__ double& TGT(int arr, int k) const { return sm[OFF_TGT + (arr * H + k) * NT + tid]; }
   __device__ __forceinline__ double& U(int arr, int k) const { return sm[OFF_U + arr * H + k]; }
   __device__ __forceinline__ void sync() const {
-    if (G == 1) __syncwarp(); else __syncthreads();
+    if (G == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
   }
 
   // ---- reductions over the threads of the problem --------------------------------------------------------------
@@ -166,7 +173,7 @@ struct LaneIpm {
       psel ^= 1;
       double* P = sm + OFF_P + psel * G * 32;
       if (lane == 0) { P[warp * 32] = a; P[warp * 32 + 1] = b; }
-      __syncthreads();
+      sync();
 #pragma unroll
       for (int g = 0; g < G; ++g) { a = fmax(a, P[g * 32]); b = fmax(b, P[g * 32 + 1]); }
     }
@@ -177,7 +184,7 @@ struct LaneIpm {
       psel ^= 1;
       double* P = sm + OFF_P + psel * G * 32;
       if (lane == 0) P[warp * 32] = a;
-      __syncthreads();
+      sync();
       a = P[0];
 #pragma unroll
       for (int g = 1; g < G; ++g) a += P[g * 32];
@@ -216,7 +223,7 @@ struct LaneIpm {
       psel ^= 1;
       double* P = sm + OFF_P + psel * G * 32;
       if (warp > 0) P[warp * 32 + lane] = s;
-      __syncthreads();
+      sync();
       if (warp == 0) {
 #pragma unroll
         for (int g = 1; g < G; ++g) s += P[g * 32 + lane];
@@ -227,7 +234,8 @@ struct LaneIpm {
     if (warp == 0 && lane < count) sm[OFF_K + g_kmap<H>.rc[first + lane]] = s;
   }
 
-  __device__ __forceinline__ bool factorize() {
+  // element-wise barrier factors, conductance sweeps, border matrix K (shared memory)
+  __device__ __forceinline__ void factor_a() {
     double ad[H], e[H];
 #pragma unroll
     for (int k = 0; k < H; ++k) {
@@ -329,7 +337,11 @@ struct LaneIpm {
     }
 #undef KMPC_FLUSH_IF_FULL
     sync();
-    // ---- Cholesky by warp 0: lane = row, row in registers, columns exchanged by shuffles ----------------------
+  }
+
+  // Cholesky of K by warp 0: lane = row, row in registers, columns exchanged by shuffles.  False on a
+  // non-positive pivot.
+  __device__ __forceinline__ bool factor_b() {
     if (warp == 0) {
       const int nb = has_c ? 3 * H : 2 * H;
       double a[NB];
@@ -362,7 +374,8 @@ struct LaneIpm {
       if (lane == 0) sm[OFF_FLAG] = pd ? 1.0 : 0.0;
     }
     sync();
-    return uni(sm[OFF_FLAG] > 0.5);
+    fact_ok_ = uni(sm[OFF_FLAG] > 0.5);
+    return fact_ok_;
   }
 
   // t (OFF_T) <- K^{-1} t by warp 0
@@ -487,21 +500,26 @@ struct LaneIpm {
     rp_ = rp; rd_ = rd;
   }
 
-  // Solve one problem.  R[] (gross returns of my asset, all stages) is set; w0 = my current weight.
-  // Returns the status; w[] holds my entries of the plan (w0 in every stage on failure).
-  __device__ __forceinline__ int solve(double w0, int N, double lam_, double tau_, bool allow_short,
-                                       const IpmOptions& opt, int& iters, double (&kkt)[3]) {
+  // ---- the solve, in pieces (so that a caller can interleave several problems in lockstep) ---------------------
+  //   begin()        screening + initial point.  Returns -1 (iterate) or a terminal status.
+  //   check()        residuals of the current iterate.  Returns -1 (take another Newton step) or the final status.
+  //   factor_a/b()   factorisation at the current iterate
+  //   newton_phase() predictor (0) and corrector + step (1)
+  // R[] (gross returns of my asset, all stages) must be set before begin(); w0 = my current weight.
+  __device__ __forceinline__ int begin(double w0, int N, double lam_, double tau_, bool allow_short,
+                                       const IpmOptions& opt) {
     lam = lam_; tau = tau_; delta = opt.delta;
     has_u = uni((lam > 0.0) || (tau > 0.0));
     has_c = has_u && uni(tau > 0.0);
-    has_w = !allow_short;
-    iters = 0;
-    kkt[0] = kkt[1] = kkt[2] = CUDART_NAN;
+    has_w = !allow_short; allow_short_ = allow_short;
+    it_ = 0; fact_ok_ = true;
+    kkt_[0] = kkt_[1] = kkt_[2] = CUDART_NAN;
     if (!valid) {
       w0 = 0.0;
 #pragma unroll
       for (int k = 0; k < H; ++k) R[k] = 1.0;
     }
+    w0_ = w0;
     // ---- screening, initial point (oracle/mpc_oracle.py::_initial_point) --------------------------------------
     const double base = valid ? (allow_short ? w0 : fmax(w0, 0.0)) : 0.0;
     double mxR[H];
@@ -511,11 +529,7 @@ struct LaneIpm {
       for (int k = 0; k < H; ++k) okv = okv && isfinite(R[k]) && (R[k] > 0.0);
       double bad = okv ? 0.0 : 1.0, dummy = 0.0;
       block_max2(bad, dummy);
-      if (uni(bad > 0.0)) {
-#pragma unroll
-        for (int k = 0; k < H; ++k) w[k] = w0;
-        return ST_NONFINITE;
-      }
+      if (uni(bad > 0.0)) return finish(ST_NONFINITE);
     }
     const double sb = block_sum1(base);
     const double invN = 1.0 / (double)N;
@@ -539,10 +553,8 @@ struct LaneIpm {
       if (uni(tau > 0.0)) {
         const double room0 = tau - absd0;
         if (uni(!(room0 > 0.0))) {
-#pragma unroll
-          for (int k = 0; k < H; ++k) w[k] = w0;
-          kkt[0] = kkt[1] = kkt[2] = CUDART_INF;
-          return ST_FAILED;
+          kkt_[0] = kkt_[1] = kkt_[2] = CUDART_INF;
+          return finish(ST_FAILED);
         }
         dl0 = room0 / (2.0 * N); dlk = tau / (2.0 * N);
       } else { dl0 = dlk = 0.05 * invN; }
@@ -551,9 +563,7 @@ struct LaneIpm {
     const bool dual_start = has_w && uni(opt.dual_init > 0.0);
     const double zeta0 = has_c ? opt.dual_init : 0.0;
 #pragma unroll
-    for (int k = 0; k < H; ++k) {
-      mxR[k] = valid ? R[k] : 0.0;
-    }
+    for (int k = 0; k < H; ++k) mxR[k] = valid ? R[k] : 0.0;
     if (dual_start) {
       // stage maxima of R (two per butterfly)
 #pragma unroll
@@ -591,132 +601,158 @@ struct LaneIpm {
       if (!valid) { zw[k] = 1.0; zp[k] = 1.0; zq[k] = 1.0; }      // benign padding (never updated, never summed)
     }
     sync();
-    const double mcount = (has_w ? (double)H * N : 0.0) + (has_u ? 2.0 * H * N : 0.0) + (has_c ? (double)H : 0.0);
-    int status = ST_FAILED;
-#pragma unroll 1
-    for (int it = 1; it <= opt.max_iter + 1; ++it) {
-      iters = it;
-      // ---- residuals ---------------------------------------------------------------------------------------------
-      double gap, pres;
-      {
-        double v[2 * H + 1];
-        double g = 0.0;
+    mcount_ = (has_w ? (double)H * N : 0.0) + (has_u ? 2.0 * H * N : 0.0) + (has_c ? (double)H : 0.0);
+    return -1;
+  }
+
+  // final status of a solve that left the iteration without meeting the tolerances (or never started)
+  __device__ __forceinline__ int finish(int status) {
+    if (status == ST_FAILED && isfinite(kkt_[1] + kkt_[2]) && kkt_[0] < 1e-8 && kkt_[1] < 1e-6 && kkt_[2] < 1e-8)
+      status = ST_INACCURATE;
+    if (status >= ST_FAILED) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-          v[k] = valid ? w[k] * R[k] : 0.0;
-          v[H + k] = valid ? w[k] : 0.0;
-          if (has_w) g = fma(w[k], zw[k], g);
-          if (has_u) g = fma(sp[k], zp[k], fma(sq[k], zq[k], g));
-        }
-        if (!valid) g = 0.0;
-        if (has_c && tid < H) g = fma(U(U_SC, tid), U(U_ZC, tid), g);
-        v[2 * H] = g;
-        tile_reduce<2 * H + 1>(v);
-        gap = ptotal(2 * H);
-        pres = 0.0;
+      for (int k = 0; k < H; ++k) w[k] = w0_;              // mpc.py:113-115: hold the current weights
+    }
+    return status;
+  }
+
+  __device__ __forceinline__ int check(const IpmOptions& opt) {
+    if (!fact_ok_) return finish(ST_FAILED);               // the previous factorisation broke down
+    ++it_;
+    double gap, pres;
+    {
+      double v[2 * H + 1];
+      double g = 0.0;
 #pragma unroll
-        for (int k = 0; k < H; ++k) pres = fmax(pres, fabs(ptotal(H + k) - 1.0));
-        if (tid < H) {
-          const double rho = ptotal(tid);
-          U(U_RHO, tid) = rho; U(U_IRHO, tid) = rcp_fast(rho);
-          U(U_RP, tid) = ptotal(H + tid) - 1.0;
-          U(U_ISC, tid) = has_c ? rcp_fast(U(U_SC, tid)) : 0.0;
-        }
+      for (int k = 0; k < H; ++k) {
+        v[k] = valid ? w[k] * R[k] : 0.0;
+        v[H + k] = valid ? w[k] : 0.0;
+        if (has_w) g = fma(w[k], zw[k], g);
+        if (has_u) g = fma(sp[k], zp[k], fma(sq[k], zq[k], g));
       }
-      sync();
-      double dres = 0.0;
+      if (!valid) g = 0.0;
+      if (has_c && tid < H) g = fma(U(U_SC, tid), U(U_ZC, tid), g);
+      v[2 * H] = g;
+      tile_reduce<2 * H + 1>(v);
+      gap = ptotal(2 * H);
+      pres = 0.0;
+#pragma unroll
+      for (int k = 0; k < H; ++k) pres = fmax(pres, fabs(ptotal(H + k) - 1.0));
+      if (tid < H) {
+        const double rho = ptotal(tid);
+        U(U_RHO, tid) = rho; U(U_IRHO, tid) = rcp_fast(rho);
+        U(U_RP, tid) = ptotal(H + tid) - 1.0;
+        U(U_ISC, tid) = has_c ? rcp_fast(U(U_SC, tid)) : 0.0;
+      }
+    }
+    sync();
+    double dres = 0.0;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const double yk = zp[k] - zq[k];
+        const double yn = (k + 1 < H) ? zp[(k + 1 < H) ? k + 1 : 0] - zq[(k + 1 < H) ? k + 1 : 0] : 0.0;
+        const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (has_w ? zw[k] : 0.0) + (yk - yn);
+        dres = fmax(dres, fabs(rdw));
+        if (has_u) dres = fmax(dres, fabs(lam - zp[k] - zq[k] + (has_c ? U(U_ZC, k) : 0.0)));
+      }
+    }
+    {
+      double dummy = 0.0;
+      block_max2(dres, dummy);
+    }
+    kkt_[0] = pres; kkt_[1] = dres; kkt_[2] = gap;
+    gap_ = gap;
+    if (uni(!isfinite(dres + gap))) return finish(ST_FAILED);
+    if (uni(pres < opt.tol && dres < opt.tol_dual && gap < opt.tol)) return ST_OPTIMAL;
+    // flat directions (curvature << delta): see mpc_ipm.cuh
+    if (uni(pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6)) return ST_INACCURATE;
+    if (it_ == opt.max_iter + 1) return finish(ST_FAILED);
+    mu_ = gap / fmax(mcount_, 1.0);
+    if (uni(pres < opt.tol && gap < opt.tol)) delta = fmax(0.3 * delta, 1e-9);   // endgame: shrink the proximal term
+    return -1;
+  }
+
+  // phase 0: predictor -> complementarity targets of the corrector; phase 1: corrector -> step
+  __device__ __forceinline__ void newton_phase(int phase, const IpmOptions& opt) {
+    const bool has_m = mcount_ > 0.0;
+    if (phase == 0 && !has_m) return;
+    const bool use_c = (phase == 1) && has_m;
+    const bool stepped = has_m || allow_short_;
+    double dw[H], dsp[H], dsq[H], dzw[H], dzp[H], dzq[H], dnu, dsc, dzc, rp, rd;
+    newton(use_c, dw, dsp, dsq, dzw, dzp, dzq, dnu, dsc, dzc, rp, rd);
+    if (allow_short_) {            // keep the argument of the logarithm positive: rho_k + a * sum_i R dw > 0
+      double v[H], tot[H];
+#pragma unroll
+      for (int k = 0; k < H; ++k) v[k] = dw[k] * R[k];
+      block_sum<H>(v, tot);
+#pragma unroll
+      for (int k = 0; k < H; ++k) rp = fmax(rp, -tot[k] * U(U_IRHO, k));
+    }
+    block_max2(rp, rd);
+    // largest steps keeping slacks (aa) and duals (ab) non-negative: min(1, 1 / max ratio)
+    const double aa = (stepped && rp > 1.0) ? 1.0 / rp : 1.0;
+    const double ab = (stepped && rd > 1.0) ? 1.0 / rd : 1.0;
+    if (phase == 0) {
+      double g2 = 0.0;
       if (valid) {
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-          const double yk = zp[k] - zq[k];
-          const double yn = (k + 1 < H) ? zp[(k + 1 < H) ? k + 1 : 0] - zq[(k + 1 < H) ? k + 1 : 0] : 0.0;
-          const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (has_w ? zw[k] : 0.0) + (yk - yn);
-          dres = fmax(dres, fabs(rdw));
-          if (has_u) dres = fmax(dres, fabs(lam - zp[k] - zq[k] + (has_c ? U(U_ZC, k) : 0.0)));
+          if (has_w) g2 = fma(fma(aa, dw[k], w[k]), fma(ab, dzw[k], zw[k]), g2);
+          if (has_u) g2 = fma(fma(aa, dsp[k], sp[k]), fma(ab, dzp[k], zp[k]),
+                              fma(fma(aa, dsq[k], sq[k]), fma(ab, dzq[k], zq[k]), g2));
         }
       }
-      {
-        double dummy = 0.0;
-        block_max2(dres, dummy);
+      if (has_c && tid < H) g2 = fma(fma(aa, dsc, U(U_SC, tid)), fma(ab, dzc, U(U_ZC, tid)), g2);
+      g2 = block_sum1(g2);
+      const double ratio = (gap_ > 0.0) ? fmin(1.0, fmax(g2 / gap_, 0.0)) : 0.0;
+      const double smu = ratio * ratio * ratio * mu_;
+#pragma unroll
+      for (int k = 0; k < H; ++k) {      // complementarity targets of the corrector
+        TGT(T_CW, k) = has_w ? fma(-dw[k], dzw[k], smu) : 0.0;
+        TGT(T_CP, k) = has_u ? fma(-dsp[k], dzp[k], smu) : 0.0;
+        TGT(T_CQ, k) = has_u ? fma(-dsq[k], dzq[k], smu) : 0.0;
       }
-      kkt[0] = pres; kkt[1] = dres; kkt[2] = gap;
-      if (uni(!isfinite(dres + gap))) break;
-      if (uni(pres < opt.tol && dres < opt.tol_dual && gap < opt.tol)) { status = ST_OPTIMAL; break; }
-      if (uni(pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6)) { status = ST_INACCURATE; break; }
-      if (it == opt.max_iter + 1) break;
-      const double mu = gap / fmax(mcount, 1.0);
-      if (uni(pres < opt.tol && gap < opt.tol)) delta = fmax(0.3 * delta, 1e-9);
-      if (!factorize()) break;
-      if (tid < H) U(U_CC, tid) = 0.0;
+      if (tid < H) U(U_CC, tid) = has_c ? fma(-dsc, dzc, smu) : 0.0;
       sync();
-      const bool stepped = (mcount > 0.0 || allow_short);
-#pragma unroll 1
-      for (int phase = (mcount > 0.0 ? 0 : 1); phase < 2; ++phase) {
-        const bool use_c = (phase == 1) && (mcount > 0.0);
-        double dw[H], dsp[H], dsq[H], dzw[H], dzp[H], dzq[H], dnu, dsc, dzc, rp, rd;
-        newton(use_c, dw, dsp, dsq, dzw, dzp, dzq, dnu, dsc, dzc, rp, rd);
-        if (allow_short) {            // keep the argument of the logarithm positive: rho_k + a * sum_i R dw > 0
-          double v[H], tot[H];
+    } else {
+      const double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;
+      const double pb = stepped ? fmin(1.0, opt.step_frac * ab) : 1.0;
+      if (valid) {
 #pragma unroll
-          for (int k = 0; k < H; ++k) v[k] = dw[k] * R[k];
-          block_sum<H>(v, tot);
-#pragma unroll
-          for (int k = 0; k < H; ++k) rp = fmax(rp, -tot[k] * U(U_IRHO, k));
-        }
-        block_max2(rp, rd);
-        // largest steps keeping slacks (aa) and duals (ab) non-negative: min(1, 1 / max ratio)
-        const double aa = (stepped && rp > 1.0) ? 1.0 / rp : 1.0;
-        const double ab = (stepped && rd > 1.0) ? 1.0 / rd : 1.0;
-        if (phase == 0) {
-          double g2 = 0.0;
-          if (valid) {
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-              if (has_w) g2 = fma(fma(aa, dw[k], w[k]), fma(ab, dzw[k], zw[k]), g2);
-              if (has_u) g2 = fma(fma(aa, dsp[k], sp[k]), fma(ab, dzp[k], zp[k]),
-                                  fma(fma(aa, dsq[k], sq[k]), fma(ab, dzq[k], zq[k]), g2));
-            }
+        for (int k = 0; k < H; ++k) {
+          w[k] = fma(pa, dw[k], w[k]);
+          if (has_w) zw[k] = fma(pb, dzw[k], zw[k]);
+          if (has_u) {
+            sp[k] = fma(pa, dsp[k], sp[k]); sq[k] = fma(pa, dsq[k], sq[k]);
+            zp[k] = fma(pb, dzp[k], zp[k]); zq[k] = fma(pb, dzq[k], zq[k]);
           }
-          if (has_c && tid < H) g2 = fma(fma(aa, dsc, U(U_SC, tid)), fma(ab, dzc, U(U_ZC, tid)), g2);
-          g2 = block_sum1(g2);
-          const double ratio = (gap > 0.0) ? fmin(1.0, fmax(g2 / gap, 0.0)) : 0.0;
-          const double smu = ratio * ratio * ratio * mu;
-#pragma unroll
-          for (int k = 0; k < H; ++k) {      // complementarity targets of the corrector
-            TGT(T_CW, k) = has_w ? fma(-dw[k], dzw[k], smu) : 0.0;
-            TGT(T_CP, k) = has_u ? fma(-dsp[k], dzp[k], smu) : 0.0;
-            TGT(T_CQ, k) = has_u ? fma(-dsq[k], dzq[k], smu) : 0.0;
-          }
-          if (tid < H) U(U_CC, tid) = has_c ? fma(-dsc, dzc, smu) : 0.0;
-          sync();
-        } else {
-          const double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;
-          const double pb = stepped ? fmin(1.0, opt.step_frac * ab) : 1.0;
-          if (valid) {
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-              w[k] = fma(pa, dw[k], w[k]);
-              if (has_w) zw[k] = fma(pb, dzw[k], zw[k]);
-              if (has_u) {
-                sp[k] = fma(pa, dsp[k], sp[k]); sq[k] = fma(pa, dsq[k], sq[k]);
-                zp[k] = fma(pb, dzp[k], zp[k]); zq[k] = fma(pb, dzq[k], zq[k]);
-              }
-            }
-          }
-          if (tid < H) {
-            U(U_NU, tid) = fma(pb, dnu, U(U_NU, tid));
-            if (has_c) { U(U_SC, tid) = fma(pa, dsc, U(U_SC, tid)); U(U_ZC, tid) = fma(pb, dzc, U(U_ZC, tid)); }
-          }
-          sync();
         }
       }
+      if (tid < H) {
+        U(U_NU, tid) = fma(pb, dnu, U(U_NU, tid));
+        if (has_c) { U(U_SC, tid) = fma(pa, dsc, U(U_SC, tid)); U(U_ZC, tid) = fma(pb, dzc, U(U_ZC, tid)); }
+        U(U_CC, tid) = 0.0;                  // the next predictor has no complementarity targets
+      }
+      sync();
     }
-    if (status != ST_OPTIMAL && isfinite(kkt[1] + kkt[2]) && kkt[0] < 1e-8 && kkt[1] < 1e-6 && kkt[2] < 1e-8)
-      status = ST_INACCURATE;
-    if (status == ST_FAILED) {
-#pragma unroll
-      for (int k = 0; k < H; ++k) w[k] = w0;
+  }
+
+  // Solve one problem start to end.  Returns the status; w[] holds my entries of the plan (w0 in every stage on
+  // failure), kkt = (primal residual, dual residual, complementarity gap) of the last iterate.
+  __device__ __forceinline__ int solve(double w0, int N, double lam_, double tau_, bool allow_short,
+                                       const IpmOptions& opt, int& iters, double (&kkt)[3]) {
+    int status = begin(w0, N, lam_, tau_, allow_short, opt);
+    while (status < 0) {
+      status = check(opt);
+      if (status >= 0) break;
+      factor_a();
+      if (!factor_b()) continue;
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) newton_phase(phase, opt);
     }
+    iters = it_;
+    kkt[0] = kkt_[0]; kkt[1] = kkt_[1]; kkt[2] = kkt_[2];
     return status;
   }
 

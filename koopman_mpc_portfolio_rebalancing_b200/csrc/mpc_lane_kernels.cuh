@@ -4,6 +4,7 @@
 #pragma once
 #include "kmpc_internal.cuh"
 #include "mpc_lane.cuh"
+#include <stdlib.h>
 
 #ifndef KMPC_LANE_MINB
 #define KMPC_LANE_MINB 1      // resident blocks per SM the register allocation is sized for (0/1 = no cap)
@@ -19,7 +20,7 @@ mpc_solve_lane_kernel(MpcSolveArgs A) {
   using Ipm = LaneIpm<H, G>;
   extern __shared__ double smem[];
   Ipm s;
-  s.bind(smem, A.N);
+  s.bind(smem, A.N, 0);
   const int N = A.N;
   const IpmOptions opt = A.opt;
   for (int p = blockIdx.x; p < A.P; p += gridDim.x) {
@@ -52,96 +53,152 @@ mpc_solve_lane_kernel(MpcSolveArgs A) {
   }
 }
 
-template <int H, int G>
-__global__ void __launch_bounds__(32 * G, KMPC_LANE_MINB)
+// Persistent backtest kernel.  A block hosts P independent backtests ("slots", G warps each).  The solver code is
+// ~8 k straight-line instructions per Newton iteration, several times the 32 KB instruction cache of an SM: when
+// every resident problem walks through it at its own pace the warps starve on instruction fetch (ncu: 41 % of
+// all stall samples `no_instruction`, throughput 2.15x going from 1 to 4 independent blocks per SM).  Here all
+// slots of the SM pass through the phases of an iteration TOGETHER (block-wide barrier between phases), so one
+// fetched line feeds every warp; a slot whose decision has converged books the portfolio step and starts its next
+// decision inside the same trip, so no slot ever idles through a phase.
+template <int H, int G, int P>
+__global__ void __launch_bounds__(32 * G * P, 1)
 backtest_lane_kernel(BacktestArgs A) {
   using Ipm = LaneIpm<H, G>;
   extern __shared__ double smem[];
-  __shared__ int next_b;
+  __shared__ int next_b[P];
+  __shared__ int n_idle;
+  const int slot = __shfl_sync(kFull, (int)threadIdx.x / (32 * G), 0);
   Ipm s;
-  s.bind(smem, A.N);
+  s.bind(smem + (size_t)slot * Ipm::SMEM_DOUBLES, A.N, slot);
   const int N = A.N;
   const IpmOptions opt = A.opt;
+  if (threadIdx.x == 0) n_idle = 0;
+  __syncthreads();
+  // ---- state of the slot's current backtest (replicated in the slot's threads) ----------------------------------
+  int b = 0, t = 0, n = 0, n_opt = 0, n_inacc = 0, n_fail = 0;
+  size_t yb = 0, rb = 0;
+  double lam = 0.0, tau = 0.0, ccoef = 0.0, V = 0.0, wc = 0.0;
+  double mean = 0.0, m2 = 0.0, cum = 1.0, peak = 0.0, maxdd = 0.0, sum_turn = 0.0, v_first = 0.0;
+  long long it_total = 0;
+  float y_next = 0.0f;
+  auto fetch = [&]() -> bool {                     // next backtest of this slot (dynamic: iteration counts differ)
+    if (s.tid == 0) next_b[slot] = atomicAdd(A.work_counter, 1);
+    s.sync();
+    b = __shfl_sync(kFull, next_b[slot], 0);
+    if (b >= A.B) return false;
+    yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
+    rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
+    lam = A.lam ? A.lam[b] : A.lam0;
+    tau = A.tau ? A.tau[b] : A.tau0;
+    ccoef = A.cost_coeff ? A.cost_coeff[b] : A.cost_coeff0;
+    V = A.capital ? A.capital[b] : A.capital0;
+    wc = s.valid ? 1.0 / (double)N : 0.0;                                              // backtest.py:161
+    mean = 0.0; m2 = 0.0; cum = 1.0; peak = -CUDART_INF; maxdd = CUDART_INF; sum_turn = 0.0; v_first = 0.0;
+    t = 0; n = 0; n_opt = 0; n_inacc = 0; n_fail = 0; it_total = 0;
+    return true;
+  };
+  bool active = (A.n_steps > 0) ? fetch() : false;
+  if (!active && s.tid == 0) atomicAdd(&n_idle, 1);
+  bool need_start = true;
+  int st = -1;
+  __syncthreads();
+#pragma unroll 1
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) next_b = atomicAdd(A.work_counter, 1);   // dynamic: backtests differ in iteration counts
-    __syncthreads();
-    const int b = __shfl_sync(kFull, next_b, 0);
-    if (b >= A.B) break;
-    const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
-    const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
-    const double lam = A.lam ? A.lam[b] : A.lam0;
-    const double tau = A.tau ? A.tau[b] : A.tau0;
-    const double ccoef = A.cost_coeff ? A.cost_coeff[b] : A.cost_coeff0;
-    double V = A.capital ? A.capital[b] : A.capital0;
-    double wc = s.valid ? 1.0 / (double)N : 0.0;                                       // backtest.py:161
-    double mean = 0.0, m2 = 0.0, cum = 1.0, peak = -CUDART_INF, maxdd = CUDART_INF, sum_turn = 0.0, v_first = 0.0;
-    int n = 0, n_opt = 0, n_inacc = 0, n_fail = 0;
-    long long it_total = 0;
-    for (int t = 0; t < A.n_steps; t += A.rebalance_freq) {
-      if (s.valid) {
+    if (uni(n_idle >= P)) break;
+    if (active) {
+#pragma unroll 1
+      for (;;) {
+        if (need_start) {
+          if (s.valid) {
 #pragma unroll
-        for (int k = 0; k < H; ++k)
-          s.R[k] = (double)exp_cr32_lane(A.yhat[yb + ((size_t)t * H + k) * N + s.tid]);   // mpc.py:55
+            for (int k = 0; k < H; ++k)
+              s.R[k] = (double)exp_cr32_lane(A.yhat[yb + ((size_t)t * H + k) * N + s.tid]);   // mpc.py:55
+          }
+          y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + s.tid] : 0.0f;
+          st = s.begin(wc, N, lam, tau, A.allow_short != 0, opt);
+          need_start = false;
+        }
+        if (st < 0) st = s.check(opt);
+        if (st < 0) break;                                    // take a Newton step
+        // ---- the decision is made: portfolio step (backtest.py:175-217) ---------------------------------------
+        it_total += s.it_;
+        n_opt += (st == ST_OPTIMAL); n_inacc += (st == ST_INACCURATE); n_fail += (st >= ST_FAILED);
+        const bool market = (t + 1 < A.rows);
+        const double wn = s.valid ? s.w[0] : 0.0;                                          // backtest.py:131
+        float r32 = 0.0f;
+        if (s.valid && market) r32 = __fsub_rn(exp_cr32_lane(y_next), 1.0f);               // backtest.py:193
+        double v[2] = {fabs(wn - wc), wn * (double)r32}, T[2];
+        s.sync();
+        s.template block_sum<2>(v, T);
+        const double turnover = T[0];
+        const double cost = ccoef * turnover * V;
+        V -= cost;
+        double port_ret = 0.0;
+        wc = wn;
+        if (market) {
+          port_ret = T[1];
+          V *= (1.0 + port_ret);
+          double denom = 1.0 + port_ret;
+          if (fabs(denom) < 1e-8) denom = 1e-8;
+          wc = wn * (double)__fadd_rn(1.0f, r32) / denom;                                  // (1.0 + f32) stays f32
+        }
+        if (A.history && s.tid == 0) {
+          double* hrow = A.history + ((size_t)b * A.n_hist + n) * 4;
+          hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
+        }
+        if (n == 0) v_first = V;
+        ++n;
+        const double dlt = port_ret - mean;
+        mean += dlt / (double)n;
+        m2 += dlt * (port_ret - mean);
+        cum *= (1.0 + port_ret);
+        peak = fmax(peak, cum);
+        maxdd = fmin(maxdd, (cum - peak) / peak);
+        sum_turn += turnover;
+        t += A.rebalance_freq;
+        need_start = true; st = -1;
+        if (t >= A.n_steps) {                                  // calculate_metrics (backtest.py:221-249)
+          if (s.tid == 0) {
+            double* m = A.metrics + (size_t)b * 5;
+            const double sd = sqrt(m2 / (double)n);
+            m[0] = sqrt(252.0) * mean / (sd + 1e-8);
+            m[1] = maxdd;
+            m[2] = sum_turn / (double)n;
+            m[3] = V;
+            m[4] = V / v_first - 1.0;
+            if (A.solve_stats) {
+              long long* ss = A.solve_stats + (size_t)b * 4;
+              ss[0] = n_opt; ss[1] = n_inacc; ss[2] = n_fail; ss[3] = it_total;
+            }
+          }
+          if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
+          active = fetch();
+          if (!active) {
+            if (s.tid == 0) atomicAdd(&n_idle, 1);
+            break;
+          }
+        }
       }
-      // realised return of the next day (independent of the solve: issue the load before it)
-      const bool market = (t + 1 < A.rows);
-      float y_next = 0.0f;
-      if (s.valid && market) y_next = A.realized[rb + (size_t)(t + 1) * N + s.tid];
-      int iters; double kkt[3];
-      const int st = s.solve(wc, N, lam, tau, A.allow_short != 0, opt, iters, kkt);
-      it_total += iters;
-      n_opt += (st == ST_OPTIMAL); n_inacc += (st == ST_INACCURATE); n_fail += (st >= ST_FAILED);
-      const double wn = s.valid ? s.w[0] : 0.0;                                          // backtest.py:131
-      float r32 = 0.0f;
-      if (s.valid && market) r32 = __fsub_rn(exp_cr32_lane(y_next), 1.0f);               // backtest.py:193
-      double v[2] = {fabs(wn - wc), wn * (double)r32}, T[2];
-      s.sync();
-      s.template block_sum<2>(v, T);
-      const double turnover = T[0];
-      const double cost = ccoef * turnover * V;
-      V -= cost;
-      double port_ret = 0.0;
-      wc = wn;
-      if (market) {
-        port_ret = T[1];
-        V *= (1.0 + port_ret);
-        double denom = 1.0 + port_ret;
-        if (fabs(denom) < 1e-8) denom = 1e-8;
-        wc = wn * (double)__fadd_rn(1.0f, r32) / denom;                                  // (1.0 + f32) stays f32
-      }
-      if (A.history && threadIdx.x == 0) {
-        double* hrow = A.history + ((size_t)b * A.n_hist + n) * 4;
-        hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
-      }
-      if (n == 0) v_first = V;
-      ++n;
-      const double dlt = port_ret - mean;
-      mean += dlt / (double)n;
-      m2 += dlt * (port_ret - mean);
-      cum *= (1.0 + port_ret);
-      peak = fmax(peak, cum);
-      maxdd = fmin(maxdd, (cum - peak) / peak);
-      sum_turn += turnover;
     }
-    if (threadIdx.x == 0) {
-      double* m = A.metrics + (size_t)b * 5;
-      if (n > 0) {
-        const double sd = sqrt(m2 / (double)n);
-        m[0] = sqrt(252.0) * mean / (sd + 1e-8);
-        m[1] = maxdd;
-        m[2] = sum_turn / (double)n;
-        m[3] = V;
-        m[4] = V / v_first - 1.0;
-      } else { m[0] = m[1] = m[2] = m[3] = m[4] = CUDART_NAN; }
-      if (A.solve_stats) {
-        long long* ss = A.solve_stats + (size_t)b * 4;
-        ss[0] = n_opt; ss[1] = n_inacc; ss[2] = n_fail; ss[3] = it_total;
-      }
+    __syncthreads();                                           // lockstep: all slots enter the factorisation together
+    if (active) s.factor_a();
+    __syncthreads();
+    bool ok = false;
+    if (active) ok = s.factor_b();
+    __syncthreads();
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      if (active && ok) s.newton_phase(phase, opt);
+      __syncthreads();
     }
-    if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
+  }
+  // backtests without any step: NaN metrics (the host never asks for this; kept for completeness)
+  if (A.n_steps <= 0) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < A.B * 5; q += gridDim.x * blockDim.x) A.metrics[q] = CUDART_NAN;
   }
 }
+
+template <int G> struct LaneSlots { static constexpr int P = (G == 1) ? 8 : (G == 2 ? 4 : 2); };
 
 template <typename K>
 static int lane_blocks_per_sm(K kernel, int threads, size_t smem) {
@@ -162,11 +219,15 @@ static int launch_mpc_lane(const MpcSolveArgs& A, int sm_count, cudaStream_t st)
 }
 template <int H, int G>
 static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) {
-  const size_t smem = (size_t)LaneIpm<H, G>::SMEM_DOUBLES * sizeof(double);
-  static const int bps = lane_blocks_per_sm(backtest_lane_kernel<H, G>, 32 * G, smem);
-  int blocks = A.B < sm_count * bps ? A.B : sm_count * bps;
+  // KMPC_LANE_PAD_KB (tuning experiments only): extra dynamic shared memory per block, lowers the blocks per SM
+  static const size_t pad = getenv("KMPC_LANE_PAD_KB") ? (size_t)atoi(getenv("KMPC_LANE_PAD_KB")) * 1024 : 0;
+  constexpr int P = LaneSlots<G>::P;
+  const size_t smem = (size_t)P * LaneIpm<H, G>::SMEM_DOUBLES * sizeof(double) + pad;
+  static const int bps = lane_blocks_per_sm(backtest_lane_kernel<H, G, P>, 32 * G * P, smem);
+  const int want = (A.B + P - 1) / P;
+  int blocks = want < sm_count * bps ? want : sm_count * bps;
   if (blocks < 1) blocks = 1;
-  backtest_lane_kernel<H, G><<<blocks, 32 * G, smem, st>>>(A);
+  backtest_lane_kernel<H, G, P><<<blocks, 32 * G * P, smem, st>>>(A);
   return (int)cudaGetLastError();
 }
 
