@@ -155,6 +155,11 @@ int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, i
  * 0 = fp32 SIMT everywhere) and run one bare GEMM C[M,Nout] = A[M,K] . W[Nout,K]^T through a chosen kernel
  * (mode 0 = SIMT, 1 = tcgen05; KMPC_E_CUDA with "not eligible" if the shape cannot use it). */
 int kmpc_set_gemm_mode(int use_tensor_cores);
+/* 1 [default]: when the latent step and the read-out are linear (GenericKM with NORM_FN 'id' and a one-layer
+ * decoder, or LISTAKM) kmpc_forecast evaluates all H horizons with ONE GEMM against the pre-multiplied matrices
+ * D_N (K^T)^(k+1) (built in fp64 at first use); 0: always step z <- z K and decode H times like backtest.py:107-121.
+ * Same forecasts within fp32 rounding (tests: 1e-5 relative, norm-wise). */
+int kmpc_set_forecast_fold(int on);
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode);
 
 /* ---------------------------------------------------------------------------------------------

@@ -36,6 +36,10 @@ struct kmpc_model {
   float* lista_wdT_lo;
   float* z_lo;                 // residual twin of the standardised series of the current forecast call
   size_t z_lo_cap;
+  // folded multi-horizon read-out (linear step + linear decoder): row k*N + a of fold_w = D_N[a,:] . (K^T)^(k+1),
+  // so that yhat[:, k, :] = z0 . fold_w[k]^T.  Built on first use for the largest H seen.
+  int fold_H;
+  float* fold_w; float* fold_w_lo; float* fold_b;
   std::vector<void*> owned;
 };
 
@@ -109,6 +113,30 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
     out[i] = __double2float_rn(in[i]);
 }
 
+// one warp per output: out[a, j] = sum_i prev[a, i] * K[j, i]   (fp64 accumulation; prev is fp64, K fp32)
+__global__ void fold_step_kernel(const double* __restrict__ prev, const float* __restrict__ kmat, int N, int Z,
+                                 double* __restrict__ next, float* __restrict__ w32) {
+  const long long o = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= (long long)N * Z) return;
+  const int a = (int)(o / Z), j = (int)(o - (long long)a * Z);
+  double s = 0.0;
+  for (int i = lane; i < Z; i += 32) s = fma(prev[(size_t)a * Z + i], (double)kmat[(size_t)j * Z + i], s);
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) { next[o] = s; w32[o] = __double2float_rn(s); }
+}
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (double)in[i];
+}
+__global__ void tile_bias_kernel(const float* __restrict__ b, int N, int H, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * H) out[i] = b[i % N];
+}
+
+static int g_fold = 1;
+void set_forecast_fold(int on) { g_fold = on ? 1 : 0; }
+
 static int act_to_epi(int act) { return act == KMPC_ACT_RELU ? EPI_RELU : (act == KMPC_ACT_TANH ? EPI_TANH : EPI_GELU); }
 
 struct AView {            // how the rows of the first GEMM are addressed
@@ -121,6 +149,8 @@ static GemmArgs base_args() {
   g.act = EPI_NONE;
   return g;
 }
+
+static int ensure_fold(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st);
 
 // Runs the whole chain for `M` rows.  out_mode 0: latent z0 -> out [M,Z];  1: yhat de-standardised [M,H,N];
 // 2: standardised decoder output, first n_cols columns [M,H,n_cols].
@@ -159,6 +189,13 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
     return nullptr;
   };
   int rc;
+  // z_{k+1} = z_k K and a linear read-out compose into one matrix per horizon (model.py:311-321 with NORM_FN 'id',
+  // decoder = one Linear, or the LISTAKM dictionary): the H sequential [rows,Z]x[Z,Z] products collapse into one
+  // [rows,Z]x[Z,H*N] product.  Algebraically identical, rounding differs at the fp32 level (tests: 1e-5 norm-wise).
+  const bool fold = g_fold && out_mode == 1 && H >= 1 &&
+                    ((m->kind == KMPC_MODEL_GENERIC && m->norm_fn == KMPC_NORM_ID && m->n_dec == 1) ||
+                     (m->kind == KMPC_MODEL_LISTA));
+  if (fold && (rc = ensure_fold(h, const_cast<kmpc_model*>(m), H, st))) return rc;
   for (int r0 = 0; r0 < M; r0 += CH) {
     const int rows = (M - r0 < CH) ? (M - r0) : CH;
     // ---------------- encoder ----------------
@@ -216,6 +253,18 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
       if (e != cudaSuccess) return kmpc_fail_cuda(e, "copy latent");
       continue;
     }
+    // ---------------- folded read-out: all horizons in one GEMM [rows, Z] x [H*N, Z]^T ----------------
+    if (fold) {
+      GemmArgs d = base_args();
+      d.A = zcur; d.A_lo = lo_of_buf(zcur); d.a_rows_per_group = rows; d.lda = Z; d.K = Z;
+      d.W = m->fold_w; d.W_lo = m->fold_w_lo; d.ldw = Z;
+      d.M = rows; d.Nout = H * m->N; d.n_store = H * m->N; d.bias = m->fold_b;
+      d.C = out + (size_t)r0 * H * m->N; d.ldc = (long long)H * m->N;
+      d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.stat_row0 = r0;
+      d.stat_mod = m->N;
+      if ((rc = launch_gemm(d, st, &h->launches))) return rc;
+      continue;
+    }
     // ---------------- K unroll + decoder ----------------
     float* znext = (zcur == buf[2]) ? buf[0] : buf[2];
     float* hbuf[2] = {buf[1], buf[3]};
@@ -261,6 +310,52 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
 }  // namespace kmpc
 
 // ------------------------------------------------------------------------------------------------------------
+namespace kmpc {
+// fold_w rows [k*N + a] = D_N[a,:] . (K^T)^(k+1) for k < H, built in fp64 and rounded once to fp32 (+ residual twin)
+static int ensure_fold(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st) {
+  if (m->fold_w && m->fold_H >= H) return 0;
+  const int N = m->N, Z = m->Z;
+  const float* DN = (m->kind == KMPC_MODEL_GENERIC) ? m->dec_w[0] : m->lista_wdT;      // [obs, Z], first N rows
+  const float* bN = (m->kind == KMPC_MODEL_GENERIC) ? m->dec_b[0] : nullptr;
+  float *w = nullptr, *wl = nullptr, *fb = nullptr;
+  double* tmp = nullptr;
+  cudaError_t e;
+  const size_t rows_pad = (size_t)((H * N + 127) / 128) * 128;      // whole 128-row TMA boxes
+  if ((e = cudaMalloc(&w, rows_pad * Z * sizeof(float))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(fold)");
+  if ((e = cudaMalloc(&wl, rows_pad * Z * sizeof(float))) != cudaSuccess) { cudaFree(w); return kmpc_fail_cuda(e, "cudaMalloc(fold)"); }
+  if ((e = cudaMalloc(&tmp, (size_t)2 * N * Z * sizeof(double))) != cudaSuccess) { cudaFree(w); cudaFree(wl); return kmpc_fail_cuda(e, "cudaMalloc(fold)"); }
+  cudaMemsetAsync(w, 0, rows_pad * Z * sizeof(float), st);
+  double* cur = tmp; double* nxt = tmp + (size_t)N * Z;
+  f32_to_f64_kernel<<<h->sm_count * 2, 256, 0, st>>>(DN, cur, (long long)N * Z);
+  const float* kmat = nullptr;
+  // kmatT holds K^T; out[a,j] = sum_i prev[a,i] K[j,i] reads row j of K = column j of K^T: use a transposed copy
+  float* kplain = nullptr;
+  if ((e = cudaMalloc(&kplain, (size_t)Z * Z * sizeof(float))) != cudaSuccess) { cudaFree(w); cudaFree(wl); cudaFree(tmp); return kmpc_fail_cuda(e, "cudaMalloc(fold)"); }
+  {
+    dim3 grid((Z + 31) / 32, (Z + 31) / 32), blk(32, 8);
+    transpose_kernel<<<grid, blk, 0, st>>>(m->kmatT, Z, Z, kplain);
+    kmat = kplain;
+  }
+  const long long outs = (long long)N * Z;
+  for (int k = 0; k < H; ++k) {
+    fold_step_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, st>>>(cur, kmat, N, Z, nxt, w + (size_t)k * N * Z);
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  int rc = launch_split_lo(w, wl, (long long)rows_pad * Z, st);
+  if (!rc && bN) {
+    if ((e = cudaMalloc(&fb, (size_t)H * N * sizeof(float))) != cudaSuccess) rc = (int)e;
+    else tile_bias_kernel<<<(H * N + 255) / 256, 256, 0, st>>>(bN, N, H, fb);
+  }
+  e = cudaStreamSynchronize(st);
+  cudaFree(tmp); cudaFree(kplain);
+  if (rc || e != cudaSuccess) { cudaFree(w); cudaFree(wl); if (fb) cudaFree(fb); return kmpc_fail_cuda(rc ? (cudaError_t)rc : e, "fold kernels"); }
+  if (m->fold_w) { cudaFree(m->fold_w); cudaFree(m->fold_w_lo); if (m->fold_b) cudaFree(m->fold_b); }
+  m->fold_w = w; m->fold_w_lo = wl; m->fold_b = fb; m->fold_H = H;
+  h->launches += 4 + H;
+  return 0;
+}
+}  // namespace kmpc
+
 static thread_local char f_err[256];
 static int ffail(int code, const char* msg) { snprintf(f_err, sizeof(f_err), "%s", msg); return code; }
 #define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return kmpc_fail_cuda(e_, #call); } while (0)
@@ -290,6 +385,8 @@ int kmpc_model_free(kmpc_model* m) {
   cudaSetDevice(m->h->device);
   for (void* p : m->owned) cudaFree(p);
   if (m->z_lo) cudaFree(m->z_lo);
+  if (m->fold_w) { cudaFree(m->fold_w); cudaFree(m->fold_w_lo); }
+  if (m->fold_b) cudaFree(m->fold_b);
   delete m;
   return KMPC_OK;
 }
@@ -307,6 +404,7 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
   m->lista_linear = D->lista_linear_encoder; m->lista_loops = D->lista_loops; m->lista_thr = D->lista_threshold;
   m->lista_ST = nullptr; m->lista_wdT = nullptr; m->lista_ST_lo = nullptr; m->lista_wdT_lo = nullptr; m->kmatT_lo = nullptr; m->enc_w0_win_lo = nullptr;
   m->z_lo = nullptr; m->z_lo_cap = 0;
+  m->fold_H = 0; m->fold_w = nullptr; m->fold_w_lo = nullptr; m->fold_b = nullptr;
   int rc = 0;
   auto bail = [&](int code) { kmpc_model_free(m); return code; };
   const bool mlp_enc = (D->kind == KMPC_MODEL_GENERIC) || !D->lista_linear_encoder;
@@ -496,6 +594,7 @@ int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, floa
 // ---- diagnostics -------------------------------------------------------------------------------------------
 // 1 = tcgen05 3xTF32 GEMM where eligible (default), 0 = fp32 SIMT GEMM everywhere.  Process-wide.
 int kmpc_set_gemm_mode(int use_tensor_cores) { kmpc::set_gemm_tc_mode(use_tensor_cores); return KMPC_OK; }
+int kmpc_set_forecast_fold(int on) { kmpc::set_forecast_fold(on); return KMPC_OK; }
 
 // C[M,Nout] = A[M,K] . W[Nout,K]^T through one chosen kernel: mode 0 = SIMT fp32, 1 = tcgen05 3xTF32 (returns
 // KMPC_E_UNSUPPORTED if the shape is not eligible).  Allocates the residual twins internally; synchronous.

@@ -35,6 +35,7 @@ struct GemmArgs {
   int stat_rows_per_group;
   int stat_ld;
   int stat_row0;       // logical index of row 0 of this launch for the statistics lookup
+  int stat_mod;        // > 0: statistics column = output column % stat_mod (folded multi-horizon output [H*N])
   float* C;            // output, row stride ldc, only columns < n_store are written
   long long ldc;
   int n_store;

@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
       if (g.bias) x += g.bias[n];
       if (g.addend) x += g.addend[(long long)m * g.ld_add + n];
       x = epilogue_apply(x, g.act, g.shrink_thr);
-      if (g.std32) x = __fadd_rn(__fmul_rn(x, g.std32[(long long)sg * g.stat_ld + n]), g.mean32[(long long)sg * g.stat_ld + n]);
+      if (g.std32) {
+        const int sn = g.stat_mod ? n % g.stat_mod : n;
+        x = __fadd_rn(__fmul_rn(x, g.std32[(long long)sg * g.stat_ld + sn]), g.mean32[(long long)sg * g.stat_ld + sn]);
+      }
       g.C[(long long)m * g.ldc + n] = x;
       if (g.C_lo) {
         const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);

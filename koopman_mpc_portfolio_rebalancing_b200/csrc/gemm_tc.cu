@@ -47,7 +47,7 @@ struct Params {
   const float* bias;
   const float* addend; int ld_add;
   int act; float shrink_thr;
-  const float* std32; const float* mean32; int stat_rows_per_group; int stat_ld; int row0;   // de-standardise epilogue
+  const float* std32; const float* mean32; int stat_rows_per_group; int stat_ld; int row0; int stat_mod;   // de-standardise epilogue
   float* C; float* C_lo; long long ldc; int n_store;
 };
 
@@ -265,8 +265,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (arow) t += arow[j4 * 4 + j];
               }
               t = epilogue_apply(t, p.act, p.shrink_thr);
-              if (p.std32 && n < p.n_store)
-                t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + n]), p.mean32[sg * p.stat_ld + n]);
+              if (p.std32 && n < p.n_store) {
+                const int sn = p.stat_mod ? n % p.stat_mod : n;
+                t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + sn]), p.mean32[sg * p.stat_ld + sn]);
+              }
               x[j] = t;
               lo[j] = t - __uint_as_float(__float_as_uint(t) & 0xffffe000u);
             }
@@ -351,7 +353,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.k_blocks = (g.K + BK - 1) / BK;
   p.bias = g.bias; p.addend = g.addend; p.ld_add = g.ld_add; p.act = g.act; p.shrink_thr = g.shrink_thr;
   p.C = g.C; p.C_lo = g.C_lo; p.ldc = g.ldc; p.n_store = g.n_store < g.Nout ? g.n_store : g.Nout;
-  p.std32 = g.std32; p.mean32 = g.mean32; p.stat_rows_per_group = g.stat_rows_per_group; p.stat_ld = g.stat_ld; p.row0 = g.stat_row0;
+  p.std32 = g.std32; p.mean32 = g.mean32; p.stat_rows_per_group = g.stat_rows_per_group; p.stat_ld = g.stat_ld; p.row0 = g.stat_row0; p.stat_mod = g.stat_mod;
 
   const long long a_off = flat ? (long long)g.row0 * g.lda
                                : (long long)(g.row0 / g.a_rows_per_group) * g.a_group_stride;

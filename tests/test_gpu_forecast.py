@@ -149,3 +149,43 @@ def test_multi_chunk_forecast_with_partial_last_chunk():
         want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
         worst = max(worst, rowwise_rel(y[b], want))
     assert worst < FORECAST_RTOL, worst
+
+
+@pytest.mark.parametrize("kind", ["generic", "lista"])
+def test_folded_readout_matches_sequential_steps(kind):
+    """kmpc_forecast evaluates all horizons with one GEMM against D_N (K^T)^(k+1) when step and read-out are linear
+    (kmpc_set_forecast_fold, default on).  Must agree with the step-by-step chain (fold off) and with the oracle."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, data_finance as df, model as km, synthetic
+    from oracle import forecast_oracle as fo, data_oracle as do
+    rng = np.random.default_rng(21)
+    B, T, N, d, H = 4, 200, 12, 8, 5
+    lr = rng.standard_normal((B, T, N)) * 0.012
+    mean = rng.normal(3e-4, 1e-4, (B, N)); std = rng.uniform(0.008, 0.02, (B, N))
+    if kind == "generic":
+        Z = 128
+        sd = synthetic.generic_km_weights(4, N * d, [128, 128], Z)
+        m = km.make_model(km.model_config("GenericKM", Z, [128, 128], enc_bias=True), N * d)
+        spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    else:
+        Z = 256
+        sd, L = synthetic.lista_km_weights(3, N * d, Z)
+        m = km.make_model(km.model_config("LISTAKM", Z, lista_loops=10, lista_L=L, lista_alpha=5e-3, lista_linear=True), N * d)
+        spec = fo.ModelSpec(kind="lista", linear_encoder=True, alpha=5e-3, L=L, loops=10, act="relu", last_relu=False)
+    m.load_state_dict(sd)
+    z = df.standardize_device(lr, mean, std)
+    mean_d, std_d = torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda()
+    rows = T - d + 1
+    try:
+        _capi.lib().kmpc_set_forecast_fold(0)
+        y_seq = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, rows, H).cpu().numpy()
+    finally:
+        _capi.lib().kmpc_set_forecast_fold(1)
+    y_fold = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, rows, H).cpu().numpy()
+    assert not np.array_equal(y_seq, y_fold) or H == 1      # two different evaluation orders really ran
+    for b in range(B):
+        assert rowwise_rel(y_fold[b], y_seq[b]) < FORECAST_RTOL
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)
+        want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
+        assert rowwise_rel(y_fold[b], want) < FORECAST_RTOL
+        assert rowwise_rel(y_seq[b], want) < FORECAST_RTOL
