@@ -78,11 +78,13 @@ struct LaneIpm {
   static_assert(NB + 1 <= 32, "H too large: the border must fit one row per lane");
 
   // ---- shared memory of one problem (doubles) -------------------------------------------------------------------
-  enum : int { F_QL, F_TL, F_QR, F_TR, F_GJJ, F_VD, F_FL, F_FR, NFAC };    // sweep factors [H][NT]
+  // sweep factors [stage][NT]; stage 0 of QL,TL,QR,TR,FL,FR is constant (1,0,0,0,1,0) and not stored
+  enum : int { F_GJJ, F_VD, F_QL, F_TL, F_QR, F_TR, F_FL, F_FR, NFAC };
+  static constexpr int FAC_ROWS = 2 * H + 6 * (H - 1);
   enum : int { T_CW, T_CP, T_CQ, NTGT };                                    // complementarity targets [H][NT]
   enum : int { U_NU, U_SC, U_ZC, U_RHO, U_IRHO, U_ISC, U_RP, U_CC, NUNI };
   static constexpr int OFF_FAC = 0;
-  static constexpr int OFF_TILE = OFF_FAC + NFAC * H * NT;                  // reduction tile, rows of LD doubles
+  static constexpr int OFF_TILE = OFF_FAC + FAC_ROWS * NT;                  // reduction tile, rows of LD doubles
   static constexpr int SMALL_ROWS = NB + 1;                                 // rows usable while the targets are live
   static constexpr int TILE_A = KB * LD;
   static constexpr int TILE_B = SMALL_ROWS * LD + NTGT * H * NT;
@@ -114,7 +116,10 @@ struct LaneIpm {
     valid = tid < n_assets;
     fact_ok_ = true; it_ = 0;
   }
-  __device__ __forceinline__ double& FAC(int arr, int k) const { return sm[OFF_FAC + (arr * H + k) * NT + tid]; }
+  __device__ __forceinline__ double& FAC(int arr, int k) const {      // arr >= F_QL requires k >= 1
+    const int row = (arr < F_QL) ? arr * H + k : 2 * H + (arr - F_QL) * (H - 1) + (k - 1);
+    return sm[OFF_FAC + row * NT + tid];
+  }
   __device__ __forceinline__ double& TGT(int arr, int k) const { return sm[OFF_TGT + (arr * H + k) * NT + tid]; }
   __device__ __forceinline__ double& U(int arr, int k) const { return sm[OFF_U + arr * H + k]; }
   __device__ __forceinline__ void sync() const {
@@ -208,8 +213,8 @@ struct LaneIpm {
 #pragma unroll
     for (int k = 0; k < H; ++k) {
       dw[k] = FAC(F_GJJ, k) * (JL[k] + inc[k]);
-      double t = fma(FAC(F_FL, k), JR[k], -pg[k]);
-      if (k > 0) t = fma(-FAC(F_FR, k), JL[(k > 0) ? k - 1 : 0], t);
+      double t = JR[k] - pg[k];                                        // fL[0] = 1, fR[0] = 0
+      if (k > 0) t = fma(-FAC(F_FR, k), JL[(k > 0) ? k - 1 : 0], fma(FAC(F_FL, k), JR[k], -pg[k]));
       dd[k] = FAC(F_VD, k) * t;
     }
   }
@@ -277,8 +282,11 @@ struct LaneIpm {
       }
       vd[k] = rcp_fast(fma(hR[k], fL[k], e[k]));
       if (!valid) { gjj[k] = 0.0; vd[k] = 0.0; ie[k] = 0.0; }     // padding lanes contribute exact zeros everywhere
-      FAC(F_QL, k) = qL[k]; FAC(F_TL, k) = tL[k]; FAC(F_QR, k) = qR[k]; FAC(F_TR, k) = tR[k];
-      FAC(F_GJJ, k) = gjj[k]; FAC(F_VD, k) = vd[k]; FAC(F_FL, k) = fL[k]; FAC(F_FR, k) = fR[k];
+      FAC(F_GJJ, k) = gjj[k]; FAC(F_VD, k) = vd[k];
+      if (k > 0) {
+        FAC(F_QL, k) = qL[k]; FAC(F_TL, k) = tL[k]; FAC(F_QR, k) = qR[k]; FAC(F_TR, k) = tR[k];
+        FAC(F_FL, k) = fL[k]; FAC(F_FR, k) = fR[k];
+      }
     }
     // ---- border matrix: emit the entries in KMap order, KB at a time --------------------------------------------
     if (warp == 0) {                                 // clear K (rows >= 2H stay identity when there is no cap)

@@ -6,6 +6,12 @@
 #include "mpc_lane.cuh"
 #include <stdlib.h>
 
+// register budget of the backtest kernel: __maxnreg__ and __launch_bounds__ are mutually exclusive
+#ifdef KMPC_LANE_MAXNREG
+#define KMPC_LANE_BT_ATTR(threads) __maxnreg__(KMPC_LANE_MAXNREG)
+#else
+#define KMPC_LANE_BT_ATTR(threads) __launch_bounds__(threads, 1)
+#endif
 #ifndef KMPC_LANE_MINB
 #define KMPC_LANE_MINB 1      // resident blocks per SM the register allocation is sized for (0/1 = no cap)
 #endif
@@ -60,41 +66,47 @@ mpc_solve_lane_kernel(MpcSolveArgs A) {
 // slots of the SM pass through the phases of an iteration TOGETHER (block-wide barrier between phases), so one
 // fetched line feeds every warp; a slot whose decision has converged books the portfolio step and starts its next
 // decision inside the same trip, so no slot ever idles through a phase.
+// Book-keeping of one slot's current backtest (backtest.py:161-217, 221-249).  Lives in shared memory and is
+// touched by thread 0 of the slot only: as registers it would cost every thread of the kernel ~30 registers.
+struct SlotBook {
+  double V, ccoef, mean, m2, cum, peak, maxdd, sum_turn, v_first;
+  long long it_total;
+  int n, n_opt, n_inacc, n_fail;
+};
+
 template <int H, int G, int P>
-__global__ void __launch_bounds__(32 * G * P, 1)
+__global__ void KMPC_LANE_BT_ATTR(32 * G * P)
 backtest_lane_kernel(BacktestArgs A) {
   using Ipm = LaneIpm<H, G>;
   extern __shared__ double smem[];
   __shared__ int next_b[P];
   __shared__ int n_idle;
+  __shared__ SlotBook books[P];
   const int slot = __shfl_sync(kFull, (int)threadIdx.x / (32 * G), 0);
   Ipm s;
   s.bind(smem + (size_t)slot * Ipm::SMEM_DOUBLES, A.N, slot);
   const int N = A.N;
-  const IpmOptions opt = A.opt;
+  const IpmOptions& opt = A.opt;
   if (threadIdx.x == 0) n_idle = 0;
   __syncthreads();
-  // ---- state of the slot's current backtest (replicated in the slot's threads) ----------------------------------
-  int b = 0, t = 0, n = 0, n_opt = 0, n_inacc = 0, n_fail = 0;
-  size_t yb = 0, rb = 0;
-  double lam = 0.0, tau = 0.0, ccoef = 0.0, V = 0.0, wc = 0.0;
-  double mean = 0.0, m2 = 0.0, cum = 1.0, peak = 0.0, maxdd = 0.0, sum_turn = 0.0, v_first = 0.0;
-  long long it_total = 0;
-  float y_next = 0.0f;
+  // ---- per-thread state of the slot's current backtest ----------------------------------------------------------
+  int b = 0, t = 0;
+  double wc = 0.0;                                 // my asset's current weight
+  float y_next = 0.0f;                             // realised log-return of my asset on the day after the decision
   auto fetch = [&]() -> bool {                     // next backtest of this slot (dynamic: iteration counts differ)
     if (s.tid == 0) next_b[slot] = atomicAdd(A.work_counter, 1);
     s.sync();
     b = __shfl_sync(kFull, next_b[slot], 0);
     if (b >= A.B) return false;
-    yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
-    rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
-    lam = A.lam ? A.lam[b] : A.lam0;
-    tau = A.tau ? A.tau[b] : A.tau0;
-    ccoef = A.cost_coeff ? A.cost_coeff[b] : A.cost_coeff0;
-    V = A.capital ? A.capital[b] : A.capital0;
     wc = s.valid ? 1.0 / (double)N : 0.0;                                              // backtest.py:161
-    mean = 0.0; m2 = 0.0; cum = 1.0; peak = -CUDART_INF; maxdd = CUDART_INF; sum_turn = 0.0; v_first = 0.0;
-    t = 0; n = 0; n_opt = 0; n_inacc = 0; n_fail = 0; it_total = 0;
+    t = 0;
+    if (s.tid == 0) {
+      SlotBook& k = books[slot];
+      k.V = A.capital ? A.capital[b] : A.capital0;
+      k.ccoef = A.cost_coeff ? A.cost_coeff[b] : A.cost_coeff0;
+      k.mean = 0.0; k.m2 = 0.0; k.cum = 1.0; k.peak = -CUDART_INF; k.maxdd = CUDART_INF; k.sum_turn = 0.0; k.v_first = 0.0;
+      k.it_total = 0; k.n = 0; k.n_opt = 0; k.n_inacc = 0; k.n_fail = 0;
+    }
     return true;
   };
   bool active = (A.n_steps > 0) ? fetch() : false;
@@ -109,20 +121,20 @@ backtest_lane_kernel(BacktestArgs A) {
 #pragma unroll 1
       for (;;) {
         if (need_start) {
+          const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
+          const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
           if (s.valid) {
 #pragma unroll
             for (int k = 0; k < H; ++k)
               s.R[k] = (double)exp_cr32_lane(A.yhat[yb + ((size_t)t * H + k) * N + s.tid]);   // mpc.py:55
           }
           y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + s.tid] : 0.0f;
-          st = s.begin(wc, N, lam, tau, A.allow_short != 0, opt);
+          st = s.begin(wc, N, A.lam ? A.lam[b] : A.lam0, A.tau ? A.tau[b] : A.tau0, A.allow_short != 0, opt);
           need_start = false;
         }
         if (st < 0) st = s.check(opt);
         if (st < 0) break;                                    // take a Newton step
         // ---- the decision is made: portfolio step (backtest.py:175-217) ---------------------------------------
-        it_total += s.it_;
-        n_opt += (st == ST_OPTIMAL); n_inacc += (st == ST_INACCURATE); n_fail += (st >= ST_FAILED);
         const bool market = (t + 1 < A.rows);
         const double wn = s.valid ? s.w[0] : 0.0;                                          // backtest.py:131
         float r32 = 0.0f;
@@ -131,46 +143,52 @@ backtest_lane_kernel(BacktestArgs A) {
         s.sync();
         s.template block_sum<2>(v, T);
         const double turnover = T[0];
-        const double cost = ccoef * turnover * V;
-        V -= cost;
-        double port_ret = 0.0;
+        const double port_ret = market ? T[1] : 0.0;
         wc = wn;
         if (market) {
-          port_ret = T[1];
-          V *= (1.0 + port_ret);
           double denom = 1.0 + port_ret;
           if (fabs(denom) < 1e-8) denom = 1e-8;
           wc = wn * (double)__fadd_rn(1.0f, r32) / denom;                                  // (1.0 + f32) stays f32
         }
-        if (A.history && s.tid == 0) {
-          double* hrow = A.history + ((size_t)b * A.n_hist + n) * 4;
-          hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
-        }
-        if (n == 0) v_first = V;
-        ++n;
-        const double dlt = port_ret - mean;
-        mean += dlt / (double)n;
-        m2 += dlt * (port_ret - mean);
-        cum *= (1.0 + port_ret);
-        peak = fmax(peak, cum);
-        maxdd = fmin(maxdd, (cum - peak) / peak);
-        sum_turn += turnover;
         t += A.rebalance_freq;
-        need_start = true; st = -1;
-        if (t >= A.n_steps) {                                  // calculate_metrics (backtest.py:221-249)
-          if (s.tid == 0) {
+        const bool last = (t >= A.n_steps);
+        if (s.tid == 0) {
+          SlotBook& k = books[slot];
+          k.it_total += s.it_;
+          k.n_opt += (st == ST_OPTIMAL); k.n_inacc += (st == ST_INACCURATE); k.n_fail += (st >= ST_FAILED);
+          const double cost = k.ccoef * turnover * k.V;
+          double V = k.V - cost;
+          if (market) V *= (1.0 + port_ret);
+          k.V = V;
+          if (A.history) {
+            double* hrow = A.history + ((size_t)b * A.n_hist + k.n) * 4;
+            hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
+          }
+          if (k.n == 0) k.v_first = V;
+          const int n = ++k.n;
+          const double dlt = port_ret - k.mean;
+          k.mean += dlt / (double)n;
+          k.m2 += dlt * (port_ret - k.mean);
+          k.cum *= (1.0 + port_ret);
+          k.peak = fmax(k.peak, k.cum);
+          k.maxdd = fmin(k.maxdd, (k.cum - k.peak) / k.peak);
+          k.sum_turn += turnover;
+          if (last) {                                          // calculate_metrics (backtest.py:221-249)
             double* m = A.metrics + (size_t)b * 5;
-            const double sd = sqrt(m2 / (double)n);
-            m[0] = sqrt(252.0) * mean / (sd + 1e-8);
-            m[1] = maxdd;
-            m[2] = sum_turn / (double)n;
+            const double sd = sqrt(k.m2 / (double)n);
+            m[0] = sqrt(252.0) * k.mean / (sd + 1e-8);
+            m[1] = k.maxdd;
+            m[2] = k.sum_turn / (double)n;
             m[3] = V;
-            m[4] = V / v_first - 1.0;
+            m[4] = V / k.v_first - 1.0;
             if (A.solve_stats) {
               long long* ss = A.solve_stats + (size_t)b * 4;
-              ss[0] = n_opt; ss[1] = n_inacc; ss[2] = n_fail; ss[3] = it_total;
+              ss[0] = k.n_opt; ss[1] = k.n_inacc; ss[2] = k.n_fail; ss[3] = k.it_total;
             }
           }
+        }
+        need_start = true; st = -1;
+        if (last) {
           if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
           active = fetch();
           if (!active) {
@@ -198,7 +216,10 @@ backtest_lane_kernel(BacktestArgs A) {
   }
 }
 
-template <int G> struct LaneSlots { static constexpr int P = (G == 1) ? 8 : (G == 2 ? 4 : 2); };
+#ifndef KMPC_LANE_SLOT_WARPS
+#define KMPC_LANE_SLOT_WARPS 8      // warps per block = slots per block x G
+#endif
+template <int G> struct LaneSlots { static constexpr int P = (KMPC_LANE_SLOT_WARPS / G) < 1 ? 1 : (KMPC_LANE_SLOT_WARPS / G); };
 
 template <typename K>
 static int lane_blocks_per_sm(K kernel, int threads, size_t smem) {
