@@ -90,7 +90,7 @@ struct LaneIpm {
   static constexpr int TILE_B = SMALL_ROWS * LD + NTGT * H * NT;
   static constexpr int TILE_DOUBLES = ((TILE_A > TILE_B ? TILE_A : TILE_B) + 1) & ~1;
   static constexpr int OFF_TGT = OFF_TILE + TILE_DOUBLES - NTGT * H * NT;  // targets = tail of the tile
-  static constexpr int OFF_K = OFF_TILE + TILE_DOUBLES;                     // [NB*NB] K / Cholesky factor, [NB] 1/diag
+  static constexpr int OFF_K = OFF_TILE + TILE_DOUBLES;                     // [NB*NB] K / unit-lower factor L, [NB] 1/D
   static constexpr int OFF_T = OFF_K + NB * NB + NB + ((NB * NB + NB) & 1); // [32] border right-hand side / solution
   static constexpr int OFF_P = OFF_T + 32;                                  // [2][G][32] per-warp partials
   static constexpr int OFF_U = OFF_P + 2 * G * 32;                          // [NUNI][H] stage scalars
@@ -159,6 +159,35 @@ struct LaneIpm {
     double t = P[e];
 #pragma unroll
     for (int g = 1; g < G; ++g) t += P[g * 32 + e];
+    return t;
+  }
+  // rows [0, NMAX) are max-reduced (non-negative values, 0 in padding threads), rows [NMAX, NV) summed
+  template <int NMAX, int NV>
+  __device__ __forceinline__ void tile_reduce_mixed(const double (&v)[NV]) {
+    static_assert(NV <= SMALL_ROWS, "tile too small");
+#pragma unroll
+    for (int e = 0; e < NV; ++e) sm[OFF_TILE + e * LD + tid] = v[e];
+    sync();
+    double s = 0.0;
+    if (lane < NV) {
+      const double2* p = reinterpret_cast<const double2*>(sm + OFF_TILE + lane * LD + 32 * warp);
+      double m0 = 0.0, m1 = 0.0, s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const double2 a = p[m];
+        m0 = fmax(m0, a.x); m1 = fmax(m1, a.y); s0 += a.x; s1 += a.y;
+      }
+      s = (lane < NMAX) ? fmax(m0, m1) : s0 + s1;
+    }
+    psel ^= 1;
+    sm[OFF_P + psel * G * 32 + warp * 32 + lane] = s;
+    sync();
+  }
+  __device__ __forceinline__ double ptotal_max(int e) const {
+    const double* P = sm + OFF_P + psel * G * 32;
+    double t = P[e];
+#pragma unroll
+    for (int g = 1; g < G; ++g) t = fmax(t, P[g * 32 + e]);
     return t;
   }
   template <int NV>
@@ -347,33 +376,35 @@ struct LaneIpm {
     sync();
   }
 
-  // Cholesky of K by warp 0: lane = row, row in registers, columns exchanged by shuffles.  False on a
+  // L D L' factorisation of K by warp 0: lane = row, row in registers, columns exchanged by shuffles.  False on a
   // non-positive pivot.
   __device__ __forceinline__ bool factor_b() {
     if (warp == 0) {
       const int nb = has_c ? 3 * H : 2 * H;
-      double a[NB];
       const int r = (lane < NB) ? lane : NB - 1;
+      if (lane < NB) {             // diagonal terms 1/beta_k = rho_k^2 and sc_k / zc_k, added in place (a lane-indexed
+        double add = 0.0;          // update of the register row would push the whole row to local memory)
+        if (lane < H) { const double rho = U(U_RHO, lane); add = rho * rho; }
+        if (has_c && lane >= 2 * H) add = U(U_SC, lane - 2 * H) * rcp_fast(U(U_ZC, lane - 2 * H));
+        sm[OFF_K + lane * NB + lane] += add;
+      }
+      __syncwarp();
+      double a[NB];
 #pragma unroll
       for (int c = 0; c < NB; ++c) a[c] = (c <= lane) ? sm[OFF_K + r * NB + c] : 0.0;
-      {
-        double add = 0.0;
-        if (lane < H) { const double rho = U(U_RHO, lane); add = rho * rho; }                       // 1/beta_k
-        if (has_c && lane >= 2 * H && lane < NB) add = U(U_SC, lane - 2 * H) * rcp_fast(U(U_ZC, lane - 2 * H));
-#pragma unroll
-        for (int c = 0; c < NB; ++c) if (c == lane) a[c] += add;
-      }
+      // K = L D L' (unit lower L): no square root, and the column broadcast shfl(a[j], c) does not wait for 1/D_j
       bool pd = true;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const double djj = shfl_d(a[j], j);
+        const double aj = a[j];                              // row `lane`, column j, before scaling
+        const double djj = shfl_d(aj, j);
         if (!(djj > 0.0) && j < nb) pd = false;
-        const double inv = rsqrt(djj);
-        const double l = a[j] * inv;                         // L[lane][j] (lanes >= j)
+        const double inv = rcp_fast(djj);
+        const double l = aj * inv;                           // L[lane][j] (lanes > j)
         a[j] = l;
         if (lane == j) sm[OFF_K + NB * NB + j] = inv;
 #pragma unroll
-        for (int c = j + 1; c < NB; ++c) a[c] = fma(-l, shfl_d(l, c), a[c]);
+        for (int c = j + 1; c < NB; ++c) a[c] = fma(-l, shfl_d(aj, c), a[c]);
       }
       if (lane < NB) {
 #pragma unroll
@@ -399,15 +430,10 @@ struct LaneIpm {
       const double myinv = (lane < NB) ? sm[OFF_K + NB * NB + r] : 0.0;
       double t = (lane < NB) ? sm[OFF_T + r] : 0.0;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {                       // forward: L y = t
-        const double yj = shfl_d(t * myinv, j);
-        t = (lane == j) ? yj : fma(-Lr[j], yj, t);
-      }
+      for (int j = 0; j < NB; ++j) t = fma(-Lr[j], shfl_d(t, j), t);        // L y = t   (Lr[j] = 0 for j >= lane)
+      t *= myinv;                                                              // D z = y
 #pragma unroll
-      for (int j = NB - 1; j >= 0; --j) {                  // backward: L' x = y
-        const double xj = shfl_d(t * myinv, j);
-        t = (lane == j) ? xj : fma(-Lc[j], xj, t);
-      }
+      for (int j = NB - 1; j >= 0; --j) t = fma(-Lc[j], shfl_d(t, j), t);   // L' x = z  (Lc[j] = 0 for j <= lane)
       if (lane < NB) sm[OFF_T + lane] = t;
     }
   }
@@ -531,15 +557,22 @@ struct LaneIpm {
     // ---- screening, initial point (oracle/mpc_oracle.py::_initial_point) --------------------------------------
     const double base = valid ? (allow_short ? w0 : fmax(w0, 0.0)) : 0.0;
     double mxR[H];
-    {
+    double sb;
+    {   // one round: stage maxima of R, sum of the clipped weights, count of non-finite inputs
       bool okv = isfinite(w0);
 #pragma unroll
       for (int k = 0; k < H; ++k) okv = okv && isfinite(R[k]) && (R[k] > 0.0);
-      double bad = okv ? 0.0 : 1.0, dummy = 0.0;
-      block_max2(bad, dummy);
-      if (uni(bad > 0.0)) return finish(ST_NONFINITE);
+      double v[H + 2];
+#pragma unroll
+      for (int k = 0; k < H; ++k) v[k] = (valid && okv) ? R[k] : 0.0;
+      v[H] = (valid && okv) ? base : 0.0;
+      v[H + 1] = okv ? 0.0 : 1.0;
+      tile_reduce_mixed<H, H + 2>(v);
+      if (uni(ptotal(H + 1) > 0.0)) return finish(ST_NONFINITE);
+#pragma unroll
+      for (int k = 0; k < H; ++k) mxR[k] = ptotal_max(k);
+      sb = ptotal(H);
     }
-    const double sb = block_sum1(base);
     const double invN = 1.0 / (double)N;
     const double eps = (tau <= 0.0) ? 0.1 : fmin(0.1, tau / 8.0);
     const double b0 = (sb > 0.0) ? base / sb : invN;
@@ -570,18 +603,6 @@ struct LaneIpm {
     }
     const bool dual_start = has_w && uni(opt.dual_init > 0.0);
     const double zeta0 = has_c ? opt.dual_init : 0.0;
-#pragma unroll
-    for (int k = 0; k < H; ++k) mxR[k] = valid ? R[k] : 0.0;
-    if (dual_start) {
-      // stage maxima of R (two per butterfly)
-#pragma unroll
-      for (int k = 0; k < H; k += 2) {
-        double a = mxR[k], b = (k + 1 < H) ? mxR[(k + 1 < H) ? k + 1 : 0] : 0.0;
-        block_max2(a, b);
-        mxR[k] = a;
-        if (k + 1 < H) mxR[(k + 1 < H) ? k + 1 : 0] = b;
-      }
-    }
 #pragma unroll
     for (int k = 0; k < H; ++k) {
       const double d0 = (k == 0 && valid) ? w1 - w0 : 0.0;

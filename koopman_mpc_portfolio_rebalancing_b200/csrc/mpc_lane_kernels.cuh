@@ -117,10 +117,10 @@ backtest_lane_kernel(BacktestArgs A) {
 #pragma unroll 1
   for (;;) {
     if (uni(n_idle >= P)) break;
-    if (active) {
+    if (uni(active)) {
 #pragma unroll 1
       for (;;) {
-        if (need_start) {
+        if (uni(need_start)) {
           const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
           const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
           if (s.valid) {
@@ -132,8 +132,8 @@ backtest_lane_kernel(BacktestArgs A) {
           st = s.begin(wc, N, A.lam ? A.lam[b] : A.lam0, A.tau ? A.tau[b] : A.tau0, A.allow_short != 0, opt);
           need_start = false;
         }
-        if (st < 0) st = s.check(opt);
-        if (st < 0) break;                                    // take a Newton step
+        if (uni(st < 0)) st = s.check(opt);
+        if (uni(st < 0)) break;                                    // take a Newton step
         // ---- the decision is made: portfolio step (backtest.py:175-217) ---------------------------------------
         const bool market = (t + 1 < A.rows);
         const double wn = s.valid ? s.w[0] : 0.0;                                          // backtest.py:131
@@ -188,7 +188,7 @@ backtest_lane_kernel(BacktestArgs A) {
           }
         }
         need_start = true; st = -1;
-        if (last) {
+        if (uni(last)) {
           if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
           active = fetch();
           if (!active) {
@@ -199,14 +199,15 @@ backtest_lane_kernel(BacktestArgs A) {
       }
     }
     __syncthreads();                                           // lockstep: all slots enter the factorisation together
-    if (active) s.factor_a();
+    const bool act_u = uni(active);                            // provably warp-uniform (see uni())
+    if (act_u) s.factor_a();
     __syncthreads();
     bool ok = false;
-    if (active) ok = s.factor_b();
+    if (act_u) ok = s.factor_b();
     __syncthreads();
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
-      if (active && ok) s.newton_phase(phase, opt);
+      if (ok) s.newton_phase(phase, opt);
       __syncthreads();
     }
   }
