@@ -68,7 +68,12 @@ struct KMap {
 template <int H>
 __device__ __constant__ KMap<H> g_kmap{};
 
-template <int H, int G>
+// LOC = true ("large" problems, e.g. 500 assets x 10 stages): the per-asset sweep factors and corrector targets are
+// thread-private arrays instead of shared-memory columns (a problem's 100+ rows x 512 assets do not fit an SM's
+// shared memory); together with the iterate they exceed the register file and ptxas keeps the excess in local
+// memory (L1/L2-resident).  Same code, same arithmetic; slower per decision, only the reduction tile, K and the
+// stage scalars stay in shared memory.
+template <int H, int G, bool LOC = false>
 struct LaneIpm {
   static constexpr int NT = 32 * G;                 // threads per problem
   static constexpr int NB = 3 * H;
@@ -84,12 +89,13 @@ struct LaneIpm {
   enum : int { T_CW, T_CP, T_CQ, NTGT };                                    // complementarity targets [H][NT]
   enum : int { U_NU, U_SC, U_ZC, U_RHO, U_IRHO, U_ISC, U_RP, U_CC, NUNI };
   static constexpr int OFF_FAC = 0;
-  static constexpr int OFF_TILE = OFF_FAC + FAC_ROWS * NT;                  // reduction tile, rows of LD doubles
+  static constexpr int OFF_TILE = OFF_FAC + (LOC ? 0 : FAC_ROWS * NT);      // reduction tile, rows of LD doubles
   static constexpr int SMALL_ROWS = NB + 1;                                 // rows usable while the targets are live
   static constexpr int TILE_A = KB * LD;
-  static constexpr int TILE_B = SMALL_ROWS * LD + NTGT * H * NT;
+  static constexpr int TGT_DOUBLES = LOC ? 0 : NTGT * H * NT;
+  static constexpr int TILE_B = SMALL_ROWS * LD + TGT_DOUBLES;
   static constexpr int TILE_DOUBLES = ((TILE_A > TILE_B ? TILE_A : TILE_B) + 1) & ~1;
-  static constexpr int OFF_TGT = OFF_TILE + TILE_DOUBLES - NTGT * H * NT;  // targets = tail of the tile
+  static constexpr int OFF_TGT = OFF_TILE + TILE_DOUBLES - TGT_DOUBLES;    // targets = tail of the tile
   static constexpr int OFF_K = OFF_TILE + TILE_DOUBLES;                     // [NB*NB] K / unit-lower factor L, [NB] 1/D
   static constexpr int OFF_T = OFF_K + NB * NB + NB + ((NB * NB + NB) & 1); // [32] border right-hand side / solution
   static constexpr int OFF_P = OFF_T + 32;                                  // [2][G][32] per-warp partials
@@ -100,6 +106,7 @@ struct LaneIpm {
   // ---- registers of thread i (asset i) ----------------------------------------------------------------------------
   double R[H], w[H], sp[H], sq[H], zw[H], zp[H], zq[H];      // iterate
   double iw[H], isp[H], isq[H], ie[H], ph[H];                // element-wise factors of the current iterate
+  mutable double fac_[LOC ? FAC_ROWS : 1], tgt_[LOC ? NTGT * H : 1];   // LOC only: thread-private factors / targets
   double* sm;
   int tid, lane, warp, psel, bar_id;
   bool valid, has_w, has_u, has_c, allow_short_, fact_ok_;
@@ -118,9 +125,13 @@ struct LaneIpm {
   }
   __device__ __forceinline__ double& FAC(int arr, int k) const {      // arr >= F_QL requires k >= 1
     const int row = (arr < F_QL) ? arr * H + k : 2 * H + (arr - F_QL) * (H - 1) + (k - 1);
+    if (LOC) return fac_[LOC ? row : 0];
     return sm[OFF_FAC + row * NT + tid];
   }
-  __device__ __forceinline__ double& TGT(int arr, int k) const { return sm[OFF_TGT + (arr * H + k) * NT + tid]; }
+  __device__ __forceinline__ double& TGT(int arr, int k) const {
+    if (LOC) return tgt_[LOC ? arr * H + k : 0];
+    return sm[OFF_TGT + (arr * H + k) * NT + tid];
+  }
   __device__ __forceinline__ double& U(int arr, int k) const { return sm[OFF_U + arr * H + k]; }
   __device__ __forceinline__ void sync() const {
     if (G == 1) __syncwarp();

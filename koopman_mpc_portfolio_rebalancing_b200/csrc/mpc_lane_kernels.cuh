@@ -23,7 +23,7 @@ __device__ __forceinline__ float exp_cr32_lane(float y) { return __double2float_
 template <int H, int G>
 __global__ void __launch_bounds__(32 * G, KMPC_LANE_MINB)
 mpc_solve_lane_kernel(MpcSolveArgs A) {
-  using Ipm = LaneIpm<H, G>;
+  using Ipm = LaneIpm<H, G, (G > 4 || H > 5)>;
   extern __shared__ double smem[];
   Ipm s;
   s.bind(smem, A.N, 0);
@@ -77,7 +77,7 @@ struct SlotBook {
 template <int H, int G, int P>
 __global__ void KMPC_LANE_BT_ATTR(32 * G * P)
 backtest_lane_kernel(BacktestArgs A) {
-  using Ipm = LaneIpm<H, G>;
+  using Ipm = LaneIpm<H, G, (G > 4 || H > 5)>;
   extern __shared__ double smem[];
   __shared__ int next_b[P];
   __shared__ int n_idle;
@@ -233,7 +233,7 @@ static int lane_blocks_per_sm(K kernel, int threads, size_t smem) {
 
 template <int H, int G>
 static int launch_mpc_lane(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
-  const size_t smem = (size_t)LaneIpm<H, G>::SMEM_DOUBLES * sizeof(double);
+  const size_t smem = (size_t)LaneIpm<H, G, (G > 4 || H > 5)>::SMEM_DOUBLES * sizeof(double);
   static const int bps = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G>, 32 * G, smem);
   int blocks = A.P < sm_count * bps ? A.P : sm_count * bps;
   if (blocks < 1) blocks = 1;
@@ -245,7 +245,7 @@ static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) 
   // KMPC_LANE_PAD_KB (tuning experiments only): extra dynamic shared memory per block, lowers the blocks per SM
   static const size_t pad = getenv("KMPC_LANE_PAD_KB") ? (size_t)atoi(getenv("KMPC_LANE_PAD_KB")) * 1024 : 0;
   constexpr int P = LaneSlots<G>::P;
-  const size_t smem = (size_t)P * LaneIpm<H, G>::SMEM_DOUBLES * sizeof(double) + pad;
+  const size_t smem = (size_t)P * LaneIpm<H, G, (G > 4 || H > 5)>::SMEM_DOUBLES * sizeof(double) + pad;
   static const int bps = lane_blocks_per_sm(backtest_lane_kernel<H, G, P>, 32 * G * P, smem);
   const int want = (A.B + P - 1) / P;
   int blocks = want < sm_count * bps ? want : sm_count * bps;

@@ -97,3 +97,24 @@ def test_rebalance_freq_and_short_horizon():
     hist = out["history"][0].cpu().numpy()
     assert hist.shape == rh.shape == (len(range(0, n_steps, 3)), 4)
     assert np.allclose(hist[:, 0], rh[:, 0], rtol=1e-6)
+
+
+def test_config3_shape_backtest_vs_oracle_loop(mpc_kernel_layout):
+    """500 assets, H = 10 (BASELINE config 3 shape): persistent backtest kernel vs the oracle loop on a few steps."""
+    if mpc_kernel_layout != "lane":
+        pytest.skip("shape is compiled for the lane layout only")
+    torch, bt, bo, do = _mods()
+    rng = np.random.default_rng(33)
+    B, N, H, rows = 2, 500, 10, 17
+    ns = rows - 1 - H
+    yhat = (3e-4 + rng.standard_normal((B, ns, H, N)) * 0.006).astype(np.float32)
+    realized = (3e-4 + rng.standard_normal((B, rows, N)) * 0.012).astype(np.float32)
+    out = bt.run_backtest_batched(torch.from_numpy(yhat).cuda(), torch.from_numpy(realized).cuda(), n_steps=ns, horizon=H,
+                                  lam0=1e-3, tau0=0.2, cost_coeff0=1e-3, capital0=1e4, want_history=True)
+    hist = out["history"].cpu().numpy()
+    for b in range(B):
+        ref, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat[b], 1e-3, 0.2), realized[b], rows - 1, H)
+        ref = np.asarray(ref)
+        assert hist[b].shape == ref.shape
+        assert np.allclose(hist[b][:, 0], ref[:, 0], rtol=1e-7)           # portfolio value
+        assert np.allclose(hist[b][:, 1:], ref[:, 1:], atol=2e-7)         # return, turnover, cost

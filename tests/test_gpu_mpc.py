@@ -131,3 +131,28 @@ def test_config5_shape_100_assets():
         assert st[p] == 0 and ref.status == 0
         assert abs(val[p] - ref.value) <= OBJ_RTOL * max(abs(ref.value), OBJ_FLOOR)
         assert np.abs(W[p] - ref.w).max() < W_ATOL
+
+
+@pytest.mark.parametrize("N,H", [(12, 10), (50, 10), (100, 10), (500, 10), (300, 5)])
+def test_large_shapes_lane_layout(N, H, mpc_kernel_layout):
+    """BASELINE config 3 (LISTAKM, 500 assets, H = 10, turnover cap) and the other shapes only the lane layout
+    covers (H up to 10, N up to 512; factors and targets thread-private, see LaneIpm LOC)."""
+    if mpc_kernel_layout != "lane":
+        pytest.skip("shape is compiled for the lane layout only")
+    torch, mpc, mo = _mods()
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    assert _capi.lib().kmpc_mpc_supported(H, N) == 1
+    rng = np.random.default_rng(1000 * H + N)
+    P = 6 if N >= 300 else 16
+    w0 = np.stack([rng.dirichlet(np.ones(N) * rng.choice([0.3, 1.0])) for _ in range(P)])
+    y = np.stack([(3e-4 + rng.standard_normal((H, N)) * rng.choice([0.003, 0.01])) for _ in range(P)]).astype(np.float32)
+    out = mpc.solve_mpc_batch(torch.from_numpy(w0).cuda(), torch.from_numpy(y).cuda())
+    W = out["w"].cpu().numpy(); val = out["value"].cpu().numpy(); st = out["status"].cpu().numpy()
+    kkt = out["kkt"].cpu().numpy()
+    for p in range(P):
+        ref = mo.solve_structured(w0[p], y[p], 1e-3, 0.2, apply="sweep")
+        assert ref.status == mo.STATUS_OPTIMAL and st[p] == 0, (p, st[p], kkt[p])
+        assert abs(val[p] - ref.value) <= OBJ_RTOL * max(abs(ref.value), OBJ_FLOOR)
+        assert np.abs(W[p] - ref.w).max() < W_ATOL
+        turn = np.abs(np.diff(np.vstack([w0[p], W[p]]), axis=0)).sum(axis=1)
+        assert turn.max() <= 0.2 + 1e-7
