@@ -48,7 +48,7 @@ int kmpc_create(int device, kmpc_handle** out) {
   h->launches = 0;
   h->scratch = nullptr;
   h->scratch_bytes = 0;
-  e = cudaMalloc(&h->work_counter, sizeof(int));
+  e = cudaMalloc(&h->work_counter, 4 * sizeof(int));      // [0] backtest work counter, [2] structure-flag scratch
   if (e != cudaSuccess) { delete h; return kmpc_fail_cuda(e, "cudaMalloc(work_counter)"); }
   *out = h;
   return KMPC_OK;
@@ -128,7 +128,7 @@ int kmpc_mpc_solve(kmpc_handle* h, const float* yhat, const double* yhat64, cons
   kmpc::MpcSolveArgs A;
   A.yhat = yhat; A.yhat64 = yhat64; A.w_cur = w_cur; A.lam = lam; A.tau = tau; A.lam0 = lam0; A.tau0 = tau0;
   A.allow_short = allow_short; A.P = P; A.N = N; A.w_out = w_out; A.obj = obj; A.kkt = kkt; A.status = status;
-  A.iters = iters; A.opt = kmpc::default_ipm_options();
+  A.iters = iters; A.fix_flag = h->work_counter + 2; A.opt = kmpc::default_ipm_options();
   int rc = kmpc::dispatch_mpc_solve(A, H, h->sm_count, (cudaStream_t)stream);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_solve: unsupported shape");
@@ -196,7 +196,7 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   A.lam0 = D->lam0; A.tau0 = D->tau0; A.cost_coeff0 = D->cost_coeff0; A.capital0 = D->capital0;
   A.allow_short = D->allow_short; A.B = D->B; A.N = D->N;
   A.history = D->history; A.metrics = D->metrics; A.solve_stats = (long long*)D->solve_stats;
-  A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.opt = kmpc::default_ipm_options();
+  A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = kmpc::default_ipm_options();
   int rc = kmpc::dispatch_backtest(A, D->H, h->sm_count, st);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_backtest_run: unsupported shape");

@@ -19,6 +19,7 @@ struct MpcSolveArgs {
   double* kkt;              // [P,3] primal residual, dual residual, complementarity gap
   int* status;              // [P]
   int* iters;               // [P]
+  int* fix_flag;            // device int (handle-owned scratch): 1 = every problem has lam > 0 and tau > 0
   IpmOptions opt;
 };
 
@@ -37,6 +38,7 @@ struct BacktestArgs {
   long long* solve_stats;   // [B,4] or null: #optimal, #inaccurate, #fallback, total IPM iterations
   double* final_weights;    // [B,N] or null
   int* work_counter;        // device int, zeroed before launch
+  int* fix_flag;            // device int (handle-owned scratch), see MpcSolveArgs
   IpmOptions opt;
 };
 

@@ -42,7 +42,7 @@ struct IpmOptions {
 __host__ __device__ inline IpmOptions default_ipm_options() {
   IpmOptions o;
   o.tol = 1e-10; o.tol_dual = 1e-8; o.delta = 1e-5; o.step_frac = 0.995; o.mu0 = 1e-3; o.dual_init = 3e-3;
-  o.max_iter = 50;
+  o.max_iter = 100;
   return o;
 }
 

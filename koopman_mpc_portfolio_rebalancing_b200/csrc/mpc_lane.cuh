@@ -73,7 +73,7 @@ __device__ __constant__ KMap<H> g_kmap{};
 // shared memory); together with the iterate they exceed the register file and ptxas keeps the excess in local
 // memory (L1/L2-resident).  Same code, same arithmetic; slower per decision, only the reduction tile, K and the
 // stage scalars stay in shared memory.
-template <int H, int G, bool LOC = false>
+template <int H, int G, bool LOC = false, bool FIX = false>
 struct LaneIpm {
   static constexpr int NT = 32 * G;                 // threads per problem
   static constexpr int NB = 3 * H;
@@ -109,7 +109,7 @@ struct LaneIpm {
   mutable double fac_[LOC ? FAC_ROWS : 1], tgt_[LOC ? NTGT * H : 1];   // LOC only: thread-private factors / targets
   double* sm;
   int tid, lane, warp, psel, bar_id;
-  bool valid, has_w, has_u, has_c, allow_short_, fact_ok_;
+  bool valid, has_w_, has_u_, has_c_, allow_short_, fact_ok_;
   double lam, tau, delta;
   // state of the solve in progress (begin / check / factor_a / factor_b / newton_phase)
   double w0_, mu_, gap_, mcount_, kkt_[3];
@@ -132,6 +132,12 @@ struct LaneIpm {
     if (LOC) return tgt_[LOC ? arr * H + k : 0];
     return sm[OFF_TGT + (arr * H + k) * NT + tid];
   }
+  // FIX: the caller guarantees lam > 0, tau > 0 and long-only weights (the reference defaults, mpc.py:17-25): the three
+  // structure flags are compile-time constants and every select / branch on them disappears.
+  __device__ __forceinline__ bool hw() const { return FIX ? true : has_w_; }
+  __device__ __forceinline__ bool hu() const { return FIX ? true : has_u_; }
+  __device__ __forceinline__ bool hc() const { return FIX ? true : has_c_; }
+  __device__ __forceinline__ bool ash() const { return FIX ? false : allow_short_; }
   __device__ __forceinline__ double& U(int arr, int k) const { return sm[OFF_U + arr * H + k]; }
   __device__ __forceinline__ void sync() const {
     if (G == 1) __syncwarp();
@@ -285,8 +291,8 @@ struct LaneIpm {
 #pragma unroll
     for (int k = 0; k < H; ++k) {
       iw[k] = rcp_fast(w[k]);
-      ad[k] = (has_w ? zw[k] * iw[k] : 0.0) + delta;
-      if (has_u) {
+      ad[k] = (hw() ? zw[k] * iw[k] : 0.0) + delta;
+      if (hu()) {
         isp[k] = rcp_fast(sp[k]); isq[k] = rcp_fast(sq[k]);
         const double dp = zp[k] * isp[k], dq = zq[k] * isq[k];
         const double s = dp + dq;
@@ -354,7 +360,7 @@ struct LaneIpm {
         emit(g); KMPC_FLUSH_IF_FULL();
       }
     }
-    if (has_c) {
+    if (hc()) {
 #pragma unroll
       for (int l = 0; l < H; ++l) {
 #pragma unroll
@@ -391,12 +397,12 @@ struct LaneIpm {
   // non-positive pivot.
   __device__ __forceinline__ bool factor_b() {
     if (warp == 0) {
-      const int nb = has_c ? 3 * H : 2 * H;
+      const int nb = hc() ? 3 * H : 2 * H;
       const int r = (lane < NB) ? lane : NB - 1;
       if (lane < NB) {             // diagonal terms 1/beta_k = rho_k^2 and sc_k / zc_k, added in place (a lane-indexed
         double add = 0.0;          // update of the register row would push the whole row to local memory)
         if (lane < H) { const double rho = U(U_RHO, lane); add = rho * rho; }
-        if (has_c && lane >= 2 * H) add = U(U_SC, lane - 2 * H) * rcp_fast(U(U_ZC, lane - 2 * H));
+        if (hc() && lane >= 2 * H) add = U(U_SC, lane - 2 * H) * rcp_fast(U(U_ZC, lane - 2 * H));
         sm[OFF_K + lane * NB + lane] += add;
       }
       __syncwarp();
@@ -460,13 +466,13 @@ struct LaneIpm {
       double gwk = fma(R[k], U(U_IRHO, k), -U(U_NU, k));
       double guk = 0.0;
       tq[k] = 0.0;
-      if (use_c && has_w) gwk = fma(TGT(T_CW, k), iw[k], gwk);
-      if (has_u) {
+      if (use_c && hw()) gwk = fma(TGT(T_CW, k), iw[k], gwk);
+      if (hu()) {
         double a1 = 0.0, a2 = 0.0;
         if (use_c) { a1 = TGT(T_CP, k) * isp[k]; a2 = TGT(T_CQ, k) * isq[k]; }
         tq[k] = a1 - a2;
         guk = -lam + a1 + a2;
-        if (has_c) guk = fma(-U(U_CC, k), U(U_ISC, k), guk);
+        if (hc()) guk = fma(-U(U_CC, k), U(U_ISC, k), guk);
       }
       gw[k] = gwk; gu[k] = guk;
     }
@@ -484,7 +490,7 @@ struct LaneIpm {
       for (int k = 0; k < H; ++k) {
         v[k] = R[k] * dw[k];                                 // padding lanes: dw = dd = ie = 0
         v[H + k] = dw[k];
-        v[2 * H + k] = has_c ? fma(gu[k], ie[k], -ph[k] * dd[k]) : 0.0;
+        v[2 * H + k] = hc() ? fma(gu[k], ie[k], -ph[k] * dd[k]) : 0.0;
       }
       tile_reduce<NB>(v);
       if (tid < NB) {
@@ -498,9 +504,9 @@ struct LaneIpm {
     sync();
     dnu = 0.0; dsc = 0.0; dzc = 0.0;
     if (tid < H) {                                           // stage scalars stay with their owner threads
-      const double yC = has_c ? sm[OFF_T + 2 * H + tid] : 0.0;
+      const double yC = hc() ? sm[OFF_T + 2 * H + tid] : 0.0;
       dnu = sm[OFF_T + H + tid];
-      if (has_c) {
+      if (hc()) {
         dsc = -yC * U(U_SC, tid) * rcp_fast(U(U_ZC, tid));
         dzc = fma(U(U_CC, tid), U(U_ISC, tid), -U(U_ZC, tid)) + yC;
       }
@@ -509,7 +515,7 @@ struct LaneIpm {
 #pragma unroll
     for (int k = 0; k < H; ++k) {
       gw[k] -= fma(sm[OFF_T + k], R[k], sm[OFF_T + H + k]);
-      geff[k] = gu[k] - (has_c ? sm[OFF_T + 2 * H + k] : 0.0);
+      geff[k] = gu[k] - (hc() ? sm[OFF_T + 2 * H + k] : 0.0);
       pg[k] = ph[k] * geff[k];
     }
     m0_apply(gw, pg, dw, dd);
@@ -517,13 +523,13 @@ struct LaneIpm {
     if (valid) {
 #pragma unroll
       for (int k = 0; k < H; ++k) {
-        if (has_w) {
+        if (hw()) {
           const double cw = use_c ? TGT(T_CW, k) : 0.0;
           dzw[k] = fma(iw[k], fma(-zw[k], dw[k], cw), -zw[k]);
           rp = fmax(rp, -dw[k] * iw[k]);
           rd = fmax(rd, -dzw[k] * rcp_fast(zw[k]));
         } else dzw[k] = 0.0;
-        if (has_u) {
+        if (hu()) {
           const double cp = use_c ? TGT(T_CP, k) : 0.0, cq = use_c ? TGT(T_CQ, k) : 0.0;
           const double dp = zp[k] * isp[k], dq = zq[k] * isq[k];
           dsp[k] = fma(-fma(2.0, dq, delta), dd[k], geff[k]) * ie[k];
@@ -538,7 +544,7 @@ struct LaneIpm {
 #pragma unroll
       for (int k = 0; k < H; ++k) { dw[k] = 0.0; dsp[k] = 0.0; dsq[k] = 0.0; dzw[k] = 0.0; dzp[k] = 0.0; dzq[k] = 0.0; }
     }
-    if (has_c && tid < H) {
+    if (hc() && tid < H) {
       rp = fmax(rp, -dsc * U(U_ISC, tid));
       rd = fmax(rd, -dzc * rcp_fast(U(U_ZC, tid)));
     }
@@ -554,9 +560,9 @@ struct LaneIpm {
   __device__ __forceinline__ int begin(double w0, int N, double lam_, double tau_, bool allow_short,
                                        const IpmOptions& opt) {
     lam = lam_; tau = tau_; delta = opt.delta;
-    has_u = uni((lam > 0.0) || (tau > 0.0));
-    has_c = has_u && uni(tau > 0.0);
-    has_w = !allow_short; allow_short_ = allow_short;
+    has_u_ = uni((lam > 0.0) || (tau > 0.0));
+    has_c_ = has_u_ && uni(tau > 0.0);
+    has_w_ = !allow_short; allow_short_ = allow_short;
     it_ = 0; fact_ok_ = true;
     kkt_[0] = kkt_[1] = kkt_[2] = CUDART_NAN;
     if (!valid) {
@@ -566,7 +572,7 @@ struct LaneIpm {
     }
     w0_ = w0;
     // ---- screening, initial point (oracle/mpc_oracle.py::_initial_point) --------------------------------------
-    const double base = valid ? (allow_short ? w0 : fmax(w0, 0.0)) : 0.0;
+    const double base = valid ? (ash() ? w0 : fmax(w0, 0.0)) : 0.0;
     double mxR[H];
     double sb;
     {   // one round: stage maxima of R, sum of the clipped weights, count of non-finite inputs
@@ -601,7 +607,7 @@ struct LaneIpm {
       absd0 = tot[H];
     }
     double sc0 = 1.0, sck = 1.0, dl0 = 0.0, dlk = 0.0;
-    if (has_u) {
+    if (hu()) {
       if (uni(tau > 0.0)) {
         const double room0 = tau - absd0;
         if (uni(!(room0 > 0.0))) {
@@ -610,38 +616,38 @@ struct LaneIpm {
         }
         dl0 = room0 / (2.0 * N); dlk = tau / (2.0 * N);
       } else { dl0 = dlk = 0.05 * invN; }
-      if (has_c) { sc0 = tau - (absd0 + dl0 * N); sck = tau - dlk * N; }
+      if (hc()) { sc0 = tau - (absd0 + dl0 * N); sck = tau - dlk * N; }
     }
-    const bool dual_start = has_w && uni(opt.dual_init > 0.0);
-    const double zeta0 = has_c ? opt.dual_init : 0.0;
+    const bool dual_start = hw() && uni(opt.dual_init > 0.0);
+    const double zeta0 = hc() ? opt.dual_init : 0.0;
 #pragma unroll
     for (int k = 0; k < H; ++k) {
       const double d0 = (k == 0 && valid) ? w1 - w0 : 0.0;
-      const double uk = has_u ? ((k == 0) ? fabs(d0) + dl0 : dlk) : 1.0;
+      const double uk = hu() ? ((k == 0) ? fabs(d0) + dl0 : dlk) : 1.0;
       w[k] = w1;
-      sp[k] = has_u ? uk - d0 : 1.0;
-      sq[k] = has_u ? uk + d0 : 1.0;
+      sp[k] = hu() ? uk - d0 : 1.0;
+      sq[k] = hu() ? uk + d0 : 1.0;
       const double sck_ = (k == 0) ? sc0 : sck;
       double nu_k;
       if (dual_start) {
         const double ir = 1.0 / rho0[k];
         nu_k = mxR[k] * ir + opt.dual_init;
         zw[k] = valid ? fma(-R[k], ir, nu_k) : 0.0;
-        zp[k] = has_u ? 0.5 * (lam + zeta0) : 0.0;
+        zp[k] = hu() ? 0.5 * (lam + zeta0) : 0.0;
         zq[k] = zp[k];
-        if (tid == 0) U(U_ZC, k) = has_c ? zeta0 : 0.0;
+        if (tid == 0) U(U_ZC, k) = hc() ? zeta0 : 0.0;
       } else {
         nu_k = 1.0;
-        zw[k] = (has_w && valid) ? opt.mu0 / w[k] : 0.0;
-        zp[k] = has_u ? opt.mu0 / sp[k] : 0.0;
-        zq[k] = has_u ? opt.mu0 / sq[k] : 0.0;
-        if (tid == 0) U(U_ZC, k) = has_c ? opt.mu0 / sck_ : 0.0;
+        zw[k] = (hw() && valid) ? opt.mu0 / w[k] : 0.0;
+        zp[k] = hu() ? opt.mu0 / sp[k] : 0.0;
+        zq[k] = hu() ? opt.mu0 / sq[k] : 0.0;
+        if (tid == 0) U(U_ZC, k) = hc() ? opt.mu0 / sck_ : 0.0;
       }
       if (tid == 0) { U(U_NU, k) = nu_k; U(U_SC, k) = sck_; U(U_CC, k) = 0.0; }
       if (!valid) { zw[k] = 1.0; zp[k] = 1.0; zq[k] = 1.0; }      // benign padding (never updated, never summed)
     }
     sync();
-    mcount_ = (has_w ? (double)H * N : 0.0) + (has_u ? 2.0 * H * N : 0.0) + (has_c ? (double)H : 0.0);
+    mcount_ = (hw() ? (double)H * N : 0.0) + (hu() ? 2.0 * H * N : 0.0) + (hc() ? (double)H : 0.0);
     return -1;
   }
 
@@ -667,11 +673,11 @@ struct LaneIpm {
       for (int k = 0; k < H; ++k) {
         v[k] = valid ? w[k] * R[k] : 0.0;
         v[H + k] = valid ? w[k] : 0.0;
-        if (has_w) g = fma(w[k], zw[k], g);
-        if (has_u) g = fma(sp[k], zp[k], fma(sq[k], zq[k], g));
+        if (hw()) g = fma(w[k], zw[k], g);
+        if (hu()) g = fma(sp[k], zp[k], fma(sq[k], zq[k], g));
       }
       if (!valid) g = 0.0;
-      if (has_c && tid < H) g = fma(U(U_SC, tid), U(U_ZC, tid), g);
+      if (hc() && tid < H) g = fma(U(U_SC, tid), U(U_ZC, tid), g);
       v[2 * H] = g;
       tile_reduce<2 * H + 1>(v);
       gap = ptotal(2 * H);
@@ -682,7 +688,7 @@ struct LaneIpm {
         const double rho = ptotal(tid);
         U(U_RHO, tid) = rho; U(U_IRHO, tid) = rcp_fast(rho);
         U(U_RP, tid) = ptotal(H + tid) - 1.0;
-        U(U_ISC, tid) = has_c ? rcp_fast(U(U_SC, tid)) : 0.0;
+        U(U_ISC, tid) = hc() ? rcp_fast(U(U_SC, tid)) : 0.0;
       }
     }
     sync();
@@ -692,9 +698,9 @@ struct LaneIpm {
       for (int k = 0; k < H; ++k) {
         const double yk = zp[k] - zq[k];
         const double yn = (k + 1 < H) ? zp[(k + 1 < H) ? k + 1 : 0] - zq[(k + 1 < H) ? k + 1 : 0] : 0.0;
-        const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (has_w ? zw[k] : 0.0) + (yk - yn);
+        const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (hw() ? zw[k] : 0.0) + (yk - yn);
         dres = fmax(dres, fabs(rdw));
-        if (has_u) dres = fmax(dres, fabs(lam - zp[k] - zq[k] + (has_c ? U(U_ZC, k) : 0.0)));
+        if (hu()) dres = fmax(dres, fabs(lam - zp[k] - zq[k] + (hc() ? U(U_ZC, k) : 0.0)));
       }
     }
     {
@@ -715,13 +721,13 @@ struct LaneIpm {
 
   // phase 0: predictor -> complementarity targets of the corrector; phase 1: corrector -> step
   __device__ __forceinline__ void newton_phase(int phase, const IpmOptions& opt) {
-    const bool has_m = mcount_ > 0.0;
+    const bool has_m = FIX ? true : (mcount_ > 0.0);
     if (phase == 0 && !has_m) return;
     const bool use_c = (phase == 1) && has_m;
-    const bool stepped = has_m || allow_short_;
+    const bool stepped = has_m || ash();
     double dw[H], dsp[H], dsq[H], dzw[H], dzp[H], dzq[H], dnu, dsc, dzc, rp, rd;
     newton(use_c, dw, dsp, dsq, dzw, dzp, dzq, dnu, dsc, dzc, rp, rd);
-    if (allow_short_) {            // keep the argument of the logarithm positive: rho_k + a * sum_i R dw > 0
+    if (ash()) {            // keep the argument of the logarithm positive: rho_k + a * sum_i R dw > 0
       double v[H], tot[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) v[k] = dw[k] * R[k];
@@ -738,22 +744,22 @@ struct LaneIpm {
       if (valid) {
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-          if (has_w) g2 = fma(fma(aa, dw[k], w[k]), fma(ab, dzw[k], zw[k]), g2);
-          if (has_u) g2 = fma(fma(aa, dsp[k], sp[k]), fma(ab, dzp[k], zp[k]),
+          if (hw()) g2 = fma(fma(aa, dw[k], w[k]), fma(ab, dzw[k], zw[k]), g2);
+          if (hu()) g2 = fma(fma(aa, dsp[k], sp[k]), fma(ab, dzp[k], zp[k]),
                               fma(fma(aa, dsq[k], sq[k]), fma(ab, dzq[k], zq[k]), g2));
         }
       }
-      if (has_c && tid < H) g2 = fma(fma(aa, dsc, U(U_SC, tid)), fma(ab, dzc, U(U_ZC, tid)), g2);
+      if (hc() && tid < H) g2 = fma(fma(aa, dsc, U(U_SC, tid)), fma(ab, dzc, U(U_ZC, tid)), g2);
       g2 = block_sum1(g2);
       const double ratio = (gap_ > 0.0) ? fmin(1.0, fmax(g2 / gap_, 0.0)) : 0.0;
       const double smu = ratio * ratio * ratio * mu_;
 #pragma unroll
       for (int k = 0; k < H; ++k) {      // complementarity targets of the corrector
-        TGT(T_CW, k) = has_w ? fma(-dw[k], dzw[k], smu) : 0.0;
-        TGT(T_CP, k) = has_u ? fma(-dsp[k], dzp[k], smu) : 0.0;
-        TGT(T_CQ, k) = has_u ? fma(-dsq[k], dzq[k], smu) : 0.0;
+        TGT(T_CW, k) = hw() ? fma(-dw[k], dzw[k], smu) : 0.0;
+        TGT(T_CP, k) = hu() ? fma(-dsp[k], dzp[k], smu) : 0.0;
+        TGT(T_CQ, k) = hu() ? fma(-dsq[k], dzq[k], smu) : 0.0;
       }
-      if (tid < H) U(U_CC, tid) = has_c ? fma(-dsc, dzc, smu) : 0.0;
+      if (tid < H) U(U_CC, tid) = hc() ? fma(-dsc, dzc, smu) : 0.0;
       sync();
     } else {
       const double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;
@@ -762,8 +768,8 @@ struct LaneIpm {
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           w[k] = fma(pa, dw[k], w[k]);
-          if (has_w) zw[k] = fma(pb, dzw[k], zw[k]);
-          if (has_u) {
+          if (hw()) zw[k] = fma(pb, dzw[k], zw[k]);
+          if (hu()) {
             sp[k] = fma(pa, dsp[k], sp[k]); sq[k] = fma(pa, dsq[k], sq[k]);
             zp[k] = fma(pb, dzp[k], zp[k]); zq[k] = fma(pb, dzq[k], zq[k]);
           }
@@ -771,7 +777,7 @@ struct LaneIpm {
       }
       if (tid < H) {
         U(U_NU, tid) = fma(pb, dnu, U(U_NU, tid));
-        if (has_c) { U(U_SC, tid) = fma(pa, dsc, U(U_SC, tid)); U(U_ZC, tid) = fma(pb, dzc, U(U_ZC, tid)); }
+        if (hc()) { U(U_SC, tid) = fma(pa, dsc, U(U_SC, tid)); U(U_ZC, tid) = fma(pb, dzc, U(U_ZC, tid)); }
         U(U_CC, tid) = 0.0;                  // the next predictor has no complementarity targets
       }
       sync();

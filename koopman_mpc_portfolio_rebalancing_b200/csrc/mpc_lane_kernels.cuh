@@ -20,11 +20,29 @@ namespace kmpc {
 
 __device__ __forceinline__ float exp_cr32_lane(float y) { return __double2float_rn(exp((double)y)); }
 
-template <int H, int G>
+// FIX kernels (structure flags compile-time, see LaneIpm) and generic kernels are launched as a pair when per-problem
+// lam / tau arrays are given: `want` selects which of the two does the work once lane_flags_kernel has looked at
+// the arrays (no host synchronisation); the other one exits at once.
+static __global__ void lane_flags_kernel(const double* lam, const double* tau, double lam0, double tau0, int n, int* flag) {
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  int b = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double l = lam ? lam[i] : lam0, t = tau ? tau[i] : tau0;
+    if (!(l > 0.0) || !(t > 0.0)) b = 1;
+  }
+  if (b) bad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) *flag = bad ? 0 : 1;
+}
+
+template <int H, int G, bool FIX>
 __global__ void __launch_bounds__(32 * G, KMPC_LANE_MINB)
-mpc_solve_lane_kernel(MpcSolveArgs A) {
-  using Ipm = LaneIpm<H, G, (G > 4 || H > 5)>;
+mpc_solve_lane_kernel(MpcSolveArgs A, int want) {
+  using Ipm = LaneIpm<H, G, (G > 4 || H > 5), FIX>;
   extern __shared__ double smem[];
+  if (want >= 0 && *A.fix_flag != want) return;
   Ipm s;
   s.bind(smem, A.N, 0);
   const int N = A.N;
@@ -74,11 +92,12 @@ struct SlotBook {
   int n, n_opt, n_inacc, n_fail;
 };
 
-template <int H, int G, int P>
+template <int H, int G, int P, bool FIX>
 __global__ void KMPC_LANE_BT_ATTR(32 * G * P)
-backtest_lane_kernel(BacktestArgs A) {
-  using Ipm = LaneIpm<H, G, (G > 4 || H > 5)>;
+backtest_lane_kernel(BacktestArgs A, int want) {
+  using Ipm = LaneIpm<H, G, (G > 4 || H > 5), FIX>;
   extern __shared__ double smem[];
+  if (want >= 0 && *A.fix_flag != want) return;
   __shared__ int next_b[P];
   __shared__ int n_idle;
   __shared__ SlotBook books[P];
@@ -231,13 +250,24 @@ static int lane_blocks_per_sm(K kernel, int threads, size_t smem) {
   return nb < 1 ? 1 : nb;
 }
 
+// which kernel(s) to launch: 1 = FIX only, 0 = generic only, 2 = both, gated on the device flag
+static int lane_fix_plan(const double* lam, const double* tau, double lam0, double tau0, int allow_short, int n, int* flag,
+                         cudaStream_t st) {
+  if (allow_short) return 0;
+  if (!lam && !tau) return (lam0 > 0.0 && tau0 > 0.0) ? 1 : 0;
+  lane_flags_kernel<<<1, 256, 0, st>>>(lam, tau, lam0, tau0, n, flag);
+  return 2;
+}
+
 template <int H, int G>
 static int launch_mpc_lane(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
-  const size_t smem = (size_t)LaneIpm<H, G, (G > 4 || H > 5)>::SMEM_DOUBLES * sizeof(double);
-  static const int bps = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G>, 32 * G, smem);
-  int blocks = A.P < sm_count * bps ? A.P : sm_count * bps;
-  if (blocks < 1) blocks = 1;
-  mpc_solve_lane_kernel<H, G><<<blocks, 32 * G, smem, st>>>(A);
+  const size_t smem = (size_t)LaneIpm<H, G, (G > 4 || H > 5), false>::SMEM_DOUBLES * sizeof(double);
+  static const int bps0 = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, false>, 32 * G, smem);
+  static const int bps1 = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, true>, 32 * G, smem);
+  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.P, A.fix_flag, st);
+  auto nblocks = [&](int bps) { int b = A.P < sm_count * bps ? A.P : sm_count * bps; return b < 1 ? 1 : b; };
+  if (plan != 0) mpc_solve_lane_kernel<H, G, true><<<nblocks(bps1), 32 * G, smem, st>>>(A, plan == 2 ? 1 : -1);
+  if (plan != 1) mpc_solve_lane_kernel<H, G, false><<<nblocks(bps0), 32 * G, smem, st>>>(A, plan == 2 ? 0 : -1);
   return (int)cudaGetLastError();
 }
 template <int H, int G>
@@ -245,12 +275,14 @@ static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) 
   // KMPC_LANE_PAD_KB (tuning experiments only): extra dynamic shared memory per block, lowers the blocks per SM
   static const size_t pad = getenv("KMPC_LANE_PAD_KB") ? (size_t)atoi(getenv("KMPC_LANE_PAD_KB")) * 1024 : 0;
   constexpr int P = LaneSlots<G>::P;
-  const size_t smem = (size_t)P * LaneIpm<H, G, (G > 4 || H > 5)>::SMEM_DOUBLES * sizeof(double) + pad;
-  static const int bps = lane_blocks_per_sm(backtest_lane_kernel<H, G, P>, 32 * G * P, smem);
+  const size_t smem = (size_t)P * LaneIpm<H, G, (G > 4 || H > 5), false>::SMEM_DOUBLES * sizeof(double) + pad;
+  static const int bps0 = lane_blocks_per_sm(backtest_lane_kernel<H, G, P, false>, 32 * G * P, smem);
+  static const int bps1 = lane_blocks_per_sm(backtest_lane_kernel<H, G, P, true>, 32 * G * P, smem);
+  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.B, A.fix_flag, st);
   const int want = (A.B + P - 1) / P;
-  int blocks = want < sm_count * bps ? want : sm_count * bps;
-  if (blocks < 1) blocks = 1;
-  backtest_lane_kernel<H, G, P><<<blocks, 32 * G * P, smem, st>>>(A);
+  auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };
+  if (plan != 0) backtest_lane_kernel<H, G, P, true><<<nblocks(bps1), 32 * G * P, smem, st>>>(A, plan == 2 ? 1 : -1);
+  if (plan != 1) backtest_lane_kernel<H, G, P, false><<<nblocks(bps0), 32 * G * P, smem, st>>>(A, plan == 2 ? 0 : -1);
   return (int)cudaGetLastError();
 }
 

@@ -69,3 +69,39 @@ def test_batched_engine_vs_oracle_paths():
         assert np.allclose(res["metrics"][b], [mo_[k] for k in bo.METRIC_KEYS], rtol=5e-4, atol=5e-4), b
     assert worst < 2e-4, worst
     assert res["stats"][:, 2].sum() == 0
+
+
+def test_config3_shape_lista_pipeline_vs_oracle():
+    """BASELINE config 3 at full model size (LISTAKM linear encoder, 500 assets, d = 10 -> obs 5000, Z = 2048, 10
+    LISTA loops, H = 10, turnover cap 0.2), a few short backtests: forecast within 1e-5 (norm-wise) of the oracle,
+    every path's history equal to the oracle backtest run on the SAME forecasts (stage-wise parity: with 500 assets
+    whose forecasts differ by ~1e-5 the LP-like program is near-degenerate, and a 1e-6 forecast difference moves the
+    optimal vertex)."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import engine, model as km, synthetic, backtest as bt
+    from oracle import backtest_oracle as bo, data_oracle as do, forecast_oracle as fo
+    B, N, d, H, rows, Z = 2, 500, 10, 10, 16, 2048
+    T = rows + d - 1
+    lr = synthetic.gbm_log_returns_batch(300, B, T, N)
+    mean = np.full((B, N), 3e-4); std = np.full((B, N), 0.014)
+    sd, L = synthetic.lista_km_weights(7, N * d, Z)
+    m = km.make_model(km.model_config("LISTAKM", Z, lista_loops=10, lista_L=L, lista_alpha=5e-3, lista_linear=True), N * d)
+    m.load_state_dict(sd)
+    eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H, cost_coeff=1e-3, max_turnover=0.2),
+                                   bt.BacktestConfig(horizon=H, cost_coeff=1e-3))
+    out = eng.run_device(torch.from_numpy(lr).cuda(), torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda(), 0, rows,
+                         want_history=True)
+    yhat_gpu = out["yhat"].cpu().numpy(); hist = out["history"].cpu().numpy()
+    spec = fo.ModelSpec(kind="lista", linear_encoder=True, alpha=5e-3, L=L, loops=10, act="relu", last_relu=False)
+    ns = rows - 1 - H
+    for b in range(B):
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)
+        yhat = fo.forecast(emb[:ns], sd, spec, H, N, mean[b], std[b])
+        rel = np.abs(yhat_gpu[b] - yhat).reshape(ns, -1).max(1) / np.abs(yhat).reshape(ns, -1).max(1)
+        assert rel.max() < 1e-5, rel.max()
+        allr = do.destandardize(do.extract_current_returns(emb, N), mean[b], std[b])
+        rh, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat_gpu[b], 1e-3, 0.2), allr, rows - 1, H)
+        rh = np.asarray(rh)
+        assert np.allclose(hist[b][:, 0], rh[:, 0], rtol=1e-6), np.abs(hist[b][:, 0] / rh[:, 0] - 1).max()
+        assert np.allclose(hist[b][:, 1:], rh[:, 1:], atol=1e-6)
+    assert out["stats"].cpu().numpy()[:, 2].sum() == 0
