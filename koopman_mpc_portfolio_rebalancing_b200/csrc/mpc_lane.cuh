@@ -229,6 +229,27 @@ struct LaneIpm {
       for (int g = 0; g < G; ++g) { a = fmax(a, P[g * 32]); b = fmax(b, P[g * 32 + 1]); }
     }
   }
+  // Maxima of non-negative quantities are taken on the HIGH WORDS of the doubles as integers (one VIMNMX instead of
+  // DSETP + 2 FSEL; a negative double has a negative high word and drops out against the initial 0) and rounded UP
+  // when converted back: the result is >= the true maximum by at most 2^-20 relative, which errs on the safe side
+  // for a step-length ratio and for a residual that is compared with a tolerance.
+  static __device__ __forceinline__ int hi_of(double x) { return __double2hiint(x); }
+  static __device__ __forceinline__ double hi_up(int h) { return __hiloint2double(h + 1, 0); }
+  __device__ __forceinline__ void block_max2i(int& a, int& b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = max(a, __shfl_xor_sync(kFull, a, o));
+      b = max(b, __shfl_xor_sync(kFull, b, o));
+    }
+    if (G > 1) {
+      psel ^= 1;
+      int* P = reinterpret_cast<int*>(sm + OFF_P + psel * G * 32);
+      if (lane == 0) { P[warp * 2] = a; P[warp * 2 + 1] = b; }
+      sync();
+#pragma unroll
+      for (int g = 0; g < G; ++g) { a = max(a, P[g * 2]); b = max(b, P[g * 2 + 1]); }
+    }
+  }
   __device__ __forceinline__ double block_sum1(double a) {
     a = warp_sum(a);
     if (G > 1) {
@@ -459,7 +480,7 @@ struct LaneIpm {
   // (dnu, dsc, dzc) of stage tid are returned to the owner threads tid < H, and (rp_, rd_) are my largest primal / dual step ratios -dv/v.
   __device__ __forceinline__ void newton(bool use_c, double (&dw)[H], double (&dsp)[H], double (&dsq)[H],
                                          double (&dzw)[H], double (&dzp)[H], double (&dzq)[H], double& dnu, double& dsc,
-                                         double& dzc, double& rp_, double& rd_) {
+                                         double& dzc, int& rp_, int& rd_) {
     double gw[H], gu[H], pg[H], tq[H];
 #pragma unroll
     for (int k = 0; k < H; ++k) {
@@ -519,15 +540,15 @@ struct LaneIpm {
       pg[k] = ph[k] * geff[k];
     }
     m0_apply(gw, pg, dw, dd);
-    double rp = 0.0, rd = 0.0;
+    int rp = 0, rd = 0;                                     // high words of the largest ratios -dv/v
     if (valid) {
 #pragma unroll
       for (int k = 0; k < H; ++k) {
         if (hw()) {
           const double cw = use_c ? TGT(T_CW, k) : 0.0;
           dzw[k] = fma(iw[k], fma(-zw[k], dw[k], cw), -zw[k]);
-          rp = fmax(rp, -dw[k] * iw[k]);
-          rd = fmax(rd, -dzw[k] * rcp_fast(zw[k]));
+          rp = max(rp, hi_of(-dw[k] * iw[k]));
+          rd = max(rd, hi_of(-dzw[k] * rcp_fast(zw[k])));
         } else dzw[k] = 0.0;
         if (hu()) {
           const double cp = use_c ? TGT(T_CP, k) : 0.0, cq = use_c ? TGT(T_CQ, k) : 0.0;
@@ -536,8 +557,8 @@ struct LaneIpm {
           dsq[k] = fma(fma(2.0, dp, delta), dd[k], geff[k]) * ie[k];
           dzp[k] = fma(isp[k], fma(-zp[k], dsp[k], cp), -zp[k]);
           dzq[k] = fma(isq[k], fma(-zq[k], dsq[k], cq), -zq[k]);
-          rp = fmax(rp, fmax(-dsp[k] * isp[k], -dsq[k] * isq[k]));
-          rd = fmax(rd, fmax(-dzp[k] * rcp_fast(zp[k]), -dzq[k] * rcp_fast(zq[k])));
+          rp = max(rp, max(hi_of(-dsp[k] * isp[k]), hi_of(-dsq[k] * isq[k])));
+          rd = max(rd, max(hi_of(-dzp[k] * rcp_fast(zp[k])), hi_of(-dzq[k] * rcp_fast(zq[k]))));
         } else { dsp[k] = 0.0; dsq[k] = 0.0; dzp[k] = 0.0; dzq[k] = 0.0; }
       }
     } else {
@@ -545,8 +566,8 @@ struct LaneIpm {
       for (int k = 0; k < H; ++k) { dw[k] = 0.0; dsp[k] = 0.0; dsq[k] = 0.0; dzw[k] = 0.0; dzp[k] = 0.0; dzq[k] = 0.0; }
     }
     if (hc() && tid < H) {
-      rp = fmax(rp, -dsc * U(U_ISC, tid));
-      rd = fmax(rd, -dzc * rcp_fast(U(U_ZC, tid)));
+      rp = max(rp, hi_of(-dsc * U(U_ISC, tid)));
+      rd = max(rd, hi_of(-dzc * rcp_fast(U(U_ZC, tid))));
     }
     rp_ = rp; rd_ = rd;
   }
@@ -692,20 +713,22 @@ struct LaneIpm {
       }
     }
     sync();
-    double dres = 0.0;
+    int dres_h = 0;
     if (valid) {
 #pragma unroll
       for (int k = 0; k < H; ++k) {
         const double yk = zp[k] - zq[k];
         const double yn = (k + 1 < H) ? zp[(k + 1 < H) ? k + 1 : 0] - zq[(k + 1 < H) ? k + 1 : 0] : 0.0;
         const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (hw() ? zw[k] : 0.0) + (yk - yn);
-        dres = fmax(dres, fabs(rdw));
-        if (hu()) dres = fmax(dres, fabs(lam - zp[k] - zq[k] + (hc() ? U(U_ZC, k) : 0.0)));
+        dres_h = max(dres_h, hi_of(fabs(rdw)));
+        if (hu()) dres_h = max(dres_h, hi_of(fabs(lam - zp[k] - zq[k] + (hc() ? U(U_ZC, k) : 0.0))));
       }
     }
+    double dres;
     {
-      double dummy = 0.0;
-      block_max2(dres, dummy);
+      int dummy = 0;
+      block_max2i(dres_h, dummy);
+      dres = (dres_h > 0) ? hi_up(dres_h) : 0.0;
     }
     kkt_[0] = pres; kkt_[1] = dres; kkt_[2] = gap;
     gap_ = gap;
@@ -725,17 +748,19 @@ struct LaneIpm {
     if (phase == 0 && !has_m) return;
     const bool use_c = (phase == 1) && has_m;
     const bool stepped = has_m || ash();
-    double dw[H], dsp[H], dsq[H], dzw[H], dzp[H], dzq[H], dnu, dsc, dzc, rp, rd;
-    newton(use_c, dw, dsp, dsq, dzw, dzp, dzq, dnu, dsc, dzc, rp, rd);
+    double dw[H], dsp[H], dsq[H], dzw[H], dzp[H], dzq[H], dnu, dsc, dzc;
+    int rph, rdh;
+    newton(use_c, dw, dsp, dsq, dzw, dzp, dzq, dnu, dsc, dzc, rph, rdh);
     if (ash()) {            // keep the argument of the logarithm positive: rho_k + a * sum_i R dw > 0
       double v[H], tot[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) v[k] = dw[k] * R[k];
       block_sum<H>(v, tot);
 #pragma unroll
-      for (int k = 0; k < H; ++k) rp = fmax(rp, -tot[k] * U(U_IRHO, k));
+      for (int k = 0; k < H; ++k) rph = max(rph, hi_of(-tot[k] * U(U_IRHO, k)));
     }
-    block_max2(rp, rd);
+    block_max2i(rph, rdh);
+    const double rp = (rph > 0) ? hi_up(rph) : 0.0, rd = (rdh > 0) ? hi_up(rdh) : 0.0;
     // largest steps keeping slacks (aa) and duals (ab) non-negative: min(1, 1 / max ratio)
     const double aa = (stepped && rp > 1.0) ? 1.0 / rp : 1.0;
     const double ab = (stepped && rd > 1.0) ? 1.0 / rd : 1.0;
