@@ -153,13 +153,18 @@ int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, i
 
 /* diagnostics: choose the GEMM kernel family process-wide (1 = tcgen05 3xTF32 where eligible [default],
  * 0 = fp32 SIMT everywhere) and run one bare GEMM C[M,Nout] = A[M,K] . W[Nout,K]^T through a chosen kernel
- * (mode 0 = SIMT, 1 = tcgen05; KMPC_E_CUDA with "not eligible" if the shape cannot use it). */
+ * (mode 0 = SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 fp16 pairs; KMPC_E_CUDA with "not eligible" if the shape cannot use it). */
 int kmpc_set_gemm_mode(int use_tensor_cores);
 /* 1 [default]: when the latent step and the read-out are linear (GenericKM with NORM_FN 'id' and a one-layer
  * decoder, or LISTAKM) kmpc_forecast evaluates all H horizons with ONE GEMM against the pre-multiplied matrices
  * D_N (K^T)^(k+1) (built in fp64 at first use); 0: always step z <- z K and decode H times like backtest.py:107-121.
  * Same forecasts within fp32 rounding (tests: 1e-5 relative, norm-wise). */
 int kmpc_set_forecast_fold(int on);
+/* 1 [default]: the GenericKM encoder + folded read-out of kmpc_forecast run on the fp16-pair tensor-core kernel
+ * (an fp32 value travels as fp16(x) and fp16((x - hi) * 2^11): 22 significant bits like the 3xTF32 pair at half the
+ * operand bytes and twice the MMA rate).  kmpc_forecast then synchronises the stream once to read a range flag and
+ * re-runs the 3xTF32 chain if any value left the fp16 range (|x| > 65504).  0: always the 3xTF32 chain. */
+int kmpc_set_gemm_fp16_pairs(int on);
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode);
 
 /* ---------------------------------------------------------------------------------------------

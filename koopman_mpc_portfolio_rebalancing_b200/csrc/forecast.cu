@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include "../../include/kmpc.h"
 #include "kmpc_internal.cuh"
+#include <string.h>
 #include "gemm.cuh"
 
 int kmpc_fail_cuda(cudaError_t e, const char* what);
@@ -40,6 +41,15 @@ struct kmpc_model {
   // so that yhat[:, k, :] = z0 . fold_w[k]^T.  Built on first use for the largest H seen.
   int fold_H;
   float* fold_w; float* fold_w_lo; float* fold_b;
+  // fp16-pair copies for gemm_tc16.cu (built on first use): encoder layers (layer 0 re-laid for the in-place window
+  // read with row stride ld16 = N rounded up to 8), the folded read-out, the standardised series of the current call
+  int ld16, fold16_H;
+  std::vector<__half*> w16_hi, w16_lo;
+  __half *fold16_hi, *fold16_lo;
+  __half *z16_hi, *z16_lo;
+  size_t z16_cap;
+  int* ovf_flag;              // device int: a value left the fp16 range -> the caller re-runs the TF32 chain
+  int* ovf_host;              // pinned host copy
   std::vector<void*> owned;
 };
 
@@ -356,6 +366,142 @@ static int ensure_fold(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st) {
 }
 }  // namespace kmpc
 
+namespace kmpc {
+static int g_tc16 = 1;
+void set_gemm_tc16_mode(int on) { g_tc16 = on ? 1 : 0; }
+
+static bool tc16_eligible(const kmpc_model* m) {
+  if (!g_tc16 || !g_fold) return false;
+  if (m->kind != KMPC_MODEL_GENERIC || m->norm_fn != KMPC_NORM_ID || m->n_dec != 1 || m->n_enc < 1) return false;
+  for (int i = 1; i <= m->n_enc; ++i) if (m->enc_dims[i] % 8) return false;
+  return true;
+}
+
+// fp16-pair copies of the encoder weights and of the folded read-out
+static int ensure_tc16(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st) {
+  cudaError_t e;
+  if (!m->ovf_flag) {
+    if ((e = cudaMalloc(&m->ovf_flag, sizeof(int))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(ovf)");
+    if ((e = cudaMallocHost(&m->ovf_host, sizeof(int))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMallocHost(ovf)");
+  }
+  if (m->w16_hi.empty()) {
+    for (int i = 0; i < m->n_enc; ++i) {
+      const int out_f = m->enc_dims[i + 1];
+      const int in_f = (i == 0) ? m->d * m->ld16 : m->enc_dims[i];
+      __half *hi = nullptr, *lo = nullptr;
+      if ((e = cudaMalloc(&hi, (size_t)out_f * in_f * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(w16)");
+      if ((e = cudaMalloc(&lo, (size_t)out_f * in_f * sizeof(__half))) != cudaSuccess) { cudaFree(hi); return kmpc_fail_cuda(e, "cudaMalloc(w16)"); }
+      m->w16_hi.push_back(hi); m->w16_lo.push_back(lo);
+      const float* src = m->enc_w[i];
+      float* tmp = nullptr;
+      if (i == 0) {          // window layout with row stride ld16
+        if ((e = cudaMalloc(&tmp, (size_t)out_f * in_f * sizeof(float))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(w16 tmp)");
+        window_permute_kernel<<<h->sm_count * 4, 256, 0, st>>>(m->enc_w[0], out_f, m->N, m->d, m->ld16, tmp);
+        src = tmp;
+      }
+      int rc = launch_split16(src, out_f, in_f, in_f, hi, lo, in_f, nullptr, st);
+      cudaStreamSynchronize(st);
+      if (tmp) cudaFree(tmp);
+      if (rc) return kmpc_fail_cuda((cudaError_t)rc, "split16(weights)");
+      h->launches += 2;
+    }
+  }
+  if (!m->fold16_hi || m->fold16_H != m->fold_H || m->fold_H < H) {
+    if (m->fold16_hi) { cudaFree(m->fold16_hi); cudaFree(m->fold16_lo); m->fold16_hi = m->fold16_lo = nullptr; }
+    const size_t rows_pad = (size_t)((m->fold_H * m->N + 127) / 128) * 128;
+    if ((e = cudaMalloc(&m->fold16_hi, rows_pad * m->Z * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(fold16)");
+    if ((e = cudaMalloc(&m->fold16_lo, rows_pad * m->Z * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(fold16)");
+    int rc = launch_split16(m->fold_w, (long long)rows_pad, m->Z, m->Z, m->fold16_hi, m->fold16_lo, m->Z, nullptr, st);
+    if (rc) return kmpc_fail_cuda((cudaError_t)rc, "split16(fold)");
+    m->fold16_H = m->fold_H;
+    h->launches++;
+  }
+  return 0;
+}
+
+// GenericKM forecast with fp16-pair operands: encoder MLP + folded read-out, all rows of all paths.
+// Returns 1 when a value left the fp16 range (the caller re-runs the TF32 chain), 0 on success, < 0 on error.
+static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int T, int row0, int t0, int t1, int H,
+                       const float* std32, const float* mean32, int stat_rows_per_group, float* out, cudaStream_t st) {
+  int rc;
+  if ((rc = ensure_fold(h, m, H, st))) return rc;
+  if ((rc = ensure_tc16(h, m, H, st))) return rc;
+  const int Z = m->Z, N = m->N, ld16 = m->ld16, rpp = t1 - t0, M = B * rpp;
+  cudaError_t e;
+  // the standardised series as an fp16 pair, row stride ld16
+  const size_t zn = (size_t)B * T * ld16;
+  if (m->z16_cap < zn) {
+    if (m->z16_hi) { cudaFree(m->z16_hi); cudaFree(m->z16_lo); m->z16_hi = m->z16_lo = nullptr; m->z16_cap = 0; }
+    if ((e = cudaMalloc(&m->z16_hi, zn * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(z16)");
+    if ((e = cudaMalloc(&m->z16_lo, zn * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(z16)");
+    m->z16_cap = zn;
+  }
+  cudaMemsetAsync(m->ovf_flag, 0, sizeof(int), st);
+  if ((rc = launch_split16(z, (long long)B * T, N, m->ld, m->z16_hi, m->z16_lo, ld16, m->ovf_flag, st)))
+    return kmpc_fail_cuda((cudaError_t)rc, "split16(series)");
+  h->launches++;
+  int maxw = Z;
+  for (int v : m->enc_dims) if (v > maxw) maxw = v;
+  long long ch = 32768;
+  if (rpp < M) { ch = (ch / rpp) * rpp; if (ch < rpp) ch = rpp; }
+  if (ch > M) ch = M;
+  const int CH = (int)ch;
+  const size_t need = (size_t)CH * maxw * 4 * sizeof(__half) + 256;
+  if (h->scratch_bytes < need) {
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr; h->scratch_bytes = 0;
+    if ((e = cudaMalloc(&h->scratch, need)) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(forecast scratch)");
+    h->scratch_bytes = need;
+  }
+  __half* act_hi[2]; __half* act_lo[2];
+  for (int i = 0; i < 2; ++i) {
+    act_hi[i] = (__half*)h->scratch + (size_t)(2 * i) * CH * maxw;
+    act_lo[i] = (__half*)h->scratch + (size_t)(2 * i + 1) * CH * maxw;
+  }
+  for (int r0 = 0; r0 < M; r0 += CH) {
+    const int rows = (M - r0 < CH) ? (M - r0) : CH;
+    int cur = 0;
+    for (int li = 0; li < m->n_enc; ++li) {
+      Gemm16Args g;
+      memset(&g, 0, sizeof(g));
+      const bool last = (li == m->n_enc - 1);
+      if (li == 0) {
+        g.A_hi = m->z16_hi + (size_t)(row0 + t0) * ld16; g.A_lo = m->z16_lo + (size_t)(row0 + t0) * ld16;
+        g.a_group_stride = (long long)T * ld16; g.a_rows_per_group = rpp; g.lda = ld16; g.row0 = r0; g.K = m->d * ld16;
+      } else {
+        g.A_hi = act_hi[cur ^ 1]; g.A_lo = act_lo[cur ^ 1]; g.a_rows_per_group = rows; g.lda = m->enc_dims[li]; g.K = m->enc_dims[li];
+      }
+      g.W_hi = m->w16_hi[li]; g.W_lo = m->w16_lo[li]; g.ldw = g.K;
+      g.M = rows; g.Nout = m->enc_dims[li + 1]; g.n_store = g.Nout;
+      g.bias = m->enc_b[li];
+      g.act = last ? (m->enc_last_relu ? EPI_RELU : EPI_NONE) : act_to_epi(m->enc_act);
+      g.C16_hi = act_hi[cur]; g.C16_lo = act_lo[cur]; g.ldc16 = g.Nout;
+      g.overflow_flag = m->ovf_flag;
+      rc = launch_gemm_tc16(g, st);
+      h->launches++;
+      if (rc == -100) return 1;                         // not eligible after all: let the TF32 chain take over
+      if (rc) return kmpc_fail_cuda((cudaError_t)rc, "gemm_tc16");
+      cur ^= 1;
+    }
+    Gemm16Args d;
+    memset(&d, 0, sizeof(d));
+    d.A_hi = act_hi[cur ^ 1]; d.A_lo = act_lo[cur ^ 1]; d.a_rows_per_group = rows; d.lda = Z; d.K = Z;
+    d.W_hi = m->fold16_hi; d.W_lo = m->fold16_lo; d.ldw = Z;
+    d.M = rows; d.Nout = H * N; d.n_store = H * N; d.bias = m->fold_b; d.act = EPI_NONE;
+    d.C = out + (size_t)r0 * H * N; d.ldc = (long long)H * N;
+    d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = N; d.stat_row0 = r0; d.stat_mod = N;
+    d.overflow_flag = m->ovf_flag;
+    rc = launch_gemm_tc16(d, st);
+    h->launches++;
+    if (rc == -100) return 1;
+    if (rc) return kmpc_fail_cuda((cudaError_t)rc, "gemm_tc16(read-out)");
+  }
+  if ((e = cudaMemcpyAsync(m->ovf_host, m->ovf_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return kmpc_fail_cuda(e, "copy ovf");
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return kmpc_fail_cuda(e, "forecast (fp16-pair chain)");
+  return *m->ovf_host ? 1 : 0;
+}
+}  // namespace kmpc
+
 static thread_local char f_err[256];
 static int ffail(int code, const char* msg) { snprintf(f_err, sizeof(f_err), "%s", msg); return code; }
 #define FCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return kmpc_fail_cuda(e_, #call); } while (0)
@@ -387,6 +533,12 @@ int kmpc_model_free(kmpc_model* m) {
   if (m->z_lo) cudaFree(m->z_lo);
   if (m->fold_w) { cudaFree(m->fold_w); cudaFree(m->fold_w_lo); }
   if (m->fold_b) cudaFree(m->fold_b);
+  for (__half* q : m->w16_hi) cudaFree(q);
+  for (__half* q : m->w16_lo) cudaFree(q);
+  if (m->fold16_hi) { cudaFree(m->fold16_hi); cudaFree(m->fold16_lo); }
+  if (m->z16_hi) { cudaFree(m->z16_hi); cudaFree(m->z16_lo); }
+  if (m->ovf_flag) cudaFree(m->ovf_flag);
+  if (m->ovf_host) cudaFreeHost(m->ovf_host);
   delete m;
   return KMPC_OK;
 }
@@ -405,6 +557,8 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
   m->lista_ST = nullptr; m->lista_wdT = nullptr; m->lista_ST_lo = nullptr; m->lista_wdT_lo = nullptr; m->kmatT_lo = nullptr; m->enc_w0_win_lo = nullptr;
   m->z_lo = nullptr; m->z_lo_cap = 0;
   m->fold_H = 0; m->fold_w = nullptr; m->fold_w_lo = nullptr; m->fold_b = nullptr;
+  m->ld16 = ((D->n_assets + 7) / 8) * 8; m->fold16_H = 0; m->fold16_hi = m->fold16_lo = nullptr;
+  m->z16_hi = m->z16_lo = nullptr; m->z16_cap = 0; m->ovf_flag = nullptr; m->ovf_host = nullptr;
   int rc = 0;
   auto bail = [&](int code) { kmpc_model_free(m); return code; };
   const bool mlp_enc = (D->kind == KMPC_MODEL_GENERIC) || !D->lista_linear_encoder;
@@ -504,8 +658,13 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
   int rc = stats_to_f32(h, mean, std, (stats_per_path ? B : 1) * m->N, &std32, &mean32, st);
   if (rc) return rc;
   const int rpp = t1 - t0;
-  // residual twin of the series for the 3xTF32 operand split of the first layer
   kmpc_model* mm = const_cast<kmpc_model*>(m);
+  if (kmpc::tc16_eligible(m) && rpp >= 1 && B * rpp >= 128) {
+    // fp16-pair tensor-core chain (gemm_tc16.cu); synchronises the stream to read the range flag
+    rc = kmpc::run_chain16(h, mm, z, B, T, row0, t0, t1, H, std32, mean32, stats_per_path ? rpp : 0, yhat, st);
+    if (rc <= 0) return rc;
+  }
+  // residual twin of the series for the 3xTF32 operand split of the first layer
   const size_t zn = (size_t)B * T * ld_z;
   if (mm->z_lo_cap < zn) {
     if (mm->z_lo) cudaFree(mm->z_lo);
@@ -595,12 +754,32 @@ int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, floa
 // 1 = tcgen05 3xTF32 GEMM where eligible (default), 0 = fp32 SIMT GEMM everywhere.  Process-wide.
 int kmpc_set_gemm_mode(int use_tensor_cores) { kmpc::set_gemm_tc_mode(use_tensor_cores); return KMPC_OK; }
 int kmpc_set_forecast_fold(int on) { kmpc::set_forecast_fold(on); return KMPC_OK; }
+int kmpc_set_gemm_fp16_pairs(int on) { kmpc::set_gemm_tc16_mode(on); return KMPC_OK; }
 
 // C[M,Nout] = A[M,K] . W[Nout,K]^T through one chosen kernel: mode 0 = SIMT fp32, 1 = tcgen05 3xTF32 (returns
 // KMPC_E_UNSUPPORTED if the shape is not eligible).  Allocates the residual twins internally; synchronous.
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode) {
   if (!h || !A || !W || !C || M <= 0 || Nout <= 0 || K <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_debug_gemm: bad argument");
   FCK(cudaSetDevice(h->device));
+  if (mode == 2) {           // fp16-pair tensor-core kernel
+    __half *Ah = nullptr, *Al = nullptr, *Wh = nullptr, *Wl = nullptr;
+    FCK(cudaMalloc(&Ah, (size_t)M * K * sizeof(__half))); FCK(cudaMalloc(&Al, (size_t)M * K * sizeof(__half)));
+    FCK(cudaMalloc(&Wh, (size_t)Nout * K * sizeof(__half))); FCK(cudaMalloc(&Wl, (size_t)Nout * K * sizeof(__half)));
+    kmpc::launch_split16(A, M, K, K, Ah, Al, K, nullptr, 0);
+    kmpc::launch_split16(W, Nout, K, K, Wh, Wl, K, nullptr, 0);
+    kmpc::Gemm16Args g;
+    memset(&g, 0, sizeof(g));
+    g.A_hi = Ah; g.A_lo = Al; g.a_rows_per_group = M; g.lda = K; g.K = K; g.W_hi = Wh; g.W_lo = Wl; g.ldw = K;
+    g.M = M; g.Nout = Nout; g.n_store = Nout; g.C = C; g.ldc = Nout; g.act = kmpc::EPI_NONE;
+    int rc = kmpc::launch_gemm_tc16(g, 0);
+    h->launches += 3;
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(Ah); cudaFree(Al); cudaFree(Wh); cudaFree(Wl);
+    if (rc == -100) return kmpc_fail_cuda(cudaErrorNotSupported, "kmpc_debug_gemm: shape not eligible for the fp16-pair tcgen05 kernel");
+    if (rc) return kmpc_fail_cuda((cudaError_t)rc, "kmpc_debug_gemm launch");
+    if (e != cudaSuccess) return kmpc_fail_cuda(e, "kmpc_debug_gemm kernel");
+    return KMPC_OK;
+  }
   float *Alo = nullptr, *Wlo = nullptr;
   FCK(cudaMalloc(&Alo, (size_t)M * K * sizeof(float)));
   cudaError_t e = cudaMalloc(&Wlo, (size_t)Nout * K * sizeof(float));

@@ -1,6 +1,7 @@
 // GEMM interface of the forecast path:  C = epilogue(A[M,K] . W[Nout,K]^T)
 // (nn.Linear convention: weight [out,in] row-major, x @ W^T + b, model.py:96-117).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,6 +43,30 @@ struct GemmArgs {
   // optional second output holding the fp32 residual of the TF32 rounding of C (3xTF32 operand split)
   float* C_lo;
 };
+
+// fp16-pair tensor-core path (gemm_tc16.cu): an fp32 value x travels as hi = fp16(x), lo = fp16((x - hi) * 2^11)
+struct Gemm16Args {
+  const __half* A_hi; const __half* A_lo;   // row addressing as in GemmArgs (elements are halves)
+  long long a_group_stride;
+  int a_rows_per_group, lda, row0;
+  const __half* W_hi; const __half* W_lo;   // [Nout, K], row stride ldw
+  int ldw;
+  int M, Nout, K;
+  const float* bias;
+  int act;                                   // EPI_NONE / RELU / TANH / GELU
+  __half* C16_hi; __half* C16_lo;            // fp16-pair output (next layer's operand) or null
+  long long ldc16;
+  float* C;                                  // fp32 output or null; row stride ldc, columns < n_store
+  long long ldc;
+  int n_store;
+  const float* std32; const float* mean32;   // de-standardise epilogue on the fp32 output, as in GemmArgs
+  int stat_rows_per_group, stat_ld, stat_row0, stat_mod;
+  int* overflow_flag;                        // device int, set to 1 when a value outside the fp16 range is written
+};
+// returns -100 when the launch is not eligible (shape, alignment)
+int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st);
+int launch_split16(const float* x, long long rows, int cols, int ld_in, __half* hi, __half* lo, int ld_out, int* overflow,
+                   cudaStream_t st);
 
 // fp32 SIMT path (exact fp32 FMA accumulation; any shape / alignment)
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);

@@ -1,0 +1,433 @@
+// tcgen05 / TMA GEMM with fp32-class accuracy from FP16 operand pairs, for the MLP encoder and the folded read-out of
+// the forecast path:    C[M, Nout] = epilogue( A[M,K] . W[Nout,K]^T )
+//
+// Why a second tensor-core kernel: the 3xTF32 kernel (gemm_tc.cu) moves 8 bytes per operand element (x and its
+// residual twin, fp32 each); at 128x128x32 tiles that is 64 KB per k-block and SM, and the forecast chain pulls
+// 8.2 TB/s out of L2 (ncu: lts__t_sectors) with the tensor pipe 34 % busy.  Here an fp32 value x travels as two
+// halves:  hi = fp16(x)  and  lo = fp16((x - hi) * 2^11)  — 22 significant bits like the TF32 pair, 4 bytes per
+// element, and kind::f16 MMAs run at twice the TF32 rate.  D = A_hi.W_hi (three rotating fp32 TMEM accumulators,
+// see gemm_tc.cu on accumulation truncation) + 2^-11 (A_lo.W_hi + A_hi.W_lo) (fourth accumulator).
+// Range: |x| must stay below 65504; the epilogue raises a device flag when it writes a half that overflowed and the
+// caller re-runs the TF32 chain (forecast.cu).  Values below 6e-5 keep an absolute accuracy of 2^-25.
+//
+// Same structure as gemm_tc.cu: one CTA per SM, persistent over 128 x 128 output tiles, k-blocks of 64 halves
+// (= one 128-byte swizzle row), 3-stage TMA ring of (A_hi, A_lo, W_hi, W_lo) boxes, warp 0 TMA producer, warp 1
+// single-thread MMA issuer (12 tcgen05.mma.kind::f16 per stage), warp 2 TMEM allocator, warps 4..7 epilogue
+// (bias / activation / de-standardise, then either the fp16 pair of the next layer or fp32 output).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "gemm.cuh"
+
+namespace kmpc {
+
+namespace tc16 {
+
+constexpr int BM = 128, BN = 128, BK = 64;          // BK halves = 128 bytes = one swizzle atom row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;             // 16 KB (BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, W_hi, W_lo
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int TMEM_COLS = 512;                      // 3 hi accumulators + 1 lo accumulator of 128 fp32 columns
+constexpr int NUM_HI = 3;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;           // bounded waits: trap instead of hanging the GPU
+
+struct Params {
+  int M, Nout, K;
+  int rows_per_group, tiles_per_group, n_groups;     // M = n_groups * rows_per_group
+  int tiles_n, num_tiles, k_blocks;
+  const float* bias;
+  int act;
+  const float* std32; const float* mean32; int stat_rows_per_group; int stat_ld; int row0; int stat_mod;
+  __half* C16_hi; __half* C16_lo; long long ldc16;
+  float* C; long long ldc; int n_store;
+  int* overflow;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) { printf("kmpc gemm_tc16: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | SBO(1024 B)>>4 at bit 32 | version 1 at bit 46 |
+// layout SWIZZLE_128B (=2) at bit 61   (cute/arch/mma_sm100_desc.hpp, UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (UMMA::InstrDescriptor): c = F32 (1 at bit 4), a = b = F16 (0 at bits 7 / 10), K-major both,
+// N = 128, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo, Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: stages first (1024-aligned), then barriers
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(base + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [1] accumulators ready
+  uint64_t* tempty_bar = tfull_bar + 1;         // [1] accumulators drained
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapWlo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tempty_bar[0], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+        const int g = tm / p.tiles_per_group, tb = tm - g * p.tiles_per_group;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = base + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_3d(&mapA, &full_bar[stage], st, kb * BK, tb * BM, g);
+          tma_load_3d(&mapAlo, &full_bar[stage], st + TILE_BYTES, kb * BK, tb * BM, g);
+          tma_load_2d(&mapW, &full_bar[stage], st + 2 * TILE_BYTES, kb * BK, tn * BN);
+          tma_load_2d(&mapWlo, &full_bar[stage], st + 3 * TILE_BYTES, kb * BK, tn * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_lo = tmem_base + NUM_HI * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
+          const uint64_t dA = make_desc(sa), dAlo = make_desc(sa + TILE_BYTES);
+          const uint64_t dW = make_desc(sa + 2 * TILE_BYTES), dWlo = make_desc(sa + 3 * TILE_BYTES);
+          const uint32_t d_hi = tmem_base + (uint32_t)(kb % NUM_HI) * BN;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * 32) >> 4);       // 16 halves = 32 bytes inside the swizzle atom
+            mma_f16(d_lo, dAlo + adv, dW + adv, (kb == 0 && kk == 0) ? 0u : 1u);
+            mma_f16(d_lo, dA + adv, dWlo + adv, 1u);
+            mma_f16(d_hi, dA + adv, dW + adv, (kb < NUM_HI && kk == 0) ? 0u : 1u);
+          }
+          umma_commit(&empty_bar[stage]);                          // frees the smem stage when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[0]);                                // accumulators complete
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                                        // TMEM lane quarter this warp may access
+    uint32_t acc_phase = 0;
+    const int nhi = p.k_blocks < NUM_HI ? p.k_blocks : NUM_HI;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+      const int g = tm / p.tiles_per_group, tb = tm - g * p.tiles_per_group;
+      const int r_in_group = tb * BM + q * 32 + lane;
+      const bool row_ok = r_in_group < p.rows_per_group;
+      const long long m = (long long)g * p.rows_per_group + r_in_group;
+      mbar_wait(&tfull_bar[0], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 16; ++cb) {
+        uint32_t v[16], u[16];
+        float acc[16];
+        tmem_ld16(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);          // lo products, scaled by 2^11
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) * (1.0f / 2048.0f);
+        for (int hsel = 0; hsel < nhi; ++hsel) {
+          tmem_ld16(lane_addr + (uint32_t)(hsel * BN + cb * 16), u);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(u[j]));
+        }
+        const int n0 = tn * BN + cb * 16;
+        if (row_ok && n0 < p.n_store) {
+          const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (m + p.row0) / p.stat_rows_per_group : 0;
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j;
+            float t = acc[j];
+            if (n < p.n_store) {
+              if (p.bias) t += p.bias[n];
+              t = epilogue_apply(t, p.act, 0.0f);
+              if (p.std32) {
+                const int sn = p.stat_mod ? n % p.stat_mod : n;
+                t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + sn]), p.mean32[sg * p.stat_ld + sn]);
+              }
+            }
+            x[j] = t;
+          }
+          if (p.C16_hi) {                       // next layer's operand: fp16 pair, lo scaled by 2^11
+            __align__(16) __half hh[16];
+            __align__(16) __half ll[16];
+            bool ovf = false;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __half h = __float2half_rn(x[j]);
+              hh[j] = h;
+              ll[j] = __float2half_rn((x[j] - __half2float(h)) * 2048.0f);
+              ovf = ovf || !(fabsf(x[j]) <= 65504.0f);
+            }
+            if (ovf && p.overflow) *p.overflow = 1;
+            __half* hrow = p.C16_hi + m * p.ldc16 + n0;
+            __half* lrow = p.C16_lo + m * p.ldc16 + n0;
+            if (n0 + 16 <= p.n_store) {
+              reinterpret_cast<uint4*>(hrow)[0] = reinterpret_cast<const uint4*>(hh)[0];
+              reinterpret_cast<uint4*>(hrow)[1] = reinterpret_cast<const uint4*>(hh)[1];
+              reinterpret_cast<uint4*>(lrow)[0] = reinterpret_cast<const uint4*>(ll)[0];
+              reinterpret_cast<uint4*>(lrow)[1] = reinterpret_cast<const uint4*>(ll)[1];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) { hrow[j] = hh[j]; lrow[j] = ll[j]; }
+            }
+          }
+          if (p.C) {
+            float* crow = p.C + m * p.ldc + n0;
+            const bool full = (n0 + 16 <= p.n_store) && ((((uintptr_t)crow) & 15) == 0);
+            if (full) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) crow[j] = x[j];
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[0]);
+      acc_phase ^= 1;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// --------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+  }
+  return fn;
+}
+
+static bool encode(CUtensorMap* map, const __half* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  EncodeFn fn = get_encode();
+  if (!fn) return false;
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, (void*)ptr, dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc16
+
+int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st) {
+  using namespace tc16;
+  if (!g.A_hi || !g.A_lo || !g.W_hi || !g.W_lo) return -100;
+  if (g.Nout < 16 || g.K < BK || g.M < BM) return -100;
+  if ((g.lda % 8) || (g.ldw % 8) || (g.a_group_stride % 8)) return -100;              // 16-byte row strides
+  if (((uintptr_t)g.A_hi & 15) || ((uintptr_t)g.A_lo & 15) || ((uintptr_t)g.W_hi & 15) || ((uintptr_t)g.W_lo & 15)) return -100;
+  if (g.C16_hi && ((g.ldc16 % 8) || ((uintptr_t)g.C16_hi & 15) || ((uintptr_t)g.C16_lo & 15) || !g.C16_lo)) return -100;
+  Params p;
+  const bool flat = g.a_rows_per_group >= g.M + g.row0;
+  if (flat) {
+    p.rows_per_group = g.M; p.n_groups = 1;
+  } else {
+    if (g.row0 % g.a_rows_per_group || g.M % g.a_rows_per_group) return -100;
+    p.rows_per_group = g.a_rows_per_group; p.n_groups = g.M / g.a_rows_per_group;
+  }
+  p.tiles_per_group = (p.rows_per_group + BM - 1) / BM;
+  p.M = g.M; p.Nout = g.Nout; p.K = g.K;
+  p.tiles_n = (g.Nout + BN - 1) / BN;
+  p.num_tiles = p.tiles_n * p.tiles_per_group * p.n_groups;
+  p.k_blocks = (g.K + BK - 1) / BK;
+  p.bias = g.bias; p.act = g.act;
+  p.C16_hi = g.C16_hi; p.C16_lo = g.C16_lo; p.ldc16 = g.ldc16;
+  p.C = g.C; p.ldc = g.ldc; p.n_store = g.n_store < g.Nout ? g.n_store : g.Nout;
+  p.std32 = g.std32; p.mean32 = g.mean32; p.stat_rows_per_group = g.stat_rows_per_group; p.stat_ld = g.stat_ld;
+  p.row0 = g.stat_row0; p.stat_mod = g.stat_mod;
+  p.overflow = g.overflow_flag;
+
+  const long long a_off = flat ? (long long)g.row0 * g.lda
+                               : (long long)(g.row0 / g.a_rows_per_group) * g.a_group_stride;
+  const long long gstride = flat ? (long long)g.M * g.lda : g.a_group_stride;
+  CUtensorMap mA, mAlo, mW, mWlo;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)p.rows_per_group, (cuuint64_t)p.n_groups};
+    cuuint64_t strides[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)gstride * 2};
+    cuuint32_t box[3] = {BK, BM, 1};
+    if (!encode(&mA, g.A_hi + a_off, 3, dims, strides, box)) return -100;
+    if (!encode(&mAlo, g.A_lo + a_off, 3, dims, strides, box)) return -100;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.Nout};
+    cuuint64_t strides[1] = {(cuuint64_t)g.ldw * 2};
+    cuuint32_t box[2] = {BK, BN};
+    if (!encode(&mW, g.W_hi, 2, dims, strides, box)) return -100;
+    if (!encode(&mWlo, g.W_lo, 2, dims, strides, box)) return -100;
+  }
+  static int sm_count = 0;
+  static bool attr_set = false;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(gemm_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  gemm_tc16_kernel<<<grid, NUM_THREADS, smem, st>>>(mA, mAlo, mW, mWlo, p);
+  return (int)cudaGetLastError();
+}
+
+// fp32 matrix [rows, cols] (row stride ld_in) -> fp16 pair (hi, lo * 2^11), row stride ld_out >= cols, padding zeroed
+__global__ void split16_kernel(const float* __restrict__ x, long long rows, int cols, int ld_in, __half* __restrict__ hi,
+                               __half* __restrict__ lo, int ld_out, int* __restrict__ overflow) {
+  const long long total = rows * ld_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld_out;
+    const int c = (int)(i - r * ld_out);
+    float v = 0.0f;
+    if (c < cols) v = x[r * ld_in + c];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+    if (overflow && !(fabsf(v) <= 65504.0f)) *overflow = 1;
+  }
+}
+int launch_split16(const float* x, long long rows, int cols, int ld_in, __half* hi, __half* lo, int ld_out, int* overflow,
+                   cudaStream_t st) {
+  const long long n = rows * ld_out;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split16_kernel<<<(int)blocks, 256, 0, st>>>(x, rows, cols, ld_in, hi, lo, ld_out, overflow);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace kmpc

@@ -189,3 +189,59 @@ def test_folded_readout_matches_sequential_steps(kind):
         want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
         assert rowwise_rel(y_fold[b], want) < FORECAST_RTOL
         assert rowwise_rel(y_seq[b], want) < FORECAST_RTOL
+
+
+def test_fp16_pair_chain_matches_tf32_chain_and_oracle():
+    """GenericKM forecast on the fp16-pair tensor-core kernel (default) vs the 3xTF32 chain (kmpc_set_gemm_fp16_pairs(0))
+    vs the oracle, tensor-core eligible widths, ragged N (padding to the 8-column fp16 row stride), per-path stats."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, data_finance as df, model as km, synthetic
+    from oracle import forecast_oracle as fo, data_oracle as do
+    rng = np.random.default_rng(31)
+    B, T, N, d, H, Z = 6, 150, 10, 12, 5, 128
+    lr = rng.standard_normal((B, T, N)) * 0.012
+    mean = rng.normal(3e-4, 1e-4, (B, N)); std = rng.uniform(0.008, 0.02, (B, N))
+    sd = synthetic.generic_km_weights(12, N * d, [256, 128], Z)
+    m = km.make_model(km.model_config("GenericKM", Z, [256, 128], enc_bias=True), N * d)
+    m.load_state_dict(sd)
+    z = df.standardize_device(lr, mean, std)
+    mean_d, std_d = torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda()
+    rows = T - d + 1
+    y16 = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, rows, H).cpu().numpy()
+    try:
+        _capi.lib().kmpc_set_gemm_fp16_pairs(0)
+        y32 = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, rows, H).cpu().numpy()
+    finally:
+        _capi.lib().kmpc_set_gemm_fp16_pairs(1)
+    assert not np.array_equal(y16, y32)                      # two different kernels really ran
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    for b in range(B):
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)
+        want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
+        assert rowwise_rel(y16[b], want) < FORECAST_RTOL
+        assert rowwise_rel(y32[b], want) < FORECAST_RTOL
+
+
+def test_fp16_pair_chain_falls_back_when_values_leave_the_fp16_range():
+    """an input beyond 65504 standard deviations cannot travel as an fp16 pair: the range flag sends the call to the
+    3xTF32 chain, and the result still matches the oracle"""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df, model as km, synthetic
+    from oracle import forecast_oracle as fo, data_oracle as do
+    rng = np.random.default_rng(32)
+    B, T, N, d, H, Z = 4, 80, 8, 8, 3, 64
+    lr = rng.standard_normal((B, T, N)) * 0.012
+    lr[1, 40, 3] = 2000.0                                       # /std 0.014 -> 1.4e5 standardised
+    mean = np.full((B, N), 3e-4); std = np.full((B, N), 0.014)
+    sd = synthetic.generic_km_weights(13, N * d, [128, 128], Z)
+    m = km.make_model(km.model_config("GenericKM", Z, [128, 128], enc_bias=True), N * d)
+    m.load_state_dict(sd)
+    z = df.standardize_device(lr, mean, std)
+    rows = T - d + 1
+    y = m.forecast_series(z, torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda(), N, d, 0, 0, rows, H).cpu().numpy()
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    for b in range(B):
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)
+        want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
+        assert np.all(np.isfinite(y[b]))
+        assert rowwise_rel(y[b], want) < FORECAST_RTOL

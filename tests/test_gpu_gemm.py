@@ -19,8 +19,8 @@ def run(A, W, mode):
     return out
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 128, 64), (384, 256, 1024), (1000, 1024, 1040), (4096, 1024, 1024),
-                                   (130, 192, 40), (777, 320, 200)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 64), (384, 256, 1024), (1000, 1024, 1040), (4096, 1024, 1024),
+                                   (130, 192, 72), (777, 320, 200)])
 def test_tcgen05_gemm_is_fp32_accurate(M, N, K):
     import torch
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
@@ -32,9 +32,12 @@ def test_tcgen05_gemm_is_fp32_accurate(M, N, K):
     scale = ref.abs().max(dim=1, keepdim=True).values
     e_simt = ((simt.double() - ref).abs() / scale).max().item()
     e_tc = ((tc.double() - ref).abs() / scale).max().item()
-    print(f"M={M} N={N} K={K}: row-wise rel err  simt {e_simt:.2e}  tcgen05-3xTF32 {e_tc:.2e}")
+    tc16 = run(A, W, 2)
+    e_tc16 = ((tc16.double() - ref).abs() / scale).max().item()
+    print(f"M={M} N={N} K={K}: row-wise rel err  simt {e_simt:.2e}  tcgen05-3xTF32 {e_tc:.2e}  tcgen05-fp16-pairs {e_tc16:.2e}")
     assert e_simt < 4e-6
     assert e_tc < 4e-6
+    assert e_tc16 < 4e-6
 
 
 def test_small_shapes_are_not_eligible_for_tcgen05():
