@@ -279,14 +279,15 @@ def run_gpu_arm(args):
         peak_src = "measured" if peaks else "fallback"
         fpd = flops_per_decision(w, folded=True)
         fc_tflops = fpd * decisions_per_step_rank / (st_fc * 1e-3) / 1e12
-        # fp32-accurate tensor rate = TF32 dense / 3 (3xTF32 split), TF32 dense taken as bf16 / 2
-        tensor_peak = bf16 / 2.0 / 3.0
+        # fp32-accurate tensor rate of the fp16-pair kernel: three kind::f16 MMAs (hi.hi, lo.hi, hi.lo) per product,
+        # fp16 dense rate = the measured bf16 rate
+        tensor_peak = bf16 / 3.0
         hbm_bytes_bt = (8 * N + 8 * H * N + 32) * decisions_per_step_rank
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         dominant = "backtest_kernel" if st_bt >= st_fc else "forecast_gemm_chain"
-        roof_fc = {"kernel": "forecast GEMM chain (gemm_tc_kernel: encoder 3 GEMMs + folded multi-horizon read-out)", "bound": "tensor", "achieved": fc_tflops,
+        roof_fc = {"kernel": "forecast GEMM chain (gemm_tc16_kernel, tcgen05 fp16 pairs: encoder 3 GEMMs + folded multi-horizon read-out)", "bound": "tensor", "achieved": fc_tflops,
                    "peak": tensor_peak, "unit": "TFLOP/s", "frac": fc_tflops / tensor_peak, "traffic": None,
-                   "peak_source": f"{peak_src} bf16 sustained / 2 (TF32) / 3 (3xTF32 split for fp32 accuracy)",
+                   "peak_source": f"{peak_src} bf16 sustained / 3 (three fp16 MMAs per fp32-accurate product)",
                    "flops_per_decision": fpd, "flops_per_decision_unfolded": flops_per_decision(w), "ms": st_fc}
         bt_gbs = hbm_bytes_bt / (st_bt * 1e-3) / 1e9
         # ncu --set full (profiles/r1_backtest_lane_kernel.txt): dram read+write 1265 B per decision

@@ -134,6 +134,59 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int ACT>
+__device__ __forceinline__ float act_apply(float x) {
+  if (ACT == EPI_RELU) return (x < 0.0f) ? 0.0f : x;                       // NaN propagates like torch.relu
+  if (ACT == EPI_TANH) return tanhf(x);
+  if (ACT == EPI_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  return x;
+}
+
+// Interior block of the fp16-pair output: 16 full columns, bias + activation, branch-free.
+template <int ACT>
+__device__ __forceinline__ void store_pair_block(const Params& p, const float (&acc)[16], long long m, int n0) {
+  float x[16];
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);          // warp-uniform address: broadcast loads
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 b = b4[j4];
+      x[j4 * 4] = acc[j4 * 4] + b.x; x[j4 * 4 + 1] = acc[j4 * 4 + 1] + b.y;
+      x[j4 * 4 + 2] = acc[j4 * 4 + 2] + b.z; x[j4 * 4 + 3] = acc[j4 * 4 + 3] + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = acc[j];
+  }
+  __align__(16) __half2 hh[8];
+  __align__(16) __half2 ll[8];
+  float mx = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a = act_apply<ACT>(x[2 * j]), b = act_apply<ACT>(x[2 * j + 1]);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    hh[j] = h;
+    ll[j] = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+    mx = fmaxf(mx, fmaxf(fabsf(a), fabsf(b)));
+  }
+  if (!(mx <= 65504.0f) && p.overflow) *p.overflow = 1;                       // also catches NaN
+  uint4* hrow = reinterpret_cast<uint4*>(p.C16_hi + m * p.ldc16 + n0);
+  uint4* lrow = reinterpret_cast<uint4*>(p.C16_lo + m * p.ldc16 + n0);
+  hrow[0] = reinterpret_cast<const uint4*>(hh)[0]; hrow[1] = reinterpret_cast<const uint4*>(hh)[1];
+  lrow[0] = reinterpret_cast<const uint4*>(ll)[0]; lrow[1] = reinterpret_cast<const uint4*>(ll)[1];
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo, Params p) {
@@ -231,22 +284,35 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tfull_bar[0], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (long long)((int)(m + p.row0) / p.stat_rows_per_group) : 0;
 #pragma unroll 1
       for (int cb = 0; cb < BN / 16; ++cb) {
-        uint32_t v[16], u[16];
+        uint32_t v[16], u0[16], u1[16], u2[16];
         float acc[16];
-        tmem_ld16(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);          // lo products, scaled by 2^11
+        tmem_ld16_nowait(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);    // lo products, scaled by 2^11
+        tmem_ld16_nowait(lane_addr + (uint32_t)(0 * BN + cb * 16), u0);
+        if (nhi > 1) tmem_ld16_nowait(lane_addr + (uint32_t)(1 * BN + cb * 16), u1);
+        if (nhi > 2) tmem_ld16_nowait(lane_addr + (uint32_t)(2 * BN + cb * 16), u2);
+        tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) * (1.0f / 2048.0f);
-        for (int hsel = 0; hsel < nhi; ++hsel) {
-          tmem_ld16(lane_addr + (uint32_t)(hsel * BN + cb * 16), u);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(u[j]));
+        for (int j = 0; j < 16; ++j) {
+          float a = __fadd_rn(__uint_as_float(v[j]) * (1.0f / 2048.0f), __uint_as_float(u0[j]));
+          if (nhi > 1) a = __fadd_rn(a, __uint_as_float(u1[j]));
+          if (nhi > 2) a = __fadd_rn(a, __uint_as_float(u2[j]));
+          acc[j] = a;
         }
         const int n0 = tn * BN + cb * 16;
-        if (row_ok && n0 < p.n_store) {
-          const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (m + p.row0) / p.stat_rows_per_group : 0;
+        if (row_ok && p.C16_hi && !p.C && n0 + 16 <= p.n_store) {       // interior block of an fp16-pair layer
+          switch (p.act) {
+            case EPI_RELU: store_pair_block<EPI_RELU>(p, acc, m, n0); break;
+            case EPI_TANH: store_pair_block<EPI_TANH>(p, acc, m, n0); break;
+            case EPI_GELU: store_pair_block<EPI_GELU>(p, acc, m, n0); break;
+            default: store_pair_block<EPI_NONE>(p, acc, m, n0); break;
+          }
+        } else if (row_ok && n0 < p.n_store) {
           float x[16];
+          const int smod = p.stat_mod ? p.stat_mod : 0x7fffffff;
+          int sn = p.stat_mod ? n0 % p.stat_mod : n0;                    // statistics column of output column n
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = n0 + j;
@@ -255,8 +321,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               if (p.bias) t += p.bias[n];
               t = epilogue_apply(t, p.act, 0.0f);
               if (p.std32) {
-                const int sn = p.stat_mod ? n % p.stat_mod : n;
                 t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + sn]), p.mean32[sg * p.stat_ld + sn]);
+                if (++sn == smod) sn = 0;
               }
             }
             x[j] = t;
