@@ -206,6 +206,7 @@ def run_gpu_arm(args):
     lr_d, mean_d, std_d = lr_h.to(dev), mean_h.to(dev), std_h.to(dev)
     handle = _capi.Handle.get(local)
     _capi.lib().kmpc_set_mpc_kernel({"lane": 2, "cta": 1, "warp": 0}[args.mpc_kernel])
+    _capi.lib().kmpc_set_gemm_fp16_pairs(1 if args.gemm == "fp16" else 0)
     B_total = B * world
 
     def step_device(timings=None):
@@ -281,7 +282,7 @@ def run_gpu_arm(args):
         fc_tflops = fpd * decisions_per_step_rank / (st_fc * 1e-3) / 1e12
         # fp32-accurate tensor rate of the fp16-pair kernel: three kind::f16 MMAs (hi.hi, lo.hi, hi.lo) per product,
         # fp16 dense rate = the measured bf16 rate
-        tensor_peak = bf16 / 3.0
+        tensor_peak = bf16 / 3.0 if args.gemm == "fp16" else bf16 / 2.0 / 3.0
         hbm_bytes_bt = (8 * N + 8 * H * N + 32) * decisions_per_step_rank
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         dominant = "backtest_kernel" if st_bt >= st_fc else "forecast_gemm_chain"
@@ -339,6 +340,7 @@ def main():
     ap.add_argument("--cpu-decisions", type=int, default=246, help="decisions per scenario in the bounded CPU sample")
     ap.add_argument("--cpu-scenarios", type=int, default=10, help="scenarios in the rank-0 cpu_baseline sample (~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default="fp16", choices=["fp16", "tf32"], help="forecast tensor-core kernel (diagnostics)")
     ap.add_argument("--mpc-kernel", default="lane", choices=["lane", "cta", "warp"], help="MPC kernel layout (diagnostics)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -137,6 +137,51 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Interior block (16 full columns, 16-byte aligned rows, no de-standardisation): bias / addend as vector loads,
+// activation resolved at compile time, C and its residual twin as float4 stores.  The per-element general path
+// below (branches per element) had made the epilogue the bottleneck of the whole GEMM (32 us of a 58 us tile).
+template <int ACT>
+__device__ __forceinline__ void store_block_fast(const Params& p, const float (&acc)[16], long long m, int n0) {
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = acc[j];
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) { const float4 b = b4[j4]; x[j4 * 4] += b.x; x[j4 * 4 + 1] += b.y; x[j4 * 4 + 2] += b.z; x[j4 * 4 + 3] += b.w; }
+  }
+  if (p.addend) {
+    const float4* a4 = reinterpret_cast<const float4*>(p.addend + m * p.ld_add + n0);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) { const float4 b = a4[j4]; x[j4 * 4] += b.x; x[j4 * 4 + 1] += b.y; x[j4 * 4 + 2] += b.z; x[j4 * 4 + 3] += b.w; }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = epilogue_apply(x[j], ACT, p.shrink_thr);
+  float4* crow = reinterpret_cast<float4*>(p.C + m * p.ldc + n0);
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) crow[j4] = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+  if (p.C_lo) {
+    float4* lrow = reinterpret_cast<float4*>(p.C_lo + m * p.ldc + n0);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      float lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float t = x[j4 * 4 + j]; lo[j] = t - __uint_as_float(__float_as_uint(t) & 0xffffe000u); }
+      lrow[j4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo, Params p) {
@@ -234,20 +279,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&tfull_bar[0], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      // vector path: rows of C / C_lo / addend 16-byte aligned, no de-standardisation
+      const bool fast_ok = !p.std32 && (p.ldc % 4 == 0) && ((((uintptr_t)p.C) & 15) == 0) &&
+                           (!p.C_lo || (((uintptr_t)p.C_lo) & 15) == 0) &&
+                           (!p.addend || ((p.ld_add % 4 == 0) && (((uintptr_t)p.addend) & 15) == 0)) &&
+                           (!p.bias || (((uintptr_t)p.bias) & 15) == 0);
 #pragma unroll 1
       for (int cb = 0; cb < BN / 16; ++cb) {
-        uint32_t v[16], u[16];
+        uint32_t v[16], u0[16], u1[16], u2[16];
         float acc[16];
-        tmem_ld16(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);          // lo products
+        tmem_ld16_nowait(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);    // lo products
+        tmem_ld16_nowait(lane_addr + (uint32_t)(0 * BN + cb * 16), u0);
+        if (nhi > 1) tmem_ld16_nowait(lane_addr + (uint32_t)(1 * BN + cb * 16), u1);
+        if (nhi > 2) tmem_ld16_nowait(lane_addr + (uint32_t)(2 * BN + cb * 16), u2);
+        tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-        for (int hsel = 0; hsel < nhi; ++hsel) {
-          tmem_ld16(lane_addr + (uint32_t)(hsel * BN + cb * 16), u);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(u[j]));
+        for (int j = 0; j < 16; ++j) {
+          float a = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(u0[j]));
+          if (nhi > 1) a = __fadd_rn(a, __uint_as_float(u1[j]));
+          if (nhi > 2) a = __fadd_rn(a, __uint_as_float(u2[j]));
+          acc[j] = a;
         }
         const int n0 = tn * BN + cb * 16;
-        if (row_ok && n0 < p.n_store) {
+        if (row_ok && fast_ok && n0 + 16 <= p.n_store) {
+          switch (p.act) {
+            case EPI_RELU: store_block_fast<EPI_RELU>(p, acc, m, n0); break;
+            case EPI_TANH: store_block_fast<EPI_TANH>(p, acc, m, n0); break;
+            case EPI_GELU: store_block_fast<EPI_GELU>(p, acc, m, n0); break;
+            case EPI_SHRINK: store_block_fast<EPI_SHRINK>(p, acc, m, n0); break;
+            default: store_block_fast<EPI_NONE>(p, acc, m, n0); break;
+          }
+        } else if (row_ok && n0 < p.n_store) {
           float* crow = p.C + m * p.ldc + n0;
           float* lrow = p.C_lo ? p.C_lo + m * p.ldc + n0 : nullptr;
           const float* arow = p.addend ? p.addend + m * p.ld_add + n0 : nullptr;
