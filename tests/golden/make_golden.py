@@ -10,6 +10,8 @@ small .npz files; large weights are regenerated from seeds by koopman_mpc_portfo
                        (model.py, backtest.py:85-121) for GenericKM (relu/id, tanh/ball, gelu + MLP decoder)
                        and LISTAKM (linear and MLP encoder); weights stored (tiny models)
   forecast_cfg1.npz    finance_sparse preset, TARGET_SIZE=128, N=10, d=20 (BASELINE config 1); weights from seed
+  dmd_small.npz        UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small env: fitted K,
+                       the forecasts handed to the MPC, history, metrics
   backtest_cfg1.npz    UNMODIFIED reference run_backtest + KoopmanMPCStrategy + calculate_metrics on config 1
                        with the substitute mpc module (tests/golden/_shims/mpc.py): history, metrics, every
                        MPC call's (w_cur, yhat, w_opt, value)
@@ -197,8 +199,42 @@ def gen_cfg1():
     print("buy&hold    ", bh_metrics)
 
 
+def gen_dmd():
+    """UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small synthetic env: the fitted K,
+    the forecasts it hands to the MPC at every step, the history and the metrics."""
+    import baselines as ref_baselines
+    N, d, H = 6, 4, 5
+    T = 700
+    frame = make_frame(21, T, N)
+    val_end = str(frame.index[T - 61].date())
+    train_end = str(frame.index[T - 61 - 100].date())
+    env, stats, (tr, va, te) = build_env(frame, train_end, val_end, d)
+    mpc_cfg = shim_mpc.MPCConfig(horizon=H, cost_coeff=1e-3, max_turnover=0.2)
+    bt_cfg = ref_backtest.BacktestConfig(initial_capital=1e4, horizon=H, cost_coeff=1e-3)
+    strat = ref_baselines.DMDStrategy(env.train_dataset.data, mpc_cfg)
+    shim_mpc.CALLS.clear()
+    df = ref_backtest.run_backtest(strat, env, bt_cfg, verbose=False)
+    metrics = ref_backtest.calculate_metrics(df)
+    calls = shim_mpc.CALLS
+    assert len(df) == len(calls) == len(env.test_dataset) - H
+    np.savez(
+        os.path.join(HERE, "dmd_small.npz"),
+        T=T, N=N, d=d, H=H, log_returns_seed=21, n_train_days=T - 61 - 100 + 1, n_val_days=100,
+        mean=stats.mean, std=stats.std, K=strat.K,
+        yhat=np.stack([c[1] for c in calls]).astype(np.float32),
+        w_cur=np.stack([c[0] for c in calls]), w_opt=np.stack([c[2] for c in calls]),
+        history=df[["portfolio_value", "return", "turnover", "cost"]].values.astype(np.float64),
+        metrics=np.array([metrics[k] for k in ("Sharpe Ratio", "Max Drawdown", "Avg Turnover", "Final Value", "Total Return")]),
+    )
+    print("dmd metrics", metrics, "K dtype", strat.K.dtype)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dmd":
+        gen_dmd()
+        sys.exit(0)
     gen_data_small()
     gen_forecasts()
     gen_cfg1()
+    gen_dmd()
     print("golden fixtures written to", HERE)
