@@ -102,6 +102,69 @@ class BatchedBacktester:
         return res
 
 
+def run_grid(models, n_assets: int, delay: int, log_returns, mean, std, lam_grid, tau_grid, *, row0: int = 0, rows: int = 252,
+             horizon: int = 5, bt_config: Optional[BacktestConfig] = None, allow_short: bool = False, device="cuda",
+             shard=None, want_history: bool = False):
+    """Sweep grid (BASELINE config 4): every (model, lambda, tau) combination is one backtest on ONE price path.
+
+    The forecast depends on (model, path, t) only, so it is computed once per model ([S, n_steps, H, N]) and the
+    S * L * T backtests share it through ``yhat_index``; lambda and tau are per-backtest arrays of the persistent
+    MPC kernel.  Backtest id = (s * L + l) * T + t.  ``shard = (rank, world)`` restricts the run to a contiguous
+    shard of ids (every rank holds all S forecast sets; no data-path communication, see gather_metrics).
+    Returns dict(metrics [n_local, 5] CUDA f64, ids (lo, hi), stats, history)."""
+    import torch
+    dev = torch.device(device)
+    bt = bt_config or BacktestConfig(horizon=horizon)
+    lr = torch.as_tensor(log_returns).to(dev, dtype=torch.float64).reshape(1, -1, n_assets).contiguous()
+    mean_d = torch.as_tensor(mean).to(dev, dtype=torch.float64).reshape(-1).contiguous()
+    std_d = torch.as_tensor(std).to(dev, dtype=torch.float64).reshape(-1).contiguous()
+    ns = (rows - 1) - bt.horizon
+    S, L, T = len(models), len(lam_grid), len(tau_grid)
+    n_total = S * L * T
+    lo, hi = shard_range(n_total, *shard) if shard is not None else (0, n_total)
+    yh, realized = [], None
+    for m in models:
+        eng = BatchedBacktester(m, n_assets, delay, MPCConfig(horizon=horizon), bt, device=dev)
+        z = eng._tensor("z", (1, lr.shape[1], pad4(n_assets)), torch.float32)
+        h = _capi.Handle.get(dev.index or 0)
+        sp = _capi.stream_ptr(dev.index or 0)
+        _capi.check(_capi.lib().kmpc_standardize(h.ptr, _capi.ptr(lr), _capi.ptr(mean_d), _capi.ptr(std_d), 0, 1, lr.shape[1],
+                                                n_assets, _capi.ptr(z), z.shape[2], sp))
+        if realized is None:
+            realized = torch.empty((1, rows, n_assets), dtype=torch.float32, device=dev)
+            _capi.check(_capi.lib().kmpc_current_returns(h.ptr, _capi.ptr(z), z.shape[2], _capi.ptr(mean_d), _capi.ptr(std_d), 0,
+                                                        1, lr.shape[1], n_assets, delay, row0, rows, _capi.ptr(realized), sp))
+        yh.append(m.forecast_series(z, mean_d, std_d, n_assets, delay, row0, 0, ns, horizon)[0].clone())
+    yhat = torch.stack(yh, dim=0)
+    ids = torch.arange(lo, hi, device=dev)
+    lam_t = torch.as_tensor(np.asarray(lam_grid, dtype=np.float64), device=dev)[(ids // T) % L]
+    tau_t = torch.as_tensor(np.asarray(tau_grid, dtype=np.float64), device=dev)[ids % T]
+    out = run_backtest_batched(yhat, realized, n_steps=ns, horizon=horizon, lam=lam_t, tau=tau_t,
+                               cost_coeff0=bt.cost_coeff, capital0=bt.initial_capital, rebalance_freq=bt.rebalance_freq,
+                               allow_short=allow_short, yhat_index=(ids // (L * T)).to(torch.int32),
+                               realized_index=torch.zeros_like(ids, dtype=torch.int32), B=hi - lo, want_history=want_history)
+    out["ids"] = (lo, hi)
+    out["yhat"] = yhat
+    return out
+
+
+def bootstrap_paths(hist_log_returns, n_paths: int, length: int, seed: int, device="cuda", offset: int = 0):
+    """Monte-Carlo stress paths (BASELINE config 5): iid row bootstrap of one historical block [T_hist, N].
+    Indices come from a Philox generator seeded with ``seed`` and advanced by ``offset`` paths, so that a rank can
+    regenerate exactly its own shard (no scatter).  Returns (log_returns [n_paths, length, N] f64 CUDA, idx int64)."""
+    import torch
+    dev = torch.device(device)
+    hist = torch.as_tensor(hist_log_returns).to(dev, dtype=torch.float64)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    # one draw per path keeps path p identical whatever the shard boundaries are
+    idx = torch.empty((n_paths, length), dtype=torch.int64, device=dev)
+    for p in range(n_paths):
+        g.manual_seed(int(seed) * 1_000_003 + offset + p)
+        idx[p] = torch.randint(0, hist.shape[0], (length,), generator=g, device=dev)
+    return hist[idx], idx
+
+
 def shard_range(n: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of n independent backtests for one rank."""
     per = (n + world - 1) // world

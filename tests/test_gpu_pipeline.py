@@ -130,3 +130,78 @@ def test_dmd_strategy_vs_reference_golden(golden):
     assert np.allclose([met[k] for k in bt.METRIC_KEYS], g["metrics"], rtol=2e-3, atol=2e-4)
     w = strat.rebalance(0, np.ones(N) / N, env)                         # single-step drop-in (baselines.py:147-187)
     assert np.abs(w - g["w_opt"][0, 0]).max() < 1e-4
+
+
+def test_sweep_grid_shares_forecasts_config4_shape():
+    """BASELINE config 4 in small: 2 weight sets x 3 lambdas x 3 taus on one price path; forecasts computed once per
+    weight set and shared through yhat_index; every grid cell equals its own oracle backtest; two shards cover the grid."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import engine, model as km, synthetic, backtest as bt
+    from oracle import backtest_oracle as bo, data_oracle as do, forecast_oracle as fo
+    N, d, H, rows, Z = 12, 6, 5, 30, 64
+    T = rows + d - 1
+    lr = synthetic.gbm_log_returns(77, T, N)
+    mean = lr.mean(axis=0); std = lr.std(axis=0, ddof=1)
+    sds, models = [], []
+    for s in range(2):
+        sd = synthetic.generic_km_weights(40 + s, N * d, [64, 64], Z)
+        m = km.make_model(km.model_config("GenericKM", Z, [64, 64], enc_bias=True), N * d)
+        m.load_state_dict(sd); sds.append(sd); models.append(m)
+    lam_grid = [1e-5, 1e-3, 1e-1]; tau_grid = [0.01, 0.2, 1.0]
+    out = engine.run_grid(models, N, d, lr, mean, std, lam_grid, tau_grid, rows=rows, horizon=H)
+    met = out["metrics"].cpu().numpy()
+    assert met.shape == (18, 5) and out["stats"].cpu().numpy()[:, 2].sum() == 0
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    emb = do.time_delay_embedding(do.standardize(lr, mean, std), d)
+    allr = do.destandardize(do.extract_current_returns(emb, N), mean, std)
+    ns = rows - 1 - H
+    yhat_gpu = out["yhat"].cpu().numpy()
+    for s in range(2):
+        want = fo.forecast(emb[:ns], sds[s], spec, H, N, mean, std)
+        rel = np.abs(yhat_gpu[s] - want).reshape(ns, -1).max(1) / np.abs(want).reshape(ns, -1).max(1)
+        assert rel.max() < 1e-5
+        for li in (0, 2):
+            for ti in (0, 1, 2):
+                rh, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat_gpu[s], lam_grid[li], tau_grid[ti]), allr, rows - 1, H)
+                mo_ = bo.calculate_metrics(np.asarray(rh))
+                b = (s * 3 + li) * 3 + ti
+                assert np.allclose(met[b], [mo_[k] for k in bo.METRIC_KEYS], rtol=1e-6, atol=1e-7), (s, li, ti)
+    # two shards of the grid reproduce the full run
+    a = engine.run_grid(models, N, d, lr, mean, std, lam_grid, tau_grid, rows=rows, horizon=H, shard=(0, 2))
+    b2 = engine.run_grid(models, N, d, lr, mean, std, lam_grid, tau_grid, rows=rows, horizon=H, shard=(1, 2))
+    assert a["ids"] == (0, 9) and b2["ids"] == (9, 18)
+    assert np.array_equal(np.vstack([a["metrics"].cpu().numpy(), b2["metrics"].cpu().numpy()]), met)
+
+
+def test_bootstrap_paths_config5_shape():
+    """BASELINE config 5 in small: 100 assets, bootstrap paths of one historical block; a rank regenerates exactly its
+    shard; a sampled path equals its own oracle backtest."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import engine, model as km, synthetic, backtest as bt
+    from oracle import backtest_oracle as bo, data_oracle as do, forecast_oracle as fo
+    N, d, H, rows, Z = 100, 5, 5, 24, 128
+    T = rows + d - 1
+    hist = synthetic.gbm_log_returns(5, 400, N)
+    mean = hist.mean(axis=0); std = hist.std(axis=0, ddof=1)
+    paths, idx = engine.bootstrap_paths(hist, 6, T, seed=1234)
+    p2, idx2 = engine.bootstrap_paths(hist, 3, T, seed=1234, offset=3)
+    assert torch.equal(idx[3:], idx2) and torch.equal(paths[3:], p2)
+    assert np.array_equal(paths.cpu().numpy(), hist[idx.cpu().numpy()])
+    sd = synthetic.generic_km_weights(50, N * d, [128, 128], Z)
+    m = km.make_model(km.model_config("GenericKM", Z, [128, 128], enc_bias=True), N * d)
+    m.load_state_dict(sd)
+    eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H), bt.BacktestConfig(horizon=H))
+    out = eng.run_device(paths, torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda(), 0, rows, want_history=True)
+    assert out["stats"].cpu().numpy()[:, 2].sum() == 0
+    yhat_gpu = out["yhat"].cpu().numpy(); hist_gpu = out["history"].cpu().numpy()
+    spec = fo.ModelSpec(kind="generic", act="relu", last_relu=False, norm_fn="id", dec_act="relu")
+    ns = rows - 1 - H
+    for b in (0, 5):
+        lrb = paths[b].cpu().numpy()
+        emb = do.time_delay_embedding(do.standardize(lrb, mean, std), d)
+        want = fo.forecast(emb[:ns], sd, spec, H, N, mean, std)
+        rel = np.abs(yhat_gpu[b] - want).reshape(ns, -1).max(1) / np.abs(want).reshape(ns, -1).max(1)
+        assert rel.max() < 1e-5
+        allr = do.destandardize(do.extract_current_returns(emb, N), mean, std)
+        rh, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat_gpu[b], 1e-3, 0.2), allr, rows - 1, H)
+        assert np.allclose(hist_gpu[b][:, 0], np.asarray(rh)[:, 0], rtol=1e-6)
