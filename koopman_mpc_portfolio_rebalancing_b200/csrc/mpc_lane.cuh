@@ -411,13 +411,13 @@ struct LaneIpm {
       if (en % KB != 0) flush_batch(en - en % KB, en % KB);
     }
 #undef KMPC_FLUSH_IF_FULL
-    sync();
   }
 
   // L D L' factorisation of K by warp 0: lane = row, row in registers, columns exchanged by shuffles.  False on a
   // non-positive pivot.
   __device__ __forceinline__ bool factor_b() {
     if (warp == 0) {
+      __syncwarp();                  // K was scattered by lanes of this warp (flush_batch); nobody else touches it
       const int nb = hc() ? 3 * H : 2 * H;
       const int r = (lane < NB) ? lane : NB - 1;
       if (lane < NB) {             // diagonal terms 1/beta_k = rho_k^2 and sc_k / zc_k, added in place (a lane-indexed
@@ -455,8 +455,8 @@ struct LaneIpm {
     return fact_ok_;
   }
 
-  // t (OFF_T) <- K^{-1} t by warp 0
-  __device__ __forceinline__ void k_solve_shared() {
+  // OFF_T <- K^{-1} t by warp 0; lane r < NB passes entry r of the right-hand side in t_in
+  __device__ __forceinline__ void k_solve_shared(double t_in) {
     if (warp == 0) {
       const int r = (lane < NB) ? lane : NB - 1;
       double Lr[NB], Lc[NB];
@@ -466,7 +466,7 @@ struct LaneIpm {
         Lc[j] = (j > lane && lane < NB) ? sm[OFF_K + j * NB + r] : 0.0;          // L[j][lane]
       }
       const double myinv = (lane < NB) ? sm[OFF_K + NB * NB + r] : 0.0;
-      double t = (lane < NB) ? sm[OFF_T + r] : 0.0;
+      double t = (lane < NB) ? t_in : 0.0;
 #pragma unroll
       for (int j = 0; j < NB; ++j) t = fma(-Lr[j], shfl_d(t, j), t);        // L y = t   (Lr[j] = 0 for j >= lane)
       t *= myinv;                                                              // D z = y
@@ -514,14 +514,13 @@ struct LaneIpm {
         v[2 * H + k] = hc() ? fma(gu[k], ie[k], -ph[k] * dd[k]) : 0.0;
       }
       tile_reduce<NB>(v);
+      double t = 0.0;
       if (tid < NB) {
-        double t = ptotal(tid);
+        t = ptotal(tid);
         if (tid >= H && tid < 2 * H) t += U(U_RP, tid - H);  // t[H+k] = sum dw0 - q, q = -rp
-        sm[OFF_T + tid] = t;
       }
+      k_solve_shared(t);
     }
-    sync();
-    k_solve_shared();
     sync();
     dnu = 0.0; dsc = 0.0; dzc = 0.0;
     if (tid < H) {                                           // stage scalars stay with their owner threads

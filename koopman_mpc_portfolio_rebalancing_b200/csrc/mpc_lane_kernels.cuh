@@ -12,6 +12,9 @@
 #else
 #define KMPC_LANE_BT_ATTR(threads) __launch_bounds__(threads, 1)
 #endif
+#ifndef KMPC_LANE_SYNC_EVERY
+#define KMPC_LANE_SYNC_EVERY 4    // block barrier every 4th trip (measured 1: 215 ms, 2: 212, 4: 208, 8: 209, 16: 215, 64: 231)
+#endif
 #ifndef KMPC_LANE_MINB
 #define KMPC_LANE_MINB 1      // resident blocks per SM the register allocation is sized for (0/1 = no cap)
 #endif
@@ -99,15 +102,12 @@ backtest_lane_kernel(BacktestArgs A, int want) {
   extern __shared__ double smem[];
   if (want >= 0 && *A.fix_flag != want) return;
   __shared__ int next_b[P];
-  __shared__ int n_idle;
   __shared__ SlotBook books[P];
   const int slot = __shfl_sync(kFull, (int)threadIdx.x / (32 * G), 0);
   Ipm s;
   s.bind(smem + (size_t)slot * Ipm::SMEM_DOUBLES, A.N, slot);
   const int N = A.N;
   const IpmOptions& opt = A.opt;
-  if (threadIdx.x == 0) n_idle = 0;
-  __syncthreads();
   // ---- per-thread state of the slot's current backtest ----------------------------------------------------------
   int b = 0, t = 0;
   double wc = 0.0;                                 // my asset's current weight
@@ -129,13 +129,11 @@ backtest_lane_kernel(BacktestArgs A, int want) {
     return true;
   };
   bool active = (A.n_steps > 0) ? fetch() : false;
-  if (!active && s.tid == 0) atomicAdd(&n_idle, 1);
   bool need_start = true;
   int st = -1;
   __syncthreads();
 #pragma unroll 1
-  for (;;) {
-    if (uni(n_idle >= P)) break;
+  for (unsigned trip = 0;; ++trip) {
     if (uni(active)) {
 #pragma unroll 1
       for (;;) {
@@ -210,16 +208,18 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         if (uni(last)) {
           if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
           active = fetch();
-          if (!active) {
-            if (s.tid == 0) atomicAdd(&n_idle, 1);
-            break;
-          }
+          if (!active) break;
         }
       }
     }
-    // One block barrier per trip keeps the slots within a phase of each other (measured: further barriers between
-    // the phases change nothing, 273-278 ms; staggering the slots half a trip apart is slower, 357 ms).
-    __syncthreads();
+    // A block barrier every few trips keeps the slots within a phase or two of each other, which is what the
+    // instruction cache needs; a barrier per trip makes every slot wait for the one that books a decision (19 % of
+    // all stall samples).  Measured: barriers between the phases change nothing, staggering the slots half a trip
+    // apart is slower (357 vs 273 ms).
+    // (the barrier doubles as the exit vote: all slots out of work)
+    if ((trip % KMPC_LANE_SYNC_EVERY) == 0) {
+      if (__syncthreads_and(!active)) break;
+    }
     const bool act_u = uni(active);                            // provably warp-uniform (see uni())
     bool ok = false;
     if (act_u) {
