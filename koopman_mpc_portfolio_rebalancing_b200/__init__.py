@@ -3,8 +3,8 @@ hot path of yli421/koopman-mpc-portfolio-rebalancing.
 
 Modules mirror the reference's for this path: ``mpc`` (MPCConfig, solve_mpc_log_utility), ``backtest``
 (BacktestConfig, Strategy, KoopmanMPCStrategy, run_backtest, calculate_metrics), ``model`` (GenericKM / SparseKM /
-LISTAKM forward path), ``data_finance`` (embedding, splits, FinanceDataset, FinanceEnv), plus ``engine`` (the
-batch-resident data-parallel form).  All compute goes through libkmpc.so (include/kmpc.h); nothing here imports
+LISTAKM forward path), ``data_finance`` (embedding, splits, FinanceDataset, FinanceEnv), ``baselines`` (DMDStrategy), ``evaluation`` (batched rollout generators), plus ``engine`` (the
+batch-resident data-parallel form: scenario batches, sweep grids, bootstrap paths).  All compute goes through libkmpc.so (include/kmpc.h); nothing here imports
 ``oracle/`` and there is no CPU fallback.
 """
-__all__ = ["mpc", "backtest", "model", "data_finance", "engine", "synthetic"]
+__all__ = ["mpc", "backtest", "baselines", "evaluation", "model", "data_finance", "engine", "synthetic"]

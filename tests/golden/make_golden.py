@@ -10,6 +10,7 @@ small .npz files; large weights are regenerated from seeds by koopman_mpc_portfo
                        (model.py, backtest.py:85-121) for GenericKM (relu/id, tanh/ball, gelu + MLP decoder)
                        and LISTAKM (linear and MLP encoder); weights stored (tiny models)
   forecast_cfg1.npz    finance_sparse preset, TARGET_SIZE=128, N=10, d=20 (BASELINE config 1); weights from seed
+  rollouts_small.npz   evaluation.rollout_{no,every_step,periodic}_reencode (evaluation.py:44-134) on two tiny models
   dmd_small.npz        UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small env: fitted K,
                        the forecasts handed to the MPC, history, metrics
   backtest_cfg1.npz    UNMODIFIED reference run_backtest + KoopmanMPCStrategy + calculate_metrics on config 1
@@ -199,6 +200,30 @@ def gen_cfg1():
     print("buy&hold    ", bh_metrics)
 
 
+def gen_rollouts():
+    """reference evaluation.rollout_no_reencode / rollout_every_step_reencode / rollout_periodic_reencode
+    (evaluation.py:44-134) on two of the tiny forecast models (weights already stored in forecast_*.npz)."""
+    import evaluation as ref_eval
+    out = {}
+    for name, preset in (("generic_small", "finance_sparse"), ("lista_linear", "lista")):
+        g = np.load(os.path.join(HERE, f"forecast_{name}.npz"))
+        sd = {k[4:]: g[k] for k in g.files if k.startswith("sd::")}
+        cfg = ref_config.get_config(preset)
+        if name == "generic_small":
+            cfg.MODEL.TARGET_SIZE = 8; cfg.MODEL.ENCODER.LAYERS = [16, 16]
+        else:
+            cfg.MODEL.TARGET_SIZE = 16
+            cfg.MODEL.ENCODER.LISTA.L = float(np.load(os.path.join(HERE, "forecast_lista_linear_meta.npz"))["L"])
+        model = ref_model.make_model(cfg, g["obs"].shape[1])
+        model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+        x0 = torch.from_numpy(g["obs"])
+        out[f"{name}::no_reencode"] = ref_eval.rollout_no_reencode(model, x0, 6).numpy()
+        out[f"{name}::every_step"] = ref_eval.rollout_every_step_reencode(model, x0, 6).numpy()
+        out[f"{name}::periodic2"] = ref_eval.rollout_periodic_reencode(model, x0, 6, 2).numpy()
+    np.savez(os.path.join(HERE, "rollouts_small.npz"), **out)
+    print("rollouts", {k: v.shape for k, v in out.items()})
+
+
 def gen_dmd():
     """UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small synthetic env: the fitted K,
     the forecasts it hands to the MPC at every step, the history and the metrics."""
@@ -233,8 +258,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dmd":
         gen_dmd()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rollouts":
+        gen_rollouts()
+        sys.exit(0)
     gen_data_small()
     gen_forecasts()
     gen_cfg1()
     gen_dmd()
+    gen_rollouts()
     print("golden fixtures written to", HERE)

@@ -245,3 +245,26 @@ def test_fp16_pair_chain_falls_back_when_values_leave_the_fp16_range():
         want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
         assert np.all(np.isfinite(y[b]))
         assert rowwise_rel(y[b], want) < FORECAST_RTOL
+
+
+@pytest.mark.parametrize("name", ["generic_small", "lista_linear"])
+def test_rollout_generators_vs_reference(golden, name):
+    """evaluation.rollout_{no,every_step,periodic}_reencode (evaluation.py:44-134) against the reference's outputs"""
+    from koopman_mpc_portfolio_rebalancing_b200 import evaluation as ev
+    g = golden(f"forecast_{name}.npz")
+    r = golden("rollouts_small.npz")
+    meta = golden(f"forecast_{name}_meta.npz") if name.startswith("lista") else None
+    m = build(name, g, meta)
+    m.load_state_dict(sd_from_npz(g))
+    import torch
+    x0 = torch.from_numpy(g["obs"]).cuda()
+    got = {"no_reencode": ev.rollout_no_reencode(m, x0, 6), "every_step": ev.rollout_every_step_reencode(m, x0, 6),
+           "periodic2": ev.rollout_periodic_reencode(m, x0, 6, 2)}
+    for k, v in got.items():
+        want = r[f"{name}::{k}"]
+        v = v.cpu().numpy()
+        assert v.shape == want.shape
+        for h in range(6):
+            assert rowwise_rel(v[h], want[h]) < FORECAST_RTOL, (k, h)
+    with pytest.raises(ValueError):
+        ev.rollout_periodic_reencode(m, x0, 3, 0)
