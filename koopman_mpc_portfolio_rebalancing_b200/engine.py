@@ -165,6 +165,48 @@ def bootstrap_paths(hist_log_returns, n_paths: int, length: int, seed: int, devi
     return hist[idx], idx
 
 
+def metrics_frame(metrics, index=None):
+    """[B,5] metric rows (device or host) -> DataFrame with the reference's column names (calculate_metrics,
+    backtest.py:243-249; the layout of full_comparison_metrics.csv, run_experiment.py:133-137, one row per backtest)."""
+    import pandas as pd
+    from .backtest import METRIC_KEYS
+    m = metrics.detach().cpu().numpy() if hasattr(metrics, "detach") else np.asarray(metrics)
+    return pd.DataFrame(m, columns=list(METRIC_KEYS), index=index)
+
+
+def history_frames(history, dates=None, rebalance_freq: int = 1):
+    """[B, n_hist, 4] histories -> one DataFrame per backtest with the columns of run_backtest (backtest.py:211-219):
+    date, portfolio_value, return, turnover, cost."""
+    import pandas as pd
+    from .backtest import HISTORY_COLS
+    h = history.detach().cpu().numpy() if hasattr(history, "detach") else np.asarray(history)
+    out = []
+    for b in range(h.shape[0]):
+        df = pd.DataFrame(h[b], columns=list(HISTORY_COLS))
+        if dates is not None:
+            df.insert(0, "date", [dates[t] for t in range(0, h.shape[1] * rebalance_freq, rebalance_freq)])
+        out.append(df)
+    return out
+
+
+def write_results(path: str, metrics, history=None, ids=None):
+    """Columnar dump of a batch for 10^4-10^6 backtests: metrics (and, optionally, the per-step history in long form)
+    as parquet through pyarrow."""
+    import pandas as pd
+    mf = metrics_frame(metrics)
+    mf.insert(0, "backtest", np.arange(len(mf)) if ids is None else np.asarray(ids))
+    mf.to_parquet(path, index=False)
+    if history is not None:
+        from .backtest import HISTORY_COLS
+        h = history.detach().cpu().numpy() if hasattr(history, "detach") else np.asarray(history)
+        B, n, _ = h.shape
+        long = pd.DataFrame(h.reshape(B * n, 4), columns=list(HISTORY_COLS))
+        long.insert(0, "step", np.tile(np.arange(n), B))
+        long.insert(0, "backtest", np.repeat(mf["backtest"].values, n))
+        long.to_parquet(path.replace(".parquet", "") + ".history.parquet", index=False)
+    return path
+
+
 def shard_range(n: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of n independent backtests for one rank."""
     per = (n + world - 1) // world

@@ -85,3 +85,22 @@ def test_shard_range_covers_everything():
             lo, hi = shard_range(n, r, w)
             seen += list(range(lo, hi))
         assert seen == list(range(n))
+
+
+def test_result_frames_and_parquet(tmp_path):
+    import numpy as np
+    """result formats of the batched engine: reference column names, parquet round trip (host-only logic)"""
+    import pandas as pd
+    from koopman_mpc_portfolio_rebalancing_b200 import engine, backtest as bt
+    rng = np.random.default_rng(0)
+    met = rng.standard_normal((7, 5)); hist = rng.standard_normal((7, 4, 4))
+    mf = engine.metrics_frame(met)
+    assert list(mf.columns) == ["Sharpe Ratio", "Max Drawdown", "Avg Turnover", "Final Value", "Total Return"] == list(bt.METRIC_KEYS)
+    hf = engine.history_frames(hist, dates=list(pd.bdate_range("2020-01-01", periods=8)), rebalance_freq=2)
+    assert len(hf) == 7 and list(hf[0].columns) == ["date", "portfolio_value", "return", "turnover", "cost"]
+    assert hf[0]["date"].iloc[1] == pd.bdate_range("2020-01-01", periods=8)[2]
+    p = engine.write_results(str(tmp_path / "out.parquet"), met, hist, ids=np.arange(10, 17))
+    back = pd.read_parquet(p)
+    assert np.array_equal(back["backtest"].values, np.arange(10, 17)) and np.allclose(back[list(bt.METRIC_KEYS)].values, met)
+    long = pd.read_parquet(str(tmp_path / "out.history.parquet"))
+    assert len(long) == 28 and np.allclose(long[long.backtest == 12][list(bt.HISTORY_COLS)].values, hist[2])
