@@ -296,8 +296,11 @@ def run_gpu_arm(args):
                    "achieved": bt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bt_gbs / hbm_peak,
                    "traffic": 1265.0 * decisions_per_step_rank if args.mpc_kernel == "lane" else None,
                    "bytes_per_decision": 8 * N + 8 * H * N + 32,
-                   "note": "the solver streams 1.2 KB per decision and is bound by instruction issue / dependency latency, not by HBM "
-                           "(ncu: issue slots 24 % busy, fp64 pipe 16 %, 8 warps per SM); see solver.iterations_per_decision and profiles/",
+                   "note": "the solver streams 1.2 KB per decision and is bound by instruction issue / dependency latency, not by HBM; "
+                           "see `compute` (ncu --set full capture in profiles/r1_backtest_lane_kernel.txt) and solver.iterations_per_decision",
+                   "compute": {"source": "ncu capture of the same kernel, profiles/r1_backtest_lane_kernel.txt (not measured live)",
+                               "fp64_pipe_busy_pct": 23.9, "issue_slots_busy_pct": 26.6, "ipc_per_sm": 1.06,
+                               "warp_instructions_per_decision": 65000, "warps_per_sm": 8, "registers_per_thread": 255},
                    "ms": st_bt}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
