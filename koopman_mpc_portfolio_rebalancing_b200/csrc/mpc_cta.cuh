@@ -424,7 +424,7 @@ struct CtaIpm {
       nu = mx + opt.dual_init;
       zc = has_c ? zeta0 : 0.0;
       zw = valid ? (-R / rho + nu) : 0.0;
-      zp = has_u ? 0.5 * (lam + zeta0) : 0.0;
+      zp = has_u ? 0.5 * fmax(lam + zeta0, opt.dual_init) : 0.0;   // floor: see oracle
       zq = zp;
     } else {
       nu = 1.0; zc = has_c ? opt.mu0 / sc : 0.0;
@@ -502,7 +502,7 @@ struct CtaIpm {
         }
       }
     }
-    if (status != ST_OPTIMAL && isfinite(kkt[1] + kkt[2]) && kkt[0] < 1e-8 && kkt[1] < 1e-6 && kkt[2] < 1e-8)
+    if (status != ST_OPTIMAL && isfinite(kkt[1] + kkt[2]) && kkt[0] < kLoosePres && kkt[1] < kLooseDres && kkt[2] < kLooseGap)
       status = ST_INACCURATE;
     if (status == ST_FAILED) w = w0;
     return status;

@@ -653,7 +653,7 @@ struct LaneIpm {
         const double ir = 1.0 / rho0[k];
         nu_k = mxR[k] * ir + opt.dual_init;
         zw[k] = valid ? fma(-R[k], ir, nu_k) : 0.0;
-        zp[k] = hu() ? 0.5 * (lam + zeta0) : 0.0;
+        zp[k] = hu() ? 0.5 * fmax(lam + zeta0, opt.dual_init) : 0.0;   // floor for the uncapped case: see oracle
         zq[k] = zp[k];
         if (tid == 0) U(U_ZC, k) = hc() ? zeta0 : 0.0;
       } else {
@@ -673,7 +673,7 @@ struct LaneIpm {
 
   // final status of a solve that left the iteration without meeting the tolerances (or never started)
   __device__ __forceinline__ int finish(int status) {
-    if (status == ST_FAILED && isfinite(kkt_[1] + kkt_[2]) && kkt_[0] < 1e-8 && kkt_[1] < 1e-6 && kkt_[2] < 1e-8)
+    if (status == ST_FAILED && isfinite(kkt_[1] + kkt_[2]) && kkt_[0] < kLoosePres && kkt_[1] < kLooseDres && kkt_[2] < kLooseGap)
       status = ST_INACCURATE;
     if (status >= ST_FAILED) {
 #pragma unroll

@@ -39,6 +39,9 @@ from __future__ import annotations
 
 import numpy as np
 
+# loose acceptance ("optimal_inaccurate") of an iterate that could not be pushed to the tolerances; same constants as
+# csrc/mpc_ipm.cuh (kLoosePres / kLooseDres / kLooseGap), see the comment there
+LOOSE_PRES, LOOSE_DRES, LOOSE_GAP = 1e-8, 1e-4, 1e-7
 STATUS_OPTIMAL = 0
 STATUS_INACCURATE = 1
 STATUS_MAXITER = 2
@@ -414,7 +417,9 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
         zeta0 = dual_init if has_c else 0.0
         if has_c: zc = np.full(H, zeta0)
         if has_u:
-            zp = np.full((H, N), 0.5 * (lam + zeta0)) if (lam + zeta0) > 0 else zp
+            # without a cap (zeta0 = 0) and a tiny lam the u-duals would start 1e4 x off-centre and collapse to zero
+            # (dual residual stuck at lam); floor them at the level the cap dual gives otherwise
+            zp = np.full((H, N), 0.5 * max(lam + zeta0, dual_init))
             zq = zp.copy()
         rho0 = (w * R).sum(axis=1)
         gw0 = -R / rho0[:, None]
@@ -605,7 +610,8 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
             sc_ = sc_ + a_ * dsc; zc = zc + b_ * dzc
     # not converged (iteration cap, numerical breakdown): accept the *current* iterate if it meets the loose
     # tolerances ("optimal_inaccurate", mpc.py:113), else fall back to holding the weights (mpc.py:113-115)
-    if status != STATUS_OPTIMAL and np.isfinite(res[1] + res[2]) and res[0] < 1e-8 and res[1] < 1e-6 and res[2] < 1e-8:
+    if status != STATUS_OPTIMAL and np.isfinite(res[1] + res[2]) and res[0] < LOOSE_PRES and res[1] < LOOSE_DRES \
+            and res[2] < LOOSE_GAP:
         status = STATUS_INACCURATE
     return _finish(w.copy(), w_cur, R, lam, status, it, res, H)
 

@@ -156,3 +156,23 @@ def test_large_shapes_lane_layout(N, H, mpc_kernel_layout):
         assert np.abs(W[p] - ref.w).max() < W_ATOL
         turn = np.abs(np.diff(np.vstack([w0[p], W[p]]), axis=0)).sum(axis=1)
         assert turn.max() <= 0.2 + 1e-7
+
+
+def test_uncapped_small_lambda_converges():
+    """max_turnover <= 0 means no cap (mpc.py:94): with a tiny cost_coeff the u-duals of the dual-feasible start
+    used to collapse (dual residual stuck at lam, 12 % of such instances failed).  All must reach the oracle optimum."""
+    torch, mpc, mo = _mods()
+    rng = np.random.default_rng(404)
+    P, N, H = 40, 50, 3
+    w0 = np.stack([rng.dirichlet(np.ones(N) * 0.5) for _ in range(P)])
+    y = (3e-4 + rng.standard_normal((P, H, N)) * 0.01).astype(np.float32)
+    lam = 10 ** rng.uniform(-5, -3, P); tau = np.zeros(P)
+    out = mpc.solve_mpc_batch(torch.from_numpy(w0).cuda(), torch.from_numpy(y).cuda(),
+                              lam=torch.from_numpy(lam).cuda(), tau=torch.from_numpy(tau).cuda())
+    st = out["status"].cpu().numpy(); val = out["value"].cpu().numpy(); its = out["iterations"].cpu().numpy()
+    assert (st == 0).all(), (st, its)
+    for p in range(0, P, 4):
+        ref = mo.solve_dense(w0[p], y[p], float(lam[p]), 0.0)
+        assert ref.status == 0
+        assert abs(val[p] - ref.value) <= OBJ_RTOL * max(abs(ref.value), OBJ_FLOOR)
+    assert its.mean() < 16
