@@ -187,6 +187,24 @@ int kmpc_mpc_solve_host(kmpc_handle* h, const void* yhat_host, int yhat_is_f64, 
                         double* obj_host, double* kkt_host, int32_t* status_host, int32_t* iters_host);
 
 /* ---------------------------------------------------------------------------------------------
+ * Mean-variance MPC — replaces mpc.solve_mpc_mean_variance (mpc.py:119-184; used by MarkowitzStrategy,
+ * baselines.py:24-106, with H = 1)
+ * ------------------------------------------------------------------------------------------- */
+
+/* P independent problems:  max sum_t [ w_t.mu_t - gamma w_t' Sigma w_t ] - lam sum_t ||w_t - w_{t-1}||_1,
+ * sum(w_t) = 1, w_t >= 0 unless allow_short, no turnover cap.  mu [P,H,N] fp64, sigma [N,N] shared or [P,N,N]
+ * (sigma_per_problem != 0), w_cur [P,N].  Outputs as kmpc_mpc_solve; on failure w_out = tile(w_cur), obj = NaN
+ * (mpc.py:179-180).  The dense Newton block must fit one SM: H * N <= 160, else KMPC_E_UNSUPPORTED. */
+int kmpc_mv_supported(int H, int N);
+int kmpc_mpc_mean_variance(kmpc_handle* h, const double* mu, const double* sigma, int sigma_per_problem, const double* w_cur,
+                           double gamma, double lam, int allow_short, int P, int H, int N, double* w_out, double* obj,
+                           double* kkt, int32_t* status, int32_t* iters, void* stream);
+/* Same, one problem, HOST buffers (the drop-in used by the Python shim). */
+int kmpc_mpc_mean_variance_host(kmpc_handle* h, const double* mu_host, const double* sigma_host, const double* w_cur_host,
+                                double gamma, double lam, int allow_short, int H, int N, double* w_out_host, double* obj_host,
+                                double* kkt_host, int32_t* status_host, int32_t* iters_host);
+
+/* ---------------------------------------------------------------------------------------------
  * Backtest — replaces run_backtest's step loop + calculate_metrics (backtest.py:133-249)
  * ------------------------------------------------------------------------------------------- */
 

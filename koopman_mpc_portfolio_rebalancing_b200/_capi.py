@@ -74,6 +74,11 @@ SIGNATURES = {
     "kmpc_debug_gemm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
     "kmpc_mpc_solve": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                  vp, vp, vp, vp, vp, vp]),
+    "kmpc_mv_supported": (C.c_int, [C.c_int, C.c_int]),
+    "kmpc_mpc_mean_variance": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         vp, vp, vp, vp, vp, vp]),
+    "kmpc_mpc_mean_variance_host": (C.c_int, [vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                              vp, vp, vp, vp, vp]),
     "kmpc_mpc_solve_host": (C.c_int, [vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                       vp, vp, vp, vp, vp]),
     "kmpc_backtest_run": (C.c_int, [vp, C.POINTER(BacktestDesc), vp]),

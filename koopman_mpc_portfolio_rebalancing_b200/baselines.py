@@ -8,8 +8,10 @@ identity encoder / decoder and ``kmat = K^T`` (row-vector convention ``z_{k+1} =
 read-out ``yhat_k = y_t . (K^{k+1})[:N]^T`` evaluated by the tcgen05 GEMM for all steps at once, and the
 persistent MPC + portfolio kernel behind ``run_backtest``.
 
-``MarkowitzStrategy`` / ``solve_mpc_mean_variance`` (baselines.py:24-106, mpc.py:119-184) use a quadratic stage cost
-and are not built yet.
+``MarkowitzStrategy`` (baselines.py:24-106): rolling-window mean / covariance estimated on the host exactly as the
+reference does (float32 ``np.mean``, ``np.cov`` + 1e-6 I), then ``solve_mpc_mean_variance`` with H = 1 — the fp64
+dense interior-point kernel ``csrc/mpc_mv.cu``.  It decides one step at a time through the generic ``run_backtest``
+loop, like in the reference.
 """
 from __future__ import annotations
 
@@ -17,7 +19,8 @@ import numpy as np
 
 from .backtest import KoopmanMPCStrategy
 from .model import make_model, model_config
-from .mpc import MPCConfig
+from .backtest import Strategy
+from .mpc import MPCConfig, solve_mpc_mean_variance
 
 
 class DMDStrategy(KoopmanMPCStrategy):
@@ -44,3 +47,26 @@ class DMDStrategy(KoopmanMPCStrategy):
         X = data[:-1].T
         X_prime = data[1:].T
         return X_prime @ pinv(X)
+
+
+class MarkowitzStrategy(Strategy):
+    """Classic mean-variance optimisation on rolling-window estimates (baselines.py:24-106)."""
+
+    def __init__(self, risk_aversion: float = 1.0, cost_coeff: float = 0.001, allow_short: bool = False):
+        self.risk_aversion = risk_aversion
+        self.cost_coeff = cost_coeff
+        self.allow_short = allow_short
+        self.mpc_config = MPCConfig(horizon=1, gamma=risk_aversion, cost_coeff=cost_coeff, allow_short=allow_short,
+                                    solver="ECOS")
+
+    def rebalance(self, t, current_weights, env, lookback_window: int = 60) -> np.ndarray:
+        past_data = env.test_dataset.data[:t + 1]
+        past_returns = env.destandardize_returns(env.extract_current_returns(past_data)).cpu().numpy()
+        if len(past_returns) < 5:                      # baselines.py:72-74
+            return current_weights
+        window = past_returns[-lookback_window:]
+        mu = np.mean(window, axis=0)
+        sigma = np.cov(window, rowvar=False)
+        sigma += np.eye(len(mu)) * 1e-6
+        w_opt, _ = solve_mpc_mean_variance(current_weights, mu.reshape(1, -1), sigma, self.mpc_config)
+        return w_opt[0]

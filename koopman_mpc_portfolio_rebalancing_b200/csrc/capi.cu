@@ -176,6 +176,56 @@ int kmpc_mpc_solve_host(kmpc_handle* h, const void* yhat_host, int yhat_is_f64, 
   return rc;
 }
 
+int kmpc_mv_supported(int H, int N) { return kmpc::mv_supported(H, N); }
+
+int kmpc_mpc_mean_variance(kmpc_handle* h, const double* mu, const double* sigma, int sigma_per_problem, const double* w_cur,
+                           double gamma, double lam, int allow_short, int P, int H, int N, double* w_out, double* obj,
+                           double* kkt, int32_t* status, int32_t* iters, void* stream) {
+  if (!h || !mu || !sigma || !w_cur || !w_out) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance: NULL argument");
+  if (P <= 0 || H <= 0 || N <= 0 || !(gamma >= 0.0) || !(lam >= 0.0)) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance: bad argument");
+  if (!kmpc::mv_supported(H, N))
+    return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_mean_variance: H*N = %d exceeds 160 (the dense Newton block must fit one SM)", H * N);
+  CK(cudaSetDevice(h->device));
+  int rc = kmpc::launch_mpc_mv(mu, sigma, sigma_per_problem ? (long long)N * N : 0, w_cur, gamma, lam, allow_short, P, H, N, w_out,
+                               obj, kkt, status, iters, h->sm_count, (cudaStream_t)stream);
+  h->launches++;
+  if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_mean_variance: unsupported shape");
+  if (rc) return kmpc_fail_cuda((cudaError_t)rc, "mpc_mv_kernel");
+  return KMPC_OK;
+}
+
+int kmpc_mpc_mean_variance_host(kmpc_handle* h, const double* mu_host, const double* sigma_host, const double* w_cur_host,
+                                double gamma, double lam, int allow_short, int H, int N, double* w_out_host, double* obj_host,
+                                double* kkt_host, int32_t* status_host, int32_t* iters_host) {
+  if (!h || !mu_host || !sigma_host || !w_cur_host || !w_out_host) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance_host: NULL argument");
+  if (H <= 0 || N <= 0) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance_host: bad shape");
+  CK(cudaSetDevice(h->device));
+  const size_t nw = (size_t)H * N;
+  const size_t doubles = nw + (size_t)N * N + N + nw + 1 + 3;
+  char* buf = nullptr;
+  CK(cudaMalloc(&buf, doubles * sizeof(double) + 2 * sizeof(int32_t) + 64));
+  double* d_mu = (double*)buf; double* d_sig = d_mu + nw; double* d_wc = d_sig + (size_t)N * N; double* d_w = d_wc + N;
+  double* d_obj = d_w + nw; double* d_kkt = d_obj + 1; int32_t* d_st = (int32_t*)(d_kkt + 3); int32_t* d_it = d_st + 1;
+  cudaError_t e;
+  if ((e = cudaMemcpy(d_mu, mu_host, nw * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_sig, sigma_host, (size_t)N * N * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_wc, w_cur_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    cudaFree(buf);
+    return kmpc_fail_cuda(e, "H2D");
+  }
+  int rc = kmpc_mpc_mean_variance(h, d_mu, d_sig, 0, d_wc, gamma, lam, allow_short, 1, H, N, d_w, d_obj, d_kkt, d_st, d_it, nullptr);
+  if (rc == KMPC_OK) {
+    e = cudaMemcpy(w_out_host, d_w, nw * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && obj_host) e = cudaMemcpy(obj_host, d_obj, sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && kkt_host) e = cudaMemcpy(kkt_host, d_kkt, 3 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && status_host) e = cudaMemcpy(status_host, d_st, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && iters_host) e = cudaMemcpy(iters_host, d_it, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = kmpc_fail_cuda(e, "D2H");
+  }
+  cudaFree(buf);
+  return rc;
+}
+
 int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream) {
   if (!h || !D) return fail(KMPC_E_INVALID, "kmpc_backtest_run: NULL argument");
   if (!D->yhat || !D->realized || !D->metrics) return fail(KMPC_E_INVALID, "kmpc_backtest_run: yhat/realized/metrics NULL");

@@ -49,6 +49,10 @@ int dispatch_backtest(const BacktestArgs& A, int H, int sm_count, cudaStream_t s
 
 namespace kmpc {
 int mpc_variant_supported(int H, int N);
+int mv_supported(int H, int N);
+int launch_mpc_mv(const double* mu, const double* sigma, long long sigma_stride, const double* w_cur, double gamma, double lam,
+                  int allow_short, int P, int H, int N, double* w_out, double* obj, double* kkt, int* status, int* iters,
+                  int sm_count, cudaStream_t st);
 void set_mpc_mode(int mode);
 int get_mpc_mode();
 int launch_standardize(const double* y, const double* mean, const double* sd, int spp, int B, int T, int N, float* out,

@@ -55,6 +55,52 @@ def solve_mpc_log_utility(current_weights: np.ndarray, predicted_log_returns: np
     return w, {"status": status, "value": float(obj[0]), "kkt": tuple(kkt), "iterations": int(it[0])}
 
 
+def solve_mpc_mean_variance(current_weights: np.ndarray, predicted_log_returns: np.ndarray, cov_matrix: np.ndarray,
+                            config: MPCConfig, device: int = 0) -> Tuple[np.ndarray, Dict]:
+    """maximize sum_t [ w_t . mu_t - gamma * w_t' Sigma w_t - cost * ||w_t - w_{t-1}||_1 ]  s.t. sum(w_t)=1, w_t>=0
+    unless allow_short; no turnover cap (mpc.py:119-184).  Returns (optimal_weights [H,N], {"status", "value"}); a
+    non-optimal status returns tile(current_weights) and {"status"} only, like the reference (mpc.py:179-180)."""
+    mu = np.ascontiguousarray(predicted_log_returns, dtype=np.float64)
+    if mu.ndim != 2:
+        raise ValueError("predicted_log_returns must be [horizon, n_assets]")
+    H, N = mu.shape
+    sig = np.ascontiguousarray(cov_matrix, dtype=np.float64)
+    if sig.shape != (N, N):
+        raise ValueError("cov_matrix must be [n_assets, n_assets]")
+    w0 = np.ascontiguousarray(current_weights, dtype=np.float64).reshape(N)
+    w = np.empty((H, N), dtype=np.float64)
+    obj = np.empty(1, dtype=np.float64); kkt = np.empty(3, dtype=np.float64)
+    st = np.empty(1, dtype=np.int32); it = np.empty(1, dtype=np.int32)
+    h = _capi.Handle.get(device)
+    _capi.check(_capi.lib().kmpc_mpc_mean_variance_host(
+        h.ptr, _capi.ptr(mu), _capi.ptr(sig), _capi.ptr(w0), float(config.gamma), float(config.cost_coeff),
+        int(bool(config.allow_short)), H, N, _capi.ptr(w), _capi.ptr(obj), _capi.ptr(kkt), _capi.ptr(st), _capi.ptr(it)))
+    status = STATUS_STRINGS[int(st[0])]
+    if status not in ("optimal", "optimal_inaccurate"):
+        return np.tile(w0, (H, 1)), {"status": status}
+    return w, {"status": status, "value": float(obj[0]), "kkt": tuple(kkt), "iterations": int(it[0])}
+
+
+def solve_mean_variance_batch(w_cur, mu, sigma, gamma: float, cost_coeff: float = 1e-3, allow_short: bool = False):
+    """P mean-variance problems resident on the device: w_cur [P,N], mu [P,H,N], sigma [N,N] or [P,N,N] (fp64 CUDA)."""
+    import torch
+    P, H, N = mu.shape
+    dev = mu.device.index or 0
+    mu = mu.contiguous().to(torch.float64); sigma = sigma.contiguous().to(torch.float64)
+    w_cur = w_cur.contiguous().to(torch.float64)
+    out = {"w": torch.empty((P, H, N), dtype=torch.float64, device=mu.device),
+           "value": torch.empty(P, dtype=torch.float64, device=mu.device),
+           "kkt": torch.empty((P, 3), dtype=torch.float64, device=mu.device),
+           "status": torch.empty(P, dtype=torch.int32, device=mu.device),
+           "iterations": torch.empty(P, dtype=torch.int32, device=mu.device)}
+    h = _capi.Handle.get(dev)
+    _capi.check(_capi.lib().kmpc_mpc_mean_variance(
+        h.ptr, _capi.ptr(mu), _capi.ptr(sigma), int(sigma.dim() == 3), _capi.ptr(w_cur), float(gamma), float(cost_coeff),
+        int(bool(allow_short)), P, H, N, _capi.ptr(out["w"]), _capi.ptr(out["value"]), _capi.ptr(out["kkt"]),
+        _capi.ptr(out["status"]), _capi.ptr(out["iterations"]), _capi.stream_ptr(dev)))
+    return out
+
+
 def solve_mpc_batch(w_cur, yhat, lam=None, tau=None, cost_coeff: float = 1e-3, max_turnover: float = 0.2,
                     allow_short: bool = False):
     """P problems resident on the device.  w_cur [P,N] f64, yhat [P,H,N] f32 (or f64) CUDA tensors; lam/tau

@@ -626,3 +626,103 @@ def solve_mpc_log_utility(current_weights, predicted_log_returns, config, method
     fn = solve_dense if method == "dense" else solve_structured
     r = fn(current_weights, yhat, lam, tau, bool(config.allow_short))
     return r.w, {"status": STATUS_NAMES[r.status], "value": r.value, "iters": r.iters, "kkt": r.kkt}
+
+
+# ----------------------------------------------------------------------------------------------
+# mean-variance MPC (mpc.py:119-184), SURVEY section 8f
+# ----------------------------------------------------------------------------------------------
+
+def mv_objective(w, w_cur, mu, Sigma, gamma, lam):
+    """Maximised objective of mpc.py:176 for a plan w[H,N] (fp64)."""
+    w = np.asarray(w, dtype=np.float64)
+    prev = np.vstack([np.asarray(w_cur, dtype=np.float64)[None, :], w[:-1]])
+    quad = np.einsum('ti,ij,tj->', w, Sigma, w)
+    return float((w * mu).sum() - gamma * quad - lam * np.abs(w - prev).sum())
+
+
+def solve_mv_dense(w_cur, mu, Sigma, gamma, lam, allow_short=False, *, tol=1e-10, tol_dual=1e-9, max_iter=120):
+    """maximise sum_t [ w_t.mu_t - gamma w_t' Sigma w_t ] - lam sum_t ||w_t - w_{t-1}||_1   (w_0 = w_cur)
+    s.t. sum(w_t) = 1, w_t >= 0 unless allow_short; NO turnover cap (mpc.py:139-176).
+
+    Same generic primal-dual interior point as solve_dense (explicit constraint matrix, dense KKT solves) with the
+    quadratic stage cost instead of the logarithm.  Ground truth for csrc/mpc_mv.cuh."""
+    w_cur = np.asarray(w_cur, dtype=np.float64)
+    mu = np.asarray(mu, dtype=np.float64)
+    Sigma = np.asarray(Sigma, dtype=np.float64)
+    H, N = mu.shape
+    if not (np.all(np.isfinite(mu)) and np.all(np.isfinite(w_cur)) and np.all(np.isfinite(Sigma))):
+        return _Result(w=np.tile(w_cur, (H, 1)), value=None, status=STATUS_NONFINITE, iters=0, kkt=(np.nan,) * 3)
+    has_u = lam > 0
+    w, u = _initial_point(w_cur, H, N, 0.0, has_u, allow_short)
+    G, h, A, b = _build_constraints(w_cur, H, N, 0.0, has_u, allow_short)
+    GT = G.T.tocsr()
+    m = G.shape[0]
+    HN = H * N
+    x = np.concatenate([w.ravel(), u.ravel()]) if has_u else w.ravel().copy()
+    n = x.size
+    cvec = np.zeros(n)
+    cvec[:HN] = -mu.ravel()
+    if has_u:
+        cvec[HN:] = lam
+    Q = np.zeros((n, n))
+    for t in range(H):
+        sl = slice(t * N, (t + 1) * N)
+        Q[sl, sl] = 2.0 * gamma * Sigma
+    nu = np.zeros(H)
+    s = h - G @ x
+    z = 1e-3 / s if m else np.zeros(0)
+    status, res, it = STATUS_MAXITER, (np.inf,) * 3, 0
+    for it in range(1, max_iter + 1):
+        grad = cvec + Q @ x
+        s = h - G @ x
+        r_d = grad + (GT @ z if m else 0.0) + A.T @ nu
+        r_p = A @ x - b
+        gap = float(s @ z) if m else 0.0
+        res = (float(np.abs(r_p).max()), float(np.abs(r_d).max()), gap)
+        if res[0] < tol and res[1] < tol_dual and gap < tol:
+            status = STATUS_OPTIMAL
+            break
+        mu_c = gap / max(m, 1)
+        Hm = Q.copy()
+        if m:
+            Hm += (GT @ (G.multiply((z / s)[:, None]))).toarray()
+        KKT = np.block([[Hm, A.T], [A, np.zeros((H, H))]])
+        KKT[np.arange(n), np.arange(n)] += 1e-300
+
+        def newton(cterm):
+            rhs = np.concatenate([-grad - A.T @ nu - (GT @ (cterm / s) if m else 0.0), -r_p])
+            sol = np.linalg.solve(KKT, rhs)
+            dx, dnu = sol[:n], sol[n:]
+            Gdx = G @ dx if m else np.zeros(0)
+            dz = (cterm / s - z) + (z / s) * Gdx if m else np.zeros(0)
+            return dx, dnu, dz, -Gdx
+
+        def max_step(ds, dz):
+            a = 1.0
+            for v, dv in ((s, ds), (z, dz)):
+                neg = dv < 0
+                if m and neg.any():
+                    a = min(a, float((-v[neg] / dv[neg]).min()))
+            return a
+
+        if m:
+            dxa, dnua, dza, dsa = newton(np.zeros(m))
+            aa = max_step(dsa, dza)
+            mu_aff = float((s + aa * dsa) @ (z + aa * dza)) / m
+            sigma = max(0.05, min(1.0, (mu_aff / mu_c) ** 3)) if mu_c > 0 else 0.0
+            cterm = sigma * mu_c - dsa * dza
+        else:
+            cterm = np.zeros(0)
+        dx, dnu, dz, ds = newton(cterm)
+        a = min(1.0, 0.995 * max_step(ds, dz)) if m else 1.0
+        x = x + a * dx
+        nu = nu + a * dnu
+        if m:
+            z = z + a * dz
+    wv = x[:HN].reshape(H, N).copy()
+    if status != STATUS_OPTIMAL and np.isfinite(res[1] + res[2]) and res[0] < LOOSE_PRES and res[1] < LOOSE_DRES \
+            and res[2] < LOOSE_GAP:
+        status = STATUS_INACCURATE
+    if status in (STATUS_OPTIMAL, STATUS_INACCURATE):
+        return _Result(w=wv, value=mv_objective(wv, w_cur, mu, Sigma, gamma, lam), status=status, iters=it, kkt=res)
+    return _Result(w=np.tile(w_cur, (H, 1)), value=None, status=status, iters=it, kkt=res)

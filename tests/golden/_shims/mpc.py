@@ -27,5 +27,15 @@ def solve_mpc_log_utility(current_weights, predicted_log_returns, config):
     return w, {"status": info["status"], "value": info["value"]}
 
 
-def solve_mpc_mean_variance(*a, **k):
-    raise NotImplementedError("mean-variance MPC is outside the hot path (SURVEY.md §8f)")
+MV_CALLS = []  # (w_cur, mu, sigma, w_opt, value) of every mean-variance call
+
+
+def solve_mpc_mean_variance(current_weights, predicted_log_returns, cov_matrix, config):
+    r = mpc_oracle.solve_mv_dense(current_weights, predicted_log_returns, cov_matrix, config.gamma, config.cost_coeff,
+                                  config.allow_short)
+    MV_CALLS.append((np.array(current_weights, dtype=np.float64), np.array(predicted_log_returns), np.array(cov_matrix),
+                     r.w.copy(), r.value))
+    status = mpc_oracle.STATUS_NAMES[r.status]
+    if r.value is None:
+        return r.w, {"status": status}
+    return r.w, {"status": status, "value": r.value}

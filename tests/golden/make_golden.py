@@ -11,6 +11,7 @@ small .npz files; large weights are regenerated from seeds by koopman_mpc_portfo
                        and LISTAKM (linear and MLP encoder); weights stored (tiny models)
   forecast_cfg1.npz    finance_sparse preset, TARGET_SIZE=128, N=10, d=20 (BASELINE config 1); weights from seed
   rollouts_small.npz   evaluation.rollout_{no,every_step,periodic}_reencode (evaluation.py:44-134) on two tiny models
+  markowitz_small.npz  UNMODIFIED reference MarkowitzStrategy + run_backtest (substitute mean-variance solve = fp64 oracle)
   dmd_small.npz        UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small env: fitted K,
                        the forecasts handed to the MPC, history, metrics
   backtest_cfg1.npz    UNMODIFIED reference run_backtest + KoopmanMPCStrategy + calculate_metrics on config 1
@@ -200,6 +201,36 @@ def gen_cfg1():
     print("buy&hold    ", bh_metrics)
 
 
+def gen_markowitz():
+    """UNMODIFIED reference MarkowitzStrategy (baselines.py:24-106) + run_backtest on the small env of gen_dmd: the
+    (mu, Sigma) it estimates at every step, the weights the (substitute, fp64 oracle) mean-variance solve returns,
+    history and metrics."""
+    import baselines as ref_baselines
+    N, d, H = 6, 4, 1
+    T = 700
+    frame = make_frame(21, T, N)
+    val_end = str(frame.index[T - 61].date())
+    train_end = str(frame.index[T - 61 - 100].date())
+    env, stats, _ = build_env(frame, train_end, val_end, d)
+    bt_cfg = ref_backtest.BacktestConfig(initial_capital=1e4, horizon=H, cost_coeff=1e-3)
+    strat = ref_baselines.MarkowitzStrategy(risk_aversion=2.0, cost_coeff=1e-3)
+    shim_mpc.MV_CALLS.clear()
+    df = ref_backtest.run_backtest(strat, env, bt_cfg, verbose=False)
+    metrics = ref_backtest.calculate_metrics(df)
+    calls = shim_mpc.MV_CALLS
+    np.savez(
+        os.path.join(HERE, "markowitz_small.npz"),
+        T=T, N=N, d=d, log_returns_seed=21, n_train_days=T - 61 - 100 + 1, n_val_days=100, gamma=2.0,
+        mean=stats.mean, std=stats.std,
+        mu=np.stack([c[1] for c in calls]), sigma=np.stack([c[2] for c in calls]),
+        w_cur=np.stack([c[0] for c in calls]), w_opt=np.stack([c[3] for c in calls]),
+        value=np.array([np.nan if c[4] is None else c[4] for c in calls]),
+        history=df[["portfolio_value", "return", "turnover", "cost"]].values.astype(np.float64),
+        metrics=np.array([metrics[k] for k in ("Sharpe Ratio", "Max Drawdown", "Avg Turnover", "Final Value", "Total Return")]),
+    )
+    print("markowitz metrics", metrics, "calls", len(calls), "steps", len(df))
+
+
 def gen_rollouts():
     """reference evaluation.rollout_no_reencode / rollout_every_step_reencode / rollout_periodic_reencode
     (evaluation.py:44-134) on two of the tiny forecast models (weights already stored in forecast_*.npz)."""
@@ -258,6 +289,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dmd":
         gen_dmd()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "markowitz":
+        gen_markowitz()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rollouts":
         gen_rollouts()
         sys.exit(0)
@@ -266,4 +300,5 @@ if __name__ == "__main__":
     gen_cfg1()
     gen_dmd()
     gen_rollouts()
+    gen_markowitz()
     print("golden fixtures written to", HERE)

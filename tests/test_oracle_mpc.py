@@ -134,3 +134,39 @@ def test_path_sweep_componentwise_accuracy():
     dw, dd = mo._path_sweep(mo._path_factors(a, e), gw, pg)
     assert float(np.max(np.abs(dw - dw_ref) / sw)) < 5e-15
     assert float(np.max(np.abs(dd - dd_ref) / sd)) < 5e-15
+
+
+def test_mean_variance_oracle_known_answers():
+    """solve_mv_dense (restatement of mpc.py:119-184) pinned by a closed form (lam = 0, shorting allowed, H = 1:
+    w = Sigma^{-1}(mu - nu 1) / (2 gamma)) and by SLSQP on the smooth epigraph form of small instances."""
+    from scipy.optimize import minimize
+    rng = np.random.default_rng(1)
+    N = 6
+    X = rng.standard_normal((60, N)) * 0.01
+    S = np.cov(X, rowvar=False) + 1e-6 * np.eye(N); mu = X.mean(0); g = 5.0
+    r = mo.solve_mv_dense(np.ones(N) / N, mu[None], S, g, 0.0, allow_short=True)
+    Si = np.linalg.inv(S); one = np.ones(N)
+    nu = (one @ Si @ mu - 2 * g) / (one @ Si @ one)
+    assert r.status == 0 and np.abs(r.w[0] - Si @ (mu - nu) / (2 * g)).max() < 1e-12
+    for trial in range(2):
+        N, H = 4, 2
+        X = rng.standard_normal((30, N)) * 0.01
+        S = np.cov(X, rowvar=False) + 1e-6 * np.eye(N); mu = rng.standard_normal((H, N)) * 1e-3
+        w0 = rng.dirichlet(np.ones(N)); lam = 1e-3; g = 2.0
+        r = mo.solve_mv_dense(w0, mu, S, g, lam)
+
+        def f(xv):
+            w = xv[:H * N].reshape(H, N); u = xv[H * N:]
+            return -((w * mu).sum() - g * np.einsum('ti,ij,tj->', w, S, w) - lam * u.sum())
+
+        def ineq(xv):
+            w = xv[:H * N].reshape(H, N); u = xv[H * N:].reshape(H, N)
+            d = w - np.vstack([w0[None], w[:-1]])
+            return np.concatenate([w.ravel(), (u - d).ravel(), (u + d).ravel()])
+        cons = [{'type': 'eq', 'fun': (lambda xv, t=t: xv[t * N:(t + 1) * N].sum() - 1)} for t in range(H)]
+        cons.append({'type': 'ineq', 'fun': ineq})
+        sol = minimize(f, np.concatenate([np.tile(w0, H), np.full(H * N, 0.1)]), constraints=cons, method='SLSQP',
+                       options={'ftol': 1e-14, 'maxiter': 500})
+        assert r.status == 0 and abs(r.value + sol.fun) < 1e-9
+        assert np.abs(r.w - sol.x[:H * N].reshape(H, N)).max() < 1e-6
+        assert abs(mo.mv_objective(r.w, w0, mu, S, g, lam) - r.value) < 1e-15
