@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include "../../include/kmpc.h"
 #include "kmpc_internal.cuh"
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -116,6 +117,18 @@ int kmpc_current_returns(kmpc_handle* h, const float* z, int ld_z, const double*
   return KMPC_OK;
 }
 
+// solver options: the defaults of mpc_ipm.cuh, with two tuning overrides read once from the environment
+// (KMPC_STEP_FRAC, KMPC_DUAL_INIT; experiments only, the tests run with the defaults)
+static kmpc::IpmOptions ipm_options() {
+  static kmpc::IpmOptions o = [] {
+    kmpc::IpmOptions v = kmpc::default_ipm_options();
+    if (const char* e = getenv("KMPC_STEP_FRAC")) v.step_frac = atof(e);
+    if (const char* e = getenv("KMPC_DUAL_INIT")) v.dual_init = atof(e);
+    return v;
+  }();
+  return o;
+}
+
 int kmpc_mpc_solve(kmpc_handle* h, const float* yhat, const double* yhat64, const double* w_cur, const double* lam,
                    const double* tau, double lam0, double tau0, int allow_short, int P, int H, int N, double* w_out,
                    double* obj, double* kkt, int32_t* status, int32_t* iters, void* stream) {
@@ -128,7 +141,7 @@ int kmpc_mpc_solve(kmpc_handle* h, const float* yhat, const double* yhat64, cons
   kmpc::MpcSolveArgs A;
   A.yhat = yhat; A.yhat64 = yhat64; A.w_cur = w_cur; A.lam = lam; A.tau = tau; A.lam0 = lam0; A.tau0 = tau0;
   A.allow_short = allow_short; A.P = P; A.N = N; A.w_out = w_out; A.obj = obj; A.kkt = kkt; A.status = status;
-  A.iters = iters; A.fix_flag = h->work_counter + 2; A.opt = kmpc::default_ipm_options();
+  A.iters = iters; A.fix_flag = h->work_counter + 2; A.opt = ipm_options();
   int rc = kmpc::dispatch_mpc_solve(A, H, h->sm_count, (cudaStream_t)stream);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_solve: unsupported shape");
@@ -246,7 +259,7 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   A.lam0 = D->lam0; A.tau0 = D->tau0; A.cost_coeff0 = D->cost_coeff0; A.capital0 = D->capital0;
   A.allow_short = D->allow_short; A.B = D->B; A.N = D->N;
   A.history = D->history; A.metrics = D->metrics; A.solve_stats = (long long*)D->solve_stats;
-  A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = kmpc::default_ipm_options();
+  A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = ipm_options();
   int rc = kmpc::dispatch_backtest(A, D->H, h->sm_count, st);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_backtest_run: unsupported shape");

@@ -41,7 +41,10 @@ struct IpmOptions {
 
 __host__ __device__ inline IpmOptions default_ipm_options() {
   IpmOptions o;
-  o.tol = 1e-10; o.tol_dual = 1e-8; o.delta = 1e-5; o.step_frac = 0.995; o.mu0 = 1e-3; o.dual_init = 3e-3;
+  // step_frac / dual_init tuned on the 1.0 M-decision config-2 replay and a random instance mix (N 2..64, H 1..5,
+  // lam 0..0.1, tau 0..1): (0.995, 3e-3) -> (0.9999, 1e-3) takes 9.35 -> 8.00 iterations per decision at the same
+  // failure rate (3 fallbacks per million), 9.8 -> 8.9 on the mix with zero failures
+  o.tol = 1e-10; o.tol_dual = 1e-8; o.delta = 1e-5; o.step_frac = 0.9999; o.mu0 = 1e-3; o.dual_init = 1e-3;
   o.max_iter = 100;
   return o;
 }

@@ -368,8 +368,8 @@ def _path_sweep(F, gw, pg):
 
 
 def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e-10, tol_dual=1e-8,
-                     max_iter=100, trace=None, delta=1e-5, split_steps=True, step_frac=0.995, mu0=1e-3,
-                     dual_init=3e-3, apply="green"):
+                     max_iter=100, trace=None, delta=1e-5, split_steps=True, step_frac=0.9999, mu0=1e-3,
+                     dual_init=1e-3, apply="green"):
     """Primal-dual IPM (Mehrotra); Newton step = per-asset path-network Green's functions + a (<=3H)
     dense border system.  This is the algorithm the CUDA kernel implements (csrc/mpc_ipm.cuh).
 
