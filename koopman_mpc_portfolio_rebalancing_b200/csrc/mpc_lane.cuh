@@ -18,12 +18,17 @@
 //               emits its <= 3H^2 + 3H(H+1)/2 products into a [entry][thread] shared-memory tile (conflict free),
 //               lane e of every warp adds up row e over its 32 columns (16 LDS.128 + 32 DADD for 32 entries; a
 //               shuffle butterfly costs ~8 instructions per entry), warp 0 combines the G partials.
-//   Cholesky  = warp 0, lane = row, the row lives in registers, columns are exchanged by shuffles: 15 dependent
-//               steps instead of 105 dependent shared-memory round trips; the factor goes back to shared memory
-//               for the two triangular solves of each Newton system.
+//   L D L'    = warp 0, lane = row, the row lives in registers, columns are exchanged by shuffles: 15 dependent
+//               steps instead of 105 dependent shared-memory round trips, no square root; the factor goes back to
+//               shared memory for the two triangular solves of each Newton system.
 //   division  = MUFU.RCP64H + one third-order Newton step (4 instructions, <= 2 ulp) for the ~40 reciprocals
 //               per asset and iteration; the step-length ratio tests multiply by reciprocals and keep a running
-//               maximum (no divergent division).
+//               integer maximum of the high words (no divergent division, no DSETP/FSEL chains).
+//   flags     = FIX = true instantiates the solver for the reference defaults (long-only, lam > 0, tau > 0) with
+//               the structure flags as compile-time constants; LOC = true keeps factors / targets thread-private
+//               (H = 10 or N > 128, see below).
+//   pieces    = begin / check / factor_a / factor_b / newton_phase, so that the persistent backtest kernel
+//               (mpc_lane_kernels.cuh) can walk several problems of one SM through an iteration together.
 #pragma once
 #include "mpc_ipm.cuh"
 
@@ -212,22 +217,6 @@ struct LaneIpm {
     tile_reduce<NV>(v);
 #pragma unroll
     for (int e = 0; e < NV; ++e) out[e] = ptotal(e);
-  }
-  // one or two values per thread -> block-wide max (shuffle butterfly, then the G partials)
-  __device__ __forceinline__ void block_max2(double& a, double& b) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a = fmax(a, shfl_xor_d(a, o));
-      b = fmax(b, shfl_xor_d(b, o));
-    }
-    if (G > 1) {
-      psel ^= 1;
-      double* P = sm + OFF_P + psel * G * 32;
-      if (lane == 0) { P[warp * 32] = a; P[warp * 32 + 1] = b; }
-      sync();
-#pragma unroll
-      for (int g = 0; g < G; ++g) { a = fmax(a, P[g * 32]); b = fmax(b, P[g * 32 + 1]); }
-    }
   }
   // Maxima of non-negative quantities are taken on the HIGH WORDS of the doubles as integers (one VIMNMX instead of
   // DSETP + 2 FSEL; a negative double has a negative high word and drops out against the initial 0) and rounded UP
