@@ -484,10 +484,11 @@ struct CtaIpm {
           reduce_sum<1>(vv, SS, TT);
           const double ratio = (gap > 0.0) ? fmin(1.0, fmax(TT[0] / gap, 0.0)) : 0.0;
           const double smu = ratio * ratio * ratio * mu;
-          dzw = has_w ? smu - dw * dzw : 0.0;           // complementarity targets replace the affine dual steps
-          dzp = has_u ? smu - dsp * dzp : 0.0;
-          dzq = has_u ? smu - dsq * dzq : 0.0;
-          cc = has_c ? smu - dsc * dzc : 0.0;
+          const double dmp = fmin(1.0, fmin(aa, ab) * (1.0 / kCorrFull));
+          dzw = has_w ? smu - dmp * dw * dzw : 0.0;           // complementarity targets replace the affine dual steps
+          dzp = has_u ? smu - dmp * dsp * dzp : 0.0;
+          dzq = has_u ? smu - dmp * dsq * dzq : 0.0;
+          cc = has_c ? smu - dmp * dsc * dzc : 0.0;
         } else {
           const bool stepped = (mcount > 0.0 || allow_short);
           const double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;

@@ -56,6 +56,8 @@ __host__ __device__ inline IpmOptions default_ipm_options() {
 // the optimal objective and 4e-4 of the optimal first-stage weights, whereas holding the weights (the fallback) is
 // 0.1 away.
 constexpr double kLoosePres = 1e-8, kLooseDres = 1e-4, kLooseGap = 1e-7;
+// Mehrotra's second-order term is scaled by min(1, affine step / kCorrFull): see oracle/mpc_oracle.py (CORRECTOR_FULL_STEP)
+constexpr double kCorrFull = 0.3;
 
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -737,19 +739,20 @@ struct WarpIpm {
           const double ratio = (gap > 0.0) ? fmin(1.0, fmax(g2 / gap, 0.0)) : 0.0;
           const double sigma = ratio * ratio * ratio;
           const double smu = sigma * mu;
+          const double dmp = fmin(1.0, fmin(aa, ab) * (1.0 / kCorrFull));
           // complementarity targets of the corrector, stored in place of the affine dual steps
 #pragma unroll 1
           for (int a = 0; a < APT; ++a) {
             if (!ok(a)) continue;
 #pragma unroll
             for (int k = 0; k < H; ++k) {
-              F(DZW, k, a) = has_w ? smu - F(DW, k, a) * F(DZW, k, a) : 0.0;
-              F(DZP, k, a) = has_u ? smu - F(DSP, k, a) * F(DZP, k, a) : 0.0;
-              F(DZQ, k, a) = has_u ? smu - F(DSQ, k, a) * F(DZQ, k, a) : 0.0;
+              F(DZW, k, a) = has_w ? smu - dmp * F(DW, k, a) * F(DZW, k, a) : 0.0;
+              F(DZP, k, a) = has_u ? smu - dmp * F(DSP, k, a) * F(DZP, k, a) : 0.0;
+              F(DZQ, k, a) = has_u ? smu - dmp * F(DSQ, k, a) * F(DZQ, k, a) : 0.0;
             }
           }
 #pragma unroll
-          for (int k = 0; k < H; ++k) U(CC, k) = has_c ? smu - U(DSC, k) * U(DZC, k) : 0.0;
+          for (int k = 0; k < H; ++k) U(CC, k) = has_c ? smu - dmp * U(DSC, k) * U(DZC, k) : 0.0;
         } else {
           const double a_ = fmin(1.0, opt.step_frac * aa), b_ = fmin(1.0, opt.step_frac * ab);
           const double pa = (mcount > 0.0 || allow_short) ? a_ : 1.0, pb = (mcount > 0.0 || allow_short) ? b_ : 1.0;

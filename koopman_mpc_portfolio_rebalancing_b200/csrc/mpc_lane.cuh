@@ -766,13 +766,14 @@ struct LaneIpm {
       g2 = block_sum1(g2);
       const double ratio = (gap_ > 0.0) ? fmin(1.0, fmax(g2 / gap_, 0.0)) : 0.0;
       const double smu = ratio * ratio * ratio * mu_;
+      const double dmp = fmin(1.0, fmin(aa, ab) * (1.0 / kCorrFull));   // short affine step: damp the corrector
 #pragma unroll
       for (int k = 0; k < H; ++k) {      // complementarity targets of the corrector
-        TGT(T_CW, k) = hw() ? fma(-dw[k], dzw[k], smu) : 0.0;
-        TGT(T_CP, k) = hu() ? fma(-dsp[k], dzp[k], smu) : 0.0;
-        TGT(T_CQ, k) = hu() ? fma(-dsq[k], dzq[k], smu) : 0.0;
+        TGT(T_CW, k) = hw() ? fma(-dmp * dw[k], dzw[k], smu) : 0.0;
+        TGT(T_CP, k) = hu() ? fma(-dmp * dsp[k], dzp[k], smu) : 0.0;
+        TGT(T_CQ, k) = hu() ? fma(-dmp * dsq[k], dzq[k], smu) : 0.0;
       }
-      if (tid < H) U(U_CC, tid) = hc() ? fma(-dsc, dzc, smu) : 0.0;
+      if (tid < H) U(U_CC, tid) = hc() ? fma(-dmp * dsc, dzc, smu) : 0.0;
       sync();
     } else {
       const double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;

@@ -363,11 +363,12 @@ mpc_mv_kernel(MvArgs A) {
           g2 = mv_warp_sum(g2);
           const double ratio = (gap > 0.0) ? fmin(1.0, fmax(g2 / gap, 0.0)) : 0.0;
           const double smu = ratio * ratio * ratio * mug;
+          const double dmp = fmin(1.0, fmin(aa, ab) * (1.0 / kCorrFull));
 #pragma unroll
           for (int s = 0; s < MV_MAX_SLOTS; ++s) {
-            cw[s] = has_w ? fma(-dw[s], dzw[s], smu) : 0.0;
-            cp[s] = has_u ? fma(-dsp[s], dzp[s], smu) : 0.0;
-            cq[s] = has_u ? fma(-dsq[s], dzq[s], smu) : 0.0;
+            cw[s] = has_w ? fma(-dmp * dw[s], dzw[s], smu) : 0.0;
+            cp[s] = has_u ? fma(-dmp * dsp[s], dzp[s], smu) : 0.0;
+            cq[s] = has_u ? fma(-dmp * dsq[s], dzq[s], smu) : 0.0;
           }
         }
       }

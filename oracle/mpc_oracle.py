@@ -42,6 +42,7 @@ import numpy as np
 # loose acceptance ("optimal_inaccurate") of an iterate that could not be pushed to the tolerances; same constants as
 # csrc/mpc_ipm.cuh (kLoosePres / kLooseDres / kLooseGap), see the comment there
 LOOSE_PRES, LOOSE_DRES, LOOSE_GAP = 1e-8, 1e-4, 1e-7
+CORRECTOR_FULL_STEP = 0.3   # affine step below which the corrector's second-order term is scaled down (kCorrFull)
 STATUS_OPTIMAL = 0
 STATUS_INACCURATE = 1
 STATUS_MAXITER = 2
@@ -591,10 +592,14 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
                 g2 += float(((sc_ + aa * dsc) * (zc + ab * dzc)).sum())
             sigma = min(1.0, max(g2 / gap, 0.0)) ** 3 if gap > 0 else 0.0
             sm = sigma * mu
-            cw = sm - dw * dzw if has_w else zHN
-            cp_ = sm - dsp * dzp if has_u else zHN
-            cq_ = sm - dsq * dzq if has_u else zHN
-            cc_ = sm - dsc * dzc if has_c else zH
+            # Mehrotra's second-order term is only trustworthy when the affine step is long; after a short affine
+            # step (< 0.3) it is scaled down in proportion (on 500-asset, 10-stage instances the undamped corrector
+            # produced steps of 0.01-0.05 for dozens of iterations: 52-64 -> 34-46 iterations; no effect on the rest)
+            dmp = min(1.0, min(aa, ab) / CORRECTOR_FULL_STEP)
+            cw = sm - dmp * dw * dzw if has_w else zHN
+            cp_ = sm - dmp * dsp * dzp if has_u else zHN
+            cq_ = sm - dmp * dsq * dzq if has_u else zHN
+            cc_ = sm - dmp * dsc * dzc if has_c else zH
         else:
             cw = cp_ = cq_ = zHN; cc_ = zH
         dw, du, dnu, dsp, dsq, dsc, dzw, dzp, dzq, dzc = newton(cw, cp_, cq_, cc_)
