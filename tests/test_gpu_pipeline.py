@@ -230,3 +230,48 @@ def test_pipelined_host_copy_equals_device_run():
     a2 = eng.run(engine.PathBatch(lr_pinned, mean[0], std[0], 0, rows), copy_chunks=4)
     b2 = eng.run(engine.PathBatch(lr_pinned, mean[0], std[0], 0, rows), copy_chunks=1)
     assert np.array_equal(a2["metrics"], b2["metrics"])
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at FULL size (4096 scenario backtests x 246 decisions, 50 assets, d = 20, H = 5, the
+    1000->1024->1024->1024 encoder) through size-independent properties: bitwise determinism, invariance under
+    sharding the batch, the turnover cap and positivity on every one of the 1.0 M decisions, device metrics equal
+    to calculate_metrics of the device history, and a sampled path equal to its own oracle backtest."""
+    import pandas as pd
+    import torch
+    import bench
+    from koopman_mpc_portfolio_rebalancing_b200 import engine, model as km, synthetic, backtest as bt
+    from oracle import backtest_oracle as bo, data_oracle as do
+    w = bench.WORKLOADS["cfg2"]
+    B, N, d, H, Z, rows = w["B"], w["N"], w["d"], w["H"], w["Z"], w["rows"]
+    ns = rows - 1 - H
+    lr, mean, std, T = bench.make_inputs(w, B, 10_000)
+    m = km.make_model(km.model_config("GenericKM", Z, w["enc"], enc_bias=True), N * d)
+    m.load_state_dict(synthetic.generic_km_weights(0, N * d, w["enc"], Z))
+    eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H, cost_coeff=1e-3, max_turnover=0.2),
+                                   bt.BacktestConfig(initial_capital=1e4, horizon=H, cost_coeff=1e-3))
+    lr_d, mean_d, std_d = torch.from_numpy(lr).cuda(), torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda()
+    out = eng.run_device(lr_d, mean_d, std_d, 0, rows, want_history=True)
+    met = out["metrics"].cpu().numpy().copy(); hist = out["history"].cpu().numpy().copy()
+    stats = out["stats"].cpu().numpy().copy(); yhat = out["yhat"][[7, 3000]].cpu().numpy().copy()
+    assert met.shape == (B, 5) and hist.shape == (B, ns, 4) and np.isfinite(met).all() and np.isfinite(hist).all()
+    assert stats[:, :3].sum() == B * ns and stats[:, 2].sum() <= 10            # fallbacks: a few per million at most
+    # every decision respects the cap (first-stage turnover <= tau) and keeps the value positive
+    assert hist[:, :, 2].max() <= 0.2 + 1e-7 and hist[:, :, 0].min() > 0
+    # determinism and shard invariance (no cross-backtest state)
+    out2 = eng.run_device(lr_d, mean_d, std_d, 0, rows, want_history=True)
+    assert np.array_equal(out2["metrics"].cpu().numpy(), met) and np.array_equal(out2["history"].cpu().numpy(), hist)
+    sl = slice(1000, 1777)
+    out3 = eng.run_device(lr_d[sl].contiguous(), mean_d[sl].contiguous(), std_d[sl].contiguous(), 0, rows, want_history=True)
+    assert np.array_equal(out3["metrics"].cpu().numpy(), met[sl])
+    # device metrics == calculate_metrics(history) (backtest.py:221-249)
+    for b in (0, 1234, 4095):
+        df = pd.DataFrame(hist[b], columns=list(bt.HISTORY_COLS))
+        m2 = bt.calculate_metrics(df)
+        assert np.allclose(met[b], [m2[k] for k in bt.METRIC_KEYS], rtol=1e-10, atol=1e-12)
+    # sampled paths vs the oracle loop on the same forecasts
+    for j, b in enumerate((7, 3000)):
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)
+        allr = do.destandardize(do.extract_current_returns(emb, N), mean[b], std[b])
+        rh, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat[j], 1e-3, 0.2), allr, rows - 1, H)
+        assert np.allclose(hist[b][:, 0], np.asarray(rh)[:, 0], rtol=1e-6)
