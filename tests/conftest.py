@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """libkmpc.so is a build artefact (git-ignored): if the suite is started in a fresh checkout before
+    __graft_entry__.build(), compile it once (nvcc cross-compiles sm_100a without a GPU, about a minute)."""
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    if not os.path.exists(_capi.LIB_PATH):
+        from koopman_mpc_portfolio_rebalancing_b200 import build as kb
+        kb.build(verbose=False)
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):
