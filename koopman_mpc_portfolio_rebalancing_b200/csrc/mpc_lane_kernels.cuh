@@ -1,6 +1,7 @@
 // Kernels around the lane-per-asset IPM solver (mpc_lane.cuh): same entry points and semantics as
-// mpc_kernels.cuh (mpc_solve = mpc.py:27-117, backtest = backtest.py:173-249); one block of G warps per problem /
-// per backtest, thread i = asset i, all stages of an asset in that thread's registers.
+// mpc_kernels.cuh (mpc_solve = mpc.py:27-117, backtest = backtest.py:173-249).  mpc_solve: one block of G warps per
+// problem; backtest: a persistent block hosts several backtests ("slots" of G warps each) that walk through the
+// Newton iteration together.  Thread i of a slot = asset i, all stages of an asset in that thread's registers.
 #pragma once
 #include "kmpc_internal.cuh"
 #include "mpc_lane.cuh"
@@ -84,8 +85,8 @@ mpc_solve_lane_kernel(MpcSolveArgs A, int want) {
 // ~8 k straight-line instructions per Newton iteration, several times the 32 KB instruction cache of an SM: when
 // every resident problem walks through it at its own pace the warps starve on instruction fetch (ncu: 41 % of
 // all stall samples `no_instruction`, throughput 2.15x going from 1 to 4 independent blocks per SM).  Here all
-// slots of the SM pass through the phases of an iteration TOGETHER (block-wide barrier between phases), so one
-// fetched line feeds every warp; a slot whose decision has converged books the portfolio step and starts its next
+// slots of the SM pass through the phases of an iteration TOGETHER (a block-wide barrier every few trips keeps them
+// within a phase or two of each other), so one fetched line feeds every warp; a slot whose decision has converged books the portfolio step and starts its next
 // decision inside the same trip, so no slot ever idles through a phase.
 // Book-keeping of one slot's current backtest (backtest.py:161-217, 221-249).  Lives in shared memory and is
 // touched by thread 0 of the slot only: as registers it would cost every thread of the kernel ~30 registers.
