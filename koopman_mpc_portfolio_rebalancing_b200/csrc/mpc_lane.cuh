@@ -122,6 +122,13 @@ struct LaneIpm {
 
   // `slot`: which of the problems that share this thread block (its threads are [slot*NT, (slot+1)*NT), its
   // named barrier is 1 + slot; barrier 0 stays free for block-wide lockstep points of the caller).
+#ifdef KMPC_LANE_PROFILE
+  // phase clocks of thread 0 of the block (tuning builds only; see profiles/README.md)
+  long long* prof_ = nullptr; long long tl_ = 0;
+#define KMPC_PROF(S, i) if ((S).prof_) { const long long n_ = clock64(); (S).prof_[i] += n_ - (S).tl_; (S).tl_ = n_; }
+#else
+#define KMPC_PROF(S, i)
+#endif
   __device__ __forceinline__ void bind(double* smem_slice, int n_assets, int slot) {
     sm = smem_slice; tid = (int)threadIdx.x - slot * NT; lane = tid & 31; psel = 0; bar_id = 1 + slot;
     warp = __shfl_sync(kFull, tid >> 5, 0);        // provably warp-uniform: branches on it need no reconvergence code
@@ -344,6 +351,7 @@ struct LaneIpm {
         FAC(F_FL, k) = fL[k]; FAC(F_FR, k) = fR[k];
       }
     }
+    KMPC_PROF(*this, 2)
     // ---- border matrix: emit the entries in KMap order, KB at a time --------------------------------------------
     if (warp == 0) {                                 // clear K (rows >= 2H stay identity when there is no cap)
       for (int q = lane; q < NB * NB; q += 32) sm[OFF_K + q] = (q / NB == q % NB) ? 1.0 : 0.0;
@@ -508,9 +516,11 @@ struct LaneIpm {
         t = ptotal(tid);
         if (tid >= H && tid < 2 * H) t += U(U_RP, tid - H);  // t[H+k] = sum dw0 - q, q = -rp
       }
+      KMPC_PROF(*this, 7)
       k_solve_shared(t);
     }
     sync();
+    KMPC_PROF(*this, 8)
     dnu = 0.0; dsc = 0.0; dzc = 0.0;
     if (tid < H) {                                           // stage scalars stay with their owner threads
       const double yC = hc() ? sm[OFF_T + 2 * H + tid] : 0.0;

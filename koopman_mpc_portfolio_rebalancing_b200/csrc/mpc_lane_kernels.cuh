@@ -6,6 +6,7 @@
 #include "kmpc_internal.cuh"
 #include "mpc_lane.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 // register budget of the backtest kernel: __maxnreg__ and __launch_bounds__ are mutually exclusive
 #ifdef KMPC_LANE_MAXNREG
@@ -132,6 +133,10 @@ backtest_lane_kernel(BacktestArgs A, int want) {
   bool active = (A.n_steps > 0) ? fetch() : false;
   bool need_start = true;
   int st = -1;
+#ifdef KMPC_LANE_PROFILE
+  __shared__ long long prof[12];
+  if (threadIdx.x == 0) { for (int i = 0; i < 12; ++i) prof[i] = 0; s.prof_ = prof; s.tl_ = clock64(); }
+#endif
   __syncthreads();
 #pragma unroll 1
   for (unsigned trip = 0;; ++trip) {
@@ -218,20 +223,32 @@ backtest_lane_kernel(BacktestArgs A, int want) {
     // all stall samples).  Measured: barriers between the phases change nothing, staggering the slots half a trip
     // apart is slower (357 vs 273 ms).
     // (the barrier doubles as the exit vote: all slots out of work)
+    KMPC_PROF(s, 0)
     if ((trip % KMPC_LANE_SYNC_EVERY) == 0) {
       if (__syncthreads_and(!active)) break;
     }
+    KMPC_PROF(s, 1)
     const bool act_u = uni(active);                            // provably warp-uniform (see uni())
     bool ok = false;
     if (act_u) {
       s.factor_a();
+      KMPC_PROF(s, 3)
       ok = s.factor_b();
+      KMPC_PROF(s, 4)
     }
     if (ok) {
 #pragma unroll 1
-      for (int phase = 0; phase < 2; ++phase) s.newton_phase(phase, opt);
+      for (int phase = 0; phase < 2; ++phase) {
+        s.newton_phase(phase, opt);
+        KMPC_PROF(s, 5 + phase)
+      }
     }
   }
+#ifdef KMPC_LANE_PROFILE
+  if (threadIdx.x == 0 && blockIdx.x < 2)
+    printf("lane_prof block %d: check/book/begin %lld  barrier %lld  factor_a.sweeps %lld  factor_a.K %lld  factor_b %lld  predictor.rest %lld  corrector.rest %lld  newton.sweep1+reduce %lld  newton.ksolve %lld\n",
+           (int)blockIdx.x, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8]);
+#endif
   // backtests without any step: NaN metrics (the host never asks for this; kept for completeness)
   if (A.n_steps <= 0) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < A.B * 5; q += gridDim.x * blockDim.x) A.metrics[q] = CUDART_NAN;

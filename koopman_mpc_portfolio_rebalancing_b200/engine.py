@@ -261,6 +261,39 @@ def write_results(path: str, metrics, history=None, ids=None):
     return path
 
 
+def compare_strategies(model, env, bt_config=None, mpc_config=None, risk_aversion: float = 1.0, out_dir=None,
+                       strategies=("Buy & Hold", "Markowitz", "DMD-MPC", "Koopman-MPC")):
+    """The four-strategy comparison of run_experiment.py:85-137 on one environment: Buy & Hold, Markowitz
+    (risk_aversion, cost 1e-3), DMD fitted on the training split, and the Koopman model, all through
+    ``run_backtest`` / ``calculate_metrics``.  Defaults are the reference's (capital 1e4, H = 5, cost 1e-3,
+    max_turnover 0.5).  Returns ``(results, metrics_df)``: per-strategy history frames and the table the reference
+    saves as ``full_comparison_metrics.csv`` (written to ``out_dir`` when given; no plotting)."""
+    import os
+    import pandas as pd
+    from .backtest import BacktestConfig, BuyAndHoldStrategy, KoopmanMPCStrategy, run_backtest, calculate_metrics
+    from .baselines import DMDStrategy, MarkowitzStrategy
+    from .mpc import MPCConfig
+    bt_config = bt_config or BacktestConfig(initial_capital=10000.0, horizon=5, rebalance_freq=1, cost_coeff=0.001)
+    mpc_config = mpc_config or MPCConfig(horizon=5, gamma=0.0, cost_coeff=0.001, max_turnover=0.5)
+    make = {
+        "Buy & Hold": lambda: BuyAndHoldStrategy(),
+        "Markowitz": lambda: MarkowitzStrategy(risk_aversion=risk_aversion, cost_coeff=0.001),
+        "DMD-MPC": lambda: DMDStrategy(env.train_dataset.data, mpc_config),
+        "Koopman-MPC": lambda: KoopmanMPCStrategy(model, mpc_config),
+    }
+    results, metrics = {}, {}
+    for name in strategies:
+        if name not in make:
+            raise ValueError(f"unknown strategy '{name}'; available: {list(make)}")
+        results[name] = run_backtest(make[name](), env, bt_config, verbose=False)
+        metrics[name] = calculate_metrics(results[name])
+    metrics_df = pd.DataFrame(metrics).T
+    if out_dir is not None:
+        os.makedirs(out_dir, exist_ok=True)
+        metrics_df.to_csv(os.path.join(out_dir, "full_comparison_metrics.csv"))
+    return results, metrics_df
+
+
 def shard_range(n: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of n independent backtests for one rank."""
     per = (n + world - 1) // world

@@ -332,3 +332,63 @@ def model_config(model_name="GenericKM", target_size=16, enc_layers=(16, 16), de
                        ENCODER=NS(LAYERS=list(enc_layers), LAST_RELU=last_relu, USE_BIAS=enc_bias, ACTIVATION=enc_act,
                                   LISTA=NS(NUM_LOOPS=lista_loops, L=lista_L, ALPHA=lista_alpha, LINEAR_ENCODER=lista_linear)),
                        DECODER=NS(LAYERS=list(dec_layers), USE_BIAS=dec_bias, ACTIVATION=dec_act)))
+
+
+def config_from_dict(d):
+    """Attribute-style view of the nested dict the reference stores under ``checkpoint['config']``
+    (``Config.to_dict()``, config.py:292-294; rebuilt there by ``Config.from_dict``, config.py:301-336).  Only
+    the MODEL sub-tree is read by this package; the rest is kept as found."""
+    from types import SimpleNamespace as NS
+    if isinstance(d, dict):
+        return NS(**{k: config_from_dict(v) for k, v in d.items()})
+    return d
+
+
+def _observation_size_of(sd):
+    for key in ("encoder.network.0.weight", "lista.We.weight", "lista.We.network.0.weight"):
+        if key in sd:
+            return int(sd[key].shape[1])
+    if "dict" in sd:
+        return int(sd["dict"].shape[1])
+    raise ValueError("cannot infer observation_size: state_dict has no encoder / dictionary weight")
+
+
+def read_checkpoint(path):
+    """Host part of the checkpoint loader: the file train.py:475-487 writes (``checkpoint.pt`` / ``last.pt``:
+    step, epoch, model_state_dict, optimizer_state_dict, config, metrics, finance_metadata).  Returns
+    ``(cfg, state_dict, info)`` with ``info = {step, epoch, metrics, finance_metadata, observation_size}``; a bare
+    state_dict file is accepted too (cfg None)."""
+    import torch
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        # finance_metadata may hold tuples/np scalars older torch versions pickled as globals
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+    if not isinstance(ck, dict):
+        raise ValueError(f"{path}: not a checkpoint dictionary")
+    if "model_state_dict" not in ck:
+        if all(hasattr(v, "shape") for v in ck.values()) and "kmat" in ck:
+            return None, dict(ck), {"observation_size": _observation_size_of(ck)}
+        raise ValueError(f"{path}: no 'model_state_dict' entry (keys {sorted(ck)})")
+    sd = dict(ck["model_state_dict"])
+    meta = ck.get("finance_metadata") or {}
+    obs = int(meta["observation_size"]) if "observation_size" in meta else _observation_size_of(sd)
+    if obs != _observation_size_of(sd):
+        raise ValueError(f"{path}: finance_metadata.observation_size {obs} != weight width {_observation_size_of(sd)}")
+    info = {"step": ck.get("step"), "epoch": ck.get("epoch"), "metrics": ck.get("metrics"),
+            "finance_metadata": meta, "observation_size": obs}
+    cfg = config_from_dict(ck["config"]) if "config" in ck else None
+    return cfg, sd, info
+
+
+def load_checkpoint(path, cfg=None, device="cuda"):
+    """``torch.load`` + ``Config.from_dict`` + ``make_model`` + ``load_state_dict`` + ``eval`` exactly as
+    run_experiment.py:67-79 / evaluate_checkpoints.py:121-151 do, for a model of this package.  ``cfg`` overrides
+    the stored config (needed for bare state_dict files).  Returns ``(model, info)``."""
+    ck_cfg, sd, info = read_checkpoint(path)
+    cfg = cfg if cfg is not None else ck_cfg
+    if cfg is None:
+        raise ValueError(f"{path}: holds no config; pass cfg=")
+    model = make_model(cfg, info["observation_size"], device=device)
+    model.load_state_dict(sd)
+    return model.eval(), info

@@ -14,6 +14,8 @@ small .npz files; large weights are regenerated from seeds by koopman_mpc_portfo
   markowitz_small.npz  UNMODIFIED reference MarkowitzStrategy + run_backtest (substitute mean-variance solve = fp64 oracle)
   dmd_small.npz        UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small env: fitted K,
                        the forecasts handed to the MPC, history, metrics
+  checkpoint_*.pt      files in the layout train.py:475-487 saves (reference model + Config.to_dict() + Adam state), for two
+                       tiny models whose forecasts are in forecast_generic_small.npz / forecast_lista_linear.npz
   backtest_cfg1.npz    UNMODIFIED reference run_backtest + KoopmanMPCStrategy + calculate_metrics on config 1
                        with the substitute mpc module (tests/golden/_shims/mpc.py): history, metrics, every
                        MPC call's (w_cur, yhat, w_opt, value)
@@ -285,7 +287,34 @@ def gen_dmd():
     print("dmd metrics", metrics, "K dtype", strat.K.dtype)
 
 
+def gen_checkpoints():
+    """The dictionary train.py:475-483 saves, written by the reference's own classes (make_model state_dict,
+    Config.to_dict, torch Adam) for the tiny models of forecast_generic_small.npz and forecast_lista_linear.npz."""
+    def one(name, cfg, N, d, sd_np):
+        model = ref_model.make_model(cfg, N * d)
+        model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd_np.items()}, strict=True)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        meta = {"tickers": [f"A{i}" for i in range(N)], "n_assets": N, "embedding_dim": d, "observation_size": N * d,
+                "train_samples": 40, "val_samples": 10, "test_samples": 10,
+                "train_date_range": ("2012-01-05", "2012-03-01"), "prices_shape": (80, N)}
+        torch.save({"step": 123, "epoch": 4, "model_state_dict": model.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                    "config": cfg.to_dict(), "metrics": {"loss": 0.5}, "finance_metadata": meta},
+                   os.path.join(HERE, f"checkpoint_{name}.pt"))
+    cfg = ref_config.get_config("finance_sparse")
+    cfg.MODEL.TARGET_SIZE = 8
+    cfg.MODEL.ENCODER.LAYERS = [16, 16]
+    one("generic_small", cfg, 3, 4, synthetic.generic_km_weights(1, 12, [16, 16], 8))
+    cfg = ref_config.get_config("lista")
+    cfg.MODEL.TARGET_SIZE = 16
+    sd, L = synthetic.lista_km_weights(4, 12, 16)
+    cfg.MODEL.ENCODER.LISTA.L = L
+    one("lista_linear", cfg, 3, 4, sd)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoints":
+        gen_checkpoints()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dmd":
         gen_dmd()
         sys.exit(0)
@@ -301,4 +330,5 @@ if __name__ == "__main__":
     gen_dmd()
     gen_rollouts()
     gen_markowitz()
+    gen_checkpoints()
     print("golden fixtures written to", HERE)

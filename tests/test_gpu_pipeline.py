@@ -275,3 +275,31 @@ def test_full_size_config2_properties():
         allr = do.destandardize(do.extract_current_returns(emb, N), mean[b], std[b])
         rh, _ = bo.run_backtest(bo.koopman_mpc_decider(yhat[j], 1e-3, 0.2), allr, rows - 1, H)
         assert np.allclose(hist[b][:, 0], np.asarray(rh)[:, 0], rtol=1e-6)
+
+
+def test_compare_strategies_table(golden, tmp_path):
+    """The four-strategy comparison of run_experiment.py:85-137 (Buy & Hold / Markowitz / DMD-MPC / Koopman-MPC) and
+    its full_comparison_metrics.csv: the DMD row must reproduce the golden run of the reference DMDStrategy."""
+    import pandas as pd
+    from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt, data_finance as df, engine, model as km, synthetic
+    g = golden("dmd_small.npz")
+    T, N, d, H = int(g["T"]), int(g["N"]), int(g["d"]), int(g["H"])
+    lr = synthetic.gbm_log_returns(int(g["log_returns_seed"]), T, N)
+    env = df.create_finance_env_from_returns(lr, embedding_dim=d, n_train_days=int(g["n_train_days"]),
+                                             n_val_days=int(g["n_val_days"]))
+    m = km.make_model(km.model_config("GenericKM", 16, [32, 32], enc_bias=True), N * d)
+    m.load_state_dict(synthetic.generic_km_weights(7, N * d, [32, 32], 16))
+    results, table = engine.compare_strategies(
+        m, env, bt.BacktestConfig(initial_capital=1e4, horizon=H, cost_coeff=1e-3),
+        bt.MPCConfig(horizon=H, cost_coeff=1e-3, max_turnover=0.2), out_dir=str(tmp_path))
+    assert list(table.index) == ["Buy & Hold", "Markowitz", "DMD-MPC", "Koopman-MPC"]
+    assert list(table.columns) == list(bt.METRIC_KEYS)
+    assert np.allclose(table.loc["DMD-MPC"].values.astype(float), g["metrics"], rtol=2e-3, atol=2e-4)
+    ns = len(env.test_dataset) - H
+    assert all(len(results[k]) == ns for k in results)
+    assert results["Buy & Hold"]["turnover"].abs().max() < 1e-12          # drifted weights are returned as the target
+    assert np.isfinite(table.values.astype(float)).all()
+    back = pd.read_csv(tmp_path / "full_comparison_metrics.csv", index_col=0)
+    assert np.allclose(back.values, table.values.astype(float), rtol=1e-12)
+    with pytest.raises(ValueError):
+        engine.compare_strategies(m, env, strategies=("nope",))
