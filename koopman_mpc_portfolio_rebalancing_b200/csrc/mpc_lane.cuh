@@ -44,6 +44,10 @@ __device__ __forceinline__ double rcp_fast(double x) {
   const double e = fma(-x, y, 1.0);
   return fma(y, fma(e, e, e), y);                            // relative error ~e^3
 }
+// a / b to within ~1.5 ulp in 7 instructions.  Used where a decision is STARTED or BOOKED: that code runs once per
+// decision, each problem of a block at its own time, so it is always fetched cold (the Newton loop has evicted it)
+// and its size, not its latency, is what it costs; an IEEE division is ~20 inline instructions plus a slow-path call.
+__device__ __forceinline__ double div_fast(double a, double b) { return a * rcp_fast(b); }
 
 // Position r * NB + c (lower triangle) of the K entries in the order LaneIpm::assemble_K emits them.
 template <int H>
@@ -201,7 +205,7 @@ struct LaneIpm {
     if (lane < NV) {
       const double2* p = reinterpret_cast<const double2*>(sm + OFF_TILE + lane * LD + 32 * warp);
       double m0 = 0.0, m1 = 0.0, s0 = 0.0, s1 = 0.0;
-#pragma unroll
+#pragma unroll 2                                     // once per decision: keep the code small (see div_fast)
       for (int m = 0; m < 16; ++m) {
         const double2 a = p[m];
         m0 = fmax(m0, a.x); m1 = fmax(m1, a.y); s0 += a.x; s1 += a.y;
@@ -570,6 +574,26 @@ struct LaneIpm {
     rp_ = rp; rd_ = rd;
   }
 
+  // R[k] = exp(y[k * stride + my asset]) in float32 like the reference (mpc.py:55), plus exp(y_extra) (the caller's
+  // realised return, backtest.py:193).  All loads are issued first; ONE rolled copy of the exp code then works through
+  // my column of the reduction tile (free between reductions; nobody else touches my column): see div_fast for why
+  // the code is kept small.  Call with the tile idle, i.e. after the previous reduction's results have been consumed.
+  __device__ __forceinline__ float load_returns(const float* y, size_t stride, float y_extra) {
+    static_assert(H + 1 <= SMALL_ROWS, "tile too small");
+    double* col = sm + OFF_TILE + tid;
+    float x[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) x[k] = valid ? y[(size_t)k * stride + tid] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) col[k * LD] = (double)x[k];
+    col[H * LD] = (double)y_extra;
+#pragma unroll 1
+    for (int k = 0; k <= H; ++k) col[k * LD] = (double)__double2float_rn(exp(col[k * LD]));
+#pragma unroll
+    for (int k = 0; k < H; ++k) R[k] = col[k * LD];
+    return (float)col[H * LD];
+  }
+
   // ---- the solve, in pieces (so that a caller can interleave several problems in lockstep) ---------------------
   //   begin()        screening + initial point.  Returns -1 (iterate) or a terminal status.
   //   check()        residuals of the current iterate.  Returns -1 (take another Newton step) or the final status.
@@ -609,9 +633,9 @@ struct LaneIpm {
       for (int k = 0; k < H; ++k) mxR[k] = ptotal_max(k);
       sb = ptotal(H);
     }
-    const double invN = 1.0 / (double)N;
-    const double eps = (tau <= 0.0) ? 0.1 : fmin(0.1, tau / 8.0);
-    const double b0 = (sb > 0.0) ? base / sb : invN;
+    const double invN = rcp_fast((double)N);
+    const double eps = (tau <= 0.0) ? 0.1 : fmin(0.1, tau * 0.125);
+    const double b0 = (sb > 0.0) ? div_fast(base, sb) : invN;
     const double w1 = valid ? fma(1.0 - eps, b0, eps * invN) : 1.0;
     double rho0[H];
     double absd0;
@@ -633,7 +657,7 @@ struct LaneIpm {
           kkt_[0] = kkt_[1] = kkt_[2] = CUDART_INF;
           return finish(ST_FAILED);
         }
-        dl0 = room0 / (2.0 * N); dlk = tau / (2.0 * N);
+        dl0 = 0.5 * room0 * invN; dlk = 0.5 * tau * invN;
       } else { dl0 = dlk = 0.05 * invN; }
       if (hc()) { sc0 = tau - (absd0 + dl0 * N); sck = tau - dlk * N; }
     }
@@ -649,7 +673,7 @@ struct LaneIpm {
       const double sck_ = (k == 0) ? sc0 : sck;
       double nu_k;
       if (dual_start) {
-        const double ir = 1.0 / rho0[k];
+        const double ir = rcp_fast(rho0[k]);
         nu_k = mxR[k] * ir + opt.dual_init;
         zw[k] = valid ? fma(-R[k], ir, nu_k) : 0.0;
         zp[k] = hu() ? 0.5 * fmax(lam + zeta0, opt.dual_init) : 0.0;   // floor for the uncapped case: see oracle
@@ -657,10 +681,10 @@ struct LaneIpm {
         if (tid == 0) U(U_ZC, k) = hc() ? zeta0 : 0.0;
       } else {
         nu_k = 1.0;
-        zw[k] = (hw() && valid) ? opt.mu0 / w[k] : 0.0;
-        zp[k] = hu() ? opt.mu0 / sp[k] : 0.0;
-        zq[k] = hu() ? opt.mu0 / sq[k] : 0.0;
-        if (tid == 0) U(U_ZC, k) = hc() ? opt.mu0 / sck_ : 0.0;
+        zw[k] = (hw() && valid) ? div_fast(opt.mu0, w[k]) : 0.0;
+        zp[k] = hu() ? div_fast(opt.mu0, sp[k]) : 0.0;
+        zq[k] = hu() ? div_fast(opt.mu0, sq[k]) : 0.0;
+        if (tid == 0) U(U_ZC, k) = hc() ? div_fast(opt.mu0, sck_) : 0.0;
       }
       if (tid == 0) { U(U_NU, k) = nu_k; U(U_SC, k) = sck_; U(U_CC, k) = 0.0; }
       if (!valid) { zw[k] = 1.0; zp[k] = 1.0; zq[k] = 1.0; }      // benign padding (never updated, never summed)
@@ -711,31 +735,34 @@ struct LaneIpm {
       }
     }
     sync();
-    int dres_h = 0;
-    if (valid) {
+    // The dual residual only decides anything once the gap is small (every acceptance test below, and the loose one
+    // in finish(), asks for gap < max(tol, kLooseGap)) or at the iteration cap: it is not evaluated before that (NaN).
+    const bool near = uni(gap < fmax(opt.tol, kLooseGap)) || (it_ == opt.max_iter + 1);
+    double dres = CUDART_NAN;
+    if (near) {
+      int dres_h = 0;
+      if (valid) {
 #pragma unroll
-      for (int k = 0; k < H; ++k) {
-        const double yk = zp[k] - zq[k];
-        const double yn = (k + 1 < H) ? zp[(k + 1 < H) ? k + 1 : 0] - zq[(k + 1 < H) ? k + 1 : 0] : 0.0;
-        const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (hw() ? zw[k] : 0.0) + (yk - yn);
-        dres_h = max(dres_h, hi_of(fabs(rdw)));
-        if (hu()) dres_h = max(dres_h, hi_of(fabs(lam - zp[k] - zq[k] + (hc() ? U(U_ZC, k) : 0.0))));
+        for (int k = 0; k < H; ++k) {
+          const double yk = zp[k] - zq[k];
+          const double yn = (k + 1 < H) ? zp[(k + 1 < H) ? k + 1 : 0] - zq[(k + 1 < H) ? k + 1 : 0] : 0.0;
+          const double rdw = fma(-R[k], U(U_IRHO, k), U(U_NU, k)) - (hw() ? zw[k] : 0.0) + (yk - yn);
+          dres_h = max(dres_h, hi_of(fabs(rdw)));
+          if (hu()) dres_h = max(dres_h, hi_of(fabs(lam - zp[k] - zq[k] + (hc() ? U(U_ZC, k) : 0.0))));
+        }
       }
-    }
-    double dres;
-    {
       int dummy = 0;
       block_max2i(dres_h, dummy);
-      dres = (dres_h > 0) ? hi_up(dres_h) : 0.0;
+      dres = (dres_h > 0) ? hi_up(dres_h) : 0.0;      // a NaN residual has a large positive high word: +inf-like
     }
     kkt_[0] = pres; kkt_[1] = dres; kkt_[2] = gap;
     gap_ = gap;
-    if (uni(!isfinite(dres + gap))) return finish(ST_FAILED);
+    if (uni(!isfinite(gap) || (near && !isfinite(dres)))) return finish(ST_FAILED);
     if (uni(pres < opt.tol && dres < opt.tol_dual && gap < opt.tol)) return ST_OPTIMAL;
     // flat directions (curvature << delta): see mpc_ipm.cuh
     if (uni(pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6)) return ST_INACCURATE;
     if (it_ == opt.max_iter + 1) return finish(ST_FAILED);
-    mu_ = gap / fmax(mcount_, 1.0);
+    mu_ = div_fast(gap, fmax(mcount_, 1.0));
     if (uni(pres < opt.tol && gap < opt.tol)) delta = fmax(0.3 * delta, 1e-9);   // endgame: shrink the proximal term
     return -1;
   }
@@ -760,8 +787,8 @@ struct LaneIpm {
     block_max2i(rph, rdh);
     const double rp = (rph > 0) ? hi_up(rph) : 0.0, rd = (rdh > 0) ? hi_up(rdh) : 0.0;
     // largest steps keeping slacks (aa) and duals (ab) non-negative: min(1, 1 / max ratio)
-    const double aa = (stepped && rp > 1.0) ? 1.0 / rp : 1.0;
-    const double ab = (stepped && rd > 1.0) ? 1.0 / rd : 1.0;
+    const double aa = (stepped && rp > 1.0) ? rcp_fast(rp) : 1.0;
+    const double ab = (stepped && rd > 1.0) ? rcp_fast(rd) : 1.0;
     if (phase == 0) {
       double g2 = 0.0;
       if (valid) {
@@ -774,7 +801,7 @@ struct LaneIpm {
       }
       if (hc() && tid < H) g2 = fma(fma(aa, dsc, U(U_SC, tid)), fma(ab, dzc, U(U_ZC, tid)), g2);
       g2 = block_sum1(g2);
-      const double ratio = (gap_ > 0.0) ? fmin(1.0, fmax(g2 / gap_, 0.0)) : 0.0;
+      const double ratio = (gap_ > 0.0) ? fmin(1.0, fmax(div_fast(g2, gap_), 0.0)) : 0.0;
       const double smu = ratio * ratio * ratio * mu_;
       const double dmp = fmin(1.0, fmin(aa, ab) * (1.0 / kCorrFull));   // short affine step: damp the corrector
 #pragma unroll
@@ -824,6 +851,16 @@ struct LaneIpm {
     iters = it_;
     kkt[0] = kkt_[0]; kkt[1] = kkt_[1]; kkt[2] = kkt_[2];
     return status;
+  }
+
+  // The first trade of the plan is the one the caller executes (backtest.py:131).  An iterate accepted after the
+  // factorisation broke down next to the optimum can sit ~1e-5 outside the turnover cap (the cap's slack is stepped,
+  // not re-derived from w): pull that trade back onto the cap along its own direction.
+  __device__ __forceinline__ void clip_first_trade(double w0) {
+    if (!uni(tau > 0.0)) return;
+    sync();
+    const double t = block_sum1(valid ? fabs(w[0] - w0) : 0.0);
+    if (t > tau && valid) w[0] = fma(div_fast(tau, t), w[0] - w0, w0);
   }
 
   // maximised objective (mpc.py:104) of the plan held in w[]; same value in every thread

@@ -67,7 +67,7 @@ mpc_solve_lane_kernel(MpcSolveArgs A, int want) {
     int iters; double kkt[3];
     const int st = s.solve(w0, N, lam, tau, A.allow_short != 0, opt, iters, kkt);
     double val = CUDART_NAN;
-    if (st <= ST_INACCURATE) val = s.objective(w0);
+    if (st <= ST_INACCURATE) { s.clip_first_trade(w0); val = s.objective(w0); }
     if (s.valid) {
 #pragma unroll
       for (int k = 0; k < H; ++k) A.w_out[((size_t)p * H + k) * N + s.tid] = s.w[k];
@@ -113,7 +113,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
   // ---- per-thread state of the slot's current backtest ----------------------------------------------------------
   int b = 0, t = 0;
   double wc = 0.0;                                 // my asset's current weight
-  float y_next = 0.0f;                             // realised log-return of my asset on the day after the decision
+  float e_next = 1.0f;                             // exp(realised log-return of my asset on the day after the decision)
   auto fetch = [&]() -> bool {                     // next backtest of this slot (dynamic: iteration counts differ)
     if (s.tid == 0) next_b[slot] = atomicAdd(A.work_counter, 1);
     s.sync();
@@ -146,12 +146,8 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         if (uni(need_start)) {
           const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
           const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
-          if (s.valid) {
-#pragma unroll
-            for (int k = 0; k < H; ++k)
-              s.R[k] = (double)exp_cr32_lane(A.yhat[yb + ((size_t)t * H + k) * N + s.tid]);   // mpc.py:55
-          }
-          y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + s.tid] : 0.0f;
+          const float y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + s.tid] : 0.0f;
+          e_next = s.load_returns(A.yhat + yb + (size_t)t * H * N, (size_t)N, y_next);      // mpc.py:55
           st = s.begin(wc, N, A.lam ? A.lam[b] : A.lam0, A.tau ? A.tau[b] : A.tau0, A.allow_short != 0, opt);
           need_start = false;
         }
@@ -159,19 +155,28 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         if (uni(st < 0)) break;                                    // take a Newton step
         // ---- the decision is made: portfolio step (backtest.py:175-217) ---------------------------------------
         const bool market = (t + 1 < A.rows);
-        const double wn = s.valid ? s.w[0] : 0.0;                                          // backtest.py:131
+        double wn = s.valid ? s.w[0] : 0.0;                                                // backtest.py:131
         float r32 = 0.0f;
-        if (s.valid && market) r32 = __fsub_rn(exp_cr32_lane(y_next), 1.0f);               // backtest.py:193
-        double v[2] = {fabs(wn - wc), wn * (double)r32}, T[2];
+        if (s.valid && market) r32 = __fsub_rn(e_next, 1.0f);                              // backtest.py:193
+        double v[3] = {fabs(wn - wc), wn * (double)r32, wc * (double)r32}, T[3];
         s.sync();
-        s.template block_sum<2>(v, T);
-        const double turnover = T[0];
-        const double port_ret = market ? T[1] : 0.0;
+        s.template block_sum<3>(v, T);
+        double turnover = T[0];
+        double port_ret = market ? T[1] : 0.0;
+        if (s.tau > 0.0 && turnover > s.tau) {
+          // An iterate accepted after the factorisation broke down next to the optimum (status optimal_inaccurate)
+          // can sit ~1e-5 outside the turnover cap, whose slack the iteration does not re-derive from w: pull the
+          // trade back onto the cap along its own direction (budget and sign constraints are kept).
+          const double sc = div_fast(s.tau, turnover);
+          wn = fma(sc, wn - wc, wc);
+          if (market) port_ret = fma(sc, T[1] - T[2], T[2]);
+          turnover = s.tau;
+        }
         wc = wn;
         if (market) {
           double denom = 1.0 + port_ret;
           if (fabs(denom) < 1e-8) denom = 1e-8;
-          wc = wn * (double)__fadd_rn(1.0f, r32) / denom;                                  // (1.0 + f32) stays f32
+          wc = div_fast(wn * (double)__fadd_rn(1.0f, r32), denom);                         // (1.0 + f32) stays f32
         }
         t += A.rebalance_freq;
         const bool last = (t >= A.n_steps);
@@ -190,11 +195,11 @@ backtest_lane_kernel(BacktestArgs A, int want) {
           if (k.n == 0) k.v_first = V;
           const int n = ++k.n;
           const double dlt = port_ret - k.mean;
-          k.mean += dlt / (double)n;
+          k.mean += div_fast(dlt, (double)n);
           k.m2 += dlt * (port_ret - k.mean);
           k.cum *= (1.0 + port_ret);
           k.peak = fmax(k.peak, k.cum);
-          k.maxdd = fmin(k.maxdd, (k.cum - k.peak) / k.peak);
+          k.maxdd = fmin(k.maxdd, div_fast(k.cum - k.peak, k.peak));
           k.sum_turn += turnover;
           if (last) {                                          // calculate_metrics (backtest.py:221-249)
             double* m = A.metrics + (size_t)b * 5;
