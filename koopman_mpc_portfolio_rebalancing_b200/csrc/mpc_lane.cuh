@@ -661,7 +661,8 @@ struct LaneIpm {
       } else { dl0 = dlk = 0.05 * invN; }
       if (hc()) { sc0 = tau - (absd0 + dl0 * N); sck = tau - dlk * N; }
     }
-    const bool dual_start = hw() && uni(opt.dual_init > 0.0);
+    // FIX kernels are only launched with dual_init > 0 (lane_fix_plan): the mu0-based start is compiled out there
+    const bool dual_start = FIX ? true : (hw() && uni(opt.dual_init > 0.0));
     const double zeta0 = hc() ? opt.dual_init : 0.0;
 #pragma unroll
     for (int k = 0; k < H; ++k) {

@@ -201,14 +201,15 @@ backtest_lane_kernel(BacktestArgs A, int want) {
           k.peak = fmax(k.peak, k.cum);
           k.maxdd = fmin(k.maxdd, div_fast(k.cum - k.peak, k.peak));
           k.sum_turn += turnover;
-          if (last) {                                          // calculate_metrics (backtest.py:221-249)
+          if (__builtin_expect(last, 0)) {                     // calculate_metrics (backtest.py:221-249)
             double* m = A.metrics + (size_t)b * 5;
-            const double sd = sqrt(k.m2 / (double)n);
-            m[0] = sqrt(252.0) * k.mean / (sd + 1e-8);
+            const double inv_n = rcp_fast((double)n);
+            const double sd = sqrt(k.m2 * inv_n);
+            m[0] = div_fast(sqrt(252.0) * k.mean, sd + 1e-8);
             m[1] = k.maxdd;
-            m[2] = k.sum_turn / (double)n;
+            m[2] = k.sum_turn * inv_n;
             m[3] = V;
-            m[4] = V / k.v_first - 1.0;
+            m[4] = div_fast(V, k.v_first) - 1.0;
             if (A.solve_stats) {
               long long* ss = A.solve_stats + (size_t)b * 4;
               ss[0] = k.n_opt; ss[1] = k.n_inacc; ss[2] = k.n_fail; ss[3] = k.it_total;
@@ -274,9 +275,9 @@ static int lane_blocks_per_sm(K kernel, int threads, size_t smem) {
 }
 
 // which kernel(s) to launch: 1 = FIX only, 0 = generic only, 2 = both, gated on the device flag
-static int lane_fix_plan(const double* lam, const double* tau, double lam0, double tau0, int allow_short, int n, int* flag,
-                         cudaStream_t st) {
-  if (allow_short) return 0;
+static int lane_fix_plan(const double* lam, const double* tau, double lam0, double tau0, int allow_short, double dual_init,
+                         int n, int* flag, cudaStream_t st) {
+  if (allow_short || !(dual_init > 0.0)) return 0;
   if (!lam && !tau) return (lam0 > 0.0 && tau0 > 0.0) ? 1 : 0;
   lane_flags_kernel<<<1, 256, 0, st>>>(lam, tau, lam0, tau0, n, flag);
   return 2;
@@ -287,7 +288,7 @@ static int launch_mpc_lane(const MpcSolveArgs& A, int sm_count, cudaStream_t st)
   const size_t smem = (size_t)LaneIpm<H, G, (G > 4 || H > 5), false>::SMEM_DOUBLES * sizeof(double);
   static const int bps0 = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, false>, 32 * G, smem);
   static const int bps1 = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, true>, 32 * G, smem);
-  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.P, A.fix_flag, st);
+  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.P, A.fix_flag, st);
   auto nblocks = [&](int bps) { int b = A.P < sm_count * bps ? A.P : sm_count * bps; return b < 1 ? 1 : b; };
   if (plan != 0) mpc_solve_lane_kernel<H, G, true><<<nblocks(bps1), 32 * G, smem, st>>>(A, plan == 2 ? 1 : -1);
   if (plan != 1) mpc_solve_lane_kernel<H, G, false><<<nblocks(bps0), 32 * G, smem, st>>>(A, plan == 2 ? 0 : -1);
@@ -301,7 +302,7 @@ static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) 
   const size_t smem = (size_t)P * LaneIpm<H, G, (G > 4 || H > 5), false>::SMEM_DOUBLES * sizeof(double) + pad;
   static const int bps0 = lane_blocks_per_sm(backtest_lane_kernel<H, G, P, false>, 32 * G * P, smem);
   static const int bps1 = lane_blocks_per_sm(backtest_lane_kernel<H, G, P, true>, 32 * G * P, smem);
-  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.B, A.fix_flag, st);
+  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.B, A.fix_flag, st);
   const int want = (A.B + P - 1) / P;
   auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };
   if (plan != 0) backtest_lane_kernel<H, G, P, true><<<nblocks(bps1), 32 * G * P, smem, st>>>(A, plan == 2 ? 1 : -1);
