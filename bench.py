@@ -291,16 +291,17 @@ def run_gpu_arm(args):
                    "peak_source": f"{peak_src} bf16 sustained / 3 (three fp16 MMAs per fp32-accurate product)",
                    "flops_per_decision": fpd, "flops_per_decision_unfolded": flops_per_decision(w), "ms": st_fc}
         bt_gbs = hbm_bytes_bt / (st_bt * 1e-3) / 1e9
-        # ncu --set full (profiles/r1_backtest_lane_kernel.txt): dram read+write 1249 B per decision
+        # ncu --set full (profiles/r1_backtest_lane_kernel.txt): dram read+write 1263 B per decision
         roof_bt = {"kernel": f"backtest_{args.mpc_kernel}_kernel (fp64 interior-point MPC + portfolio step, persistent)", "bound": "hbm",
                    "achieved": bt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bt_gbs / hbm_peak,
-                   "traffic": 1249.0 * decisions_per_step_rank if args.mpc_kernel == "lane" else None,
+                   "traffic": 1263.0 * decisions_per_step_rank if args.mpc_kernel == "lane" else None,
                    "bytes_per_decision": 8 * N + 8 * H * N + 32,
                    "note": "the solver streams 1.2 KB per decision and is bound by instruction issue / dependency latency, not by HBM; "
                            "see `compute` (ncu --set full capture in profiles/r1_backtest_lane_kernel.txt) and solver.iterations_per_decision",
                    "compute": {"source": "ncu capture of the same kernel, profiles/r1_backtest_lane_kernel.txt (not measured live)",
-                               "fp64_pipe_busy_pct": 22.9, "issue_slots_busy_pct": 25.5, "ipc_per_sm": 1.02,
-                               "warp_instructions_per_decision": 55000, "warps_per_sm": 8, "registers_per_thread": 255},
+                               "fp64_pipe_busy_pct": 23.9, "issue_slots_busy_pct": 27.0, "ipc_per_sm": 1.08,
+                               "shared_memory_pipe_busy_pct": 46.9,
+                               "warp_instructions_per_decision": 54100, "warps_per_sm": 8, "registers_per_thread": 255},
                    "ms": st_bt}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -176,3 +176,32 @@ def test_uncapped_small_lambda_converges():
         assert ref.status == 0
         assert abs(val[p] - ref.value) <= OBJ_RTOL * max(abs(ref.value), OBJ_FLOOR)
     assert its.mean() < 16
+
+
+def test_mu0_start_runs_on_generic_kernel(mpc_kernel_layout):
+    """KMPC_DUAL_INIT=0 (read once per process, hence the subprocess) selects the mu0-based starting point, which only
+    the generic lane kernel instantiation contains: defaults (lam > 0, tau > 0, long-only) must then be routed away
+    from the FIX instantiation and still reach the oracle's optimum."""
+    if mpc_kernel_layout != "lane":
+        pytest.skip("routing of the lane kernels")
+    import os, subprocess, sys
+    code = r'''
+import numpy as np, torch
+from koopman_mpc_portfolio_rebalancing_b200 import mpc
+from oracle import mpc_oracle as mo
+rng = np.random.default_rng(5)
+N, H, P = 50, 5, 16
+w0 = np.stack([rng.dirichlet(np.ones(N)) for _ in range(P)])
+y = (3e-4 + rng.standard_normal((P, H, N)) * 0.01).astype(np.float32)
+out = mpc.solve_mpc_batch(torch.from_numpy(w0).cuda(), torch.from_numpy(y).cuda())    # lam 1e-3, tau 0.2
+val = out["value"].cpu().numpy(); st = out["status"].cpu().numpy(); W = out["w"].cpu().numpy()
+for p in range(P):
+    ref = mo.solve_structured(w0[p], y[p], 1e-3, 0.2)
+    assert st[p] == 0 and abs(val[p] - ref.value) <= 1e-6 * max(abs(ref.value), 1e-3), (p, st[p], val[p], ref.value)
+    assert np.abs(W[p] - ref.w).max() < 1e-4
+print("OK", float(out["iterations"].float().mean()))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, KMPC_DUAL_INIT="0", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
