@@ -12,7 +12,7 @@
 //
 // Same structure as gemm_tc.cu: one CTA per SM, persistent over 128 x 128 output tiles, k-blocks of 64 halves
 // (= one 128-byte swizzle row), 3-stage TMA ring of (A_hi, A_lo, W_hi, W_lo) boxes, warp 0 TMA producer, warp 1
-// single-thread MMA issuer (12 tcgen05.mma.kind::f16 per stage), warp 2 TMEM allocator, warps 4..7 epilogue
+// single-thread MMA issuer (12 tcgen05.mma.kind::f16 per stage), warp 2 TMEM allocator, warps 4..11 epilogue: two per TMEM lane quarter, half of the columns each — the epilogue is not overlapped with the next tile's MMAs (the four accumulators fill TMEM), so its length counts
 // (bias / activation / de-standardise, then either the fp16 pair of the next layer or fp32 output).
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -29,8 +29,9 @@ constexpr int BM = 128, BN = 128, BK = 64;          // BK halves = 128 bytes = o
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 2;             // 16 KB (BM == BN)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, W_hi, W_lo
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, half of the tile's columns each
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;                      // 3 hi accumulators + 1 lo accumulator of 128 fp32 columns
 constexpr int NUM_HI = 3;
 constexpr uint32_t SPIN_LIMIT = 1u << 28;           // bounded waits: trap instead of hanging the GPU
@@ -209,7 +210,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tfull_bar[0], 1); mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tempty_bar[0], EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -273,6 +274,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
     const int q = warp & 3;                                        // TMEM lane quarter this warp may access
+    constexpr int CB_PER_WARP = (BN / 16) / (EPI_WARPS / 4);       // column blocks of 16 per warp
+    const int cb0 = ((warp - EPI_WARP0) >> 2) * CB_PER_WARP;
     uint32_t acc_phase = 0;
     const int nhi = p.k_blocks < NUM_HI ? p.k_blocks : NUM_HI;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -286,7 +289,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (long long)((int)(m + p.row0) / p.stat_rows_per_group) : 0;
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 16; ++cb) {
+      for (int cb = cb0; cb < cb0 + CB_PER_WARP; ++cb) {
         uint32_t v[16], u0[16], u1[16], u2[16];
         float acc[16];
         tmem_ld16_nowait(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);    // lo products, scaled by 2^11
