@@ -1,3 +1,5 @@
+"""Diagnostic: run BASELINE config 2 at full size on the GPU and list every decision whose first-stage turnover exceeds the
+cap (should print `violations 0`) together with the solver outcome counts.  Usage: python scripts/debug_cap.py"""
 import numpy as np, torch, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
