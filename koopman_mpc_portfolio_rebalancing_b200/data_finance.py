@@ -139,6 +139,13 @@ def time_delay_embedding(data: np.ndarray, embedding_dim: int) -> np.ndarray:
     return np.ascontiguousarray(data).ravel()[embedding_index(T, n_assets, embedding_dim)]
 
 
+def verify_embedding_shift(embedded, n_assets: int, embedding_dim: int) -> bool:
+    """Y_{t+1}[1:d] == Y_t[0:d-1] for every consecutive pair of embedded rows (data_finance.py:515-540), vectorised."""
+    e = np.asarray(embedded.detach().cpu() if hasattr(embedded, "detach") else embedded)
+    e = e.reshape(len(e), embedding_dim, n_assets)
+    return bool(np.allclose(e[1:, 1:], e[:-1, :-1]))
+
+
 def split_rows(n_rows: int, n_train_days: int, n_val_days: int, embedding_dim: int):
     """Row ranges (train, val, test) in the embedded array; embedded row i carries the date of raw day i+d-1
     (data_finance.py:334-343)."""
@@ -224,6 +231,22 @@ class FinanceEnv:
         mean = torch.from_numpy(self.stats.mean).float().to(standardized.device)
         std = torch.from_numpy(self.stats.std).float().to(standardized.device)
         return standardized * std + mean
+
+    def get_test_sequences(self, num_sequences: int = 100, max_length: int = 200):
+        """(initial_states [S, obs], future_states [L, S, obs]) of consecutive test observations, start rows spread
+        evenly over the test split (data_finance.py:672-715): the inputs of ``evaluation.evaluate_finance``.  One
+        gather on the device the test split lives on instead of the reference's per-sequence stack."""
+        import torch
+        test_data = self.test_dataset.data
+        n_samples = len(test_data)
+        actual_length = min(max_length, n_samples - 1)
+        actual_num_seq = min(num_sequences, n_samples - actual_length)
+        if actual_num_seq <= 0:
+            raise ValueError(f"Not enough test data for {num_sequences} sequences of length {max_length}")
+        step = (n_samples - actual_length) // actual_num_seq
+        starts = torch.arange(actual_num_seq, device=test_data.device) * step
+        offs = torch.arange(1, actual_length + 1, device=test_data.device)
+        return test_data[starts], test_data[(offs[:, None] + starts[None, :])]
 
     # ---- device views for the batch-resident path ----
     def series_device(self):

@@ -3,8 +3,9 @@
 ``rollout_no_reencode`` is the batched twin of the strategy's forecast loop (encode once, then H x step_latent +
 decode) and runs as one fused chain (``kmpc_rollout``); the re-encoding variants compose ``encode`` /
 ``step_latent`` / ``decode`` (each one launch of the GEMM kernels over the whole batch).  Like the reference, a
-non-finite prediction marks the remaining steps as NaN.  Plots and the ODE-system evaluation driver of
-evaluation.py are outside the hot path.
+non-finite prediction marks the remaining steps as NaN.  ``evaluate_finance`` is the multi-horizon scoring of
+train.py:221-300 over those rollouts (per-horizon MSE / L2 curves of every mode, best mode): what a sweep uses to pick
+a model on the device.  Plots and the ODE-system evaluation driver of evaluation.py are outside the hot path.
 """
 from __future__ import annotations
 
@@ -58,3 +59,48 @@ def rollout_periodic_reencode(model, x0, horizon: int, period: int):
         if (step + 1) % period == 0:
             latent = model.encode(x_pred)
     return _finish(preds, horizon)
+
+
+def evaluate_finance(model, initial_states, future_states, max_horizon: int = 50, periodic_reencode_periods=(5, 10, 25)):
+    """Multi-step prediction error of a model on finance test data (train.py:221-300): same arguments, same keys in the
+    returned dictionary.  initial_states [batch, obs], future_states [horizon, batch, obs]; curves are per horizon step
+    (MSE over batch and features, L2 norm over features averaged over the batch), returned on the host like the
+    reference returns them."""
+    import torch
+    model.eval()
+    dev = model.device
+    horizon = min(int(max_horizon), int(future_states.shape[0]))
+    initial_states = torch.as_tensor(initial_states).to(dev, dtype=torch.float32)
+    true = torch.as_tensor(future_states)[:horizon].to(dev, dtype=torch.float32)
+    predictions, mse_curves, l2_curves = {}, {}, {}
+
+    def score(name, pred):
+        predictions[name] = pred
+        mse_curves[name] = ((pred - true) ** 2).mean(dim=(1, 2))
+        l2_curves[name] = torch.norm(pred - true, dim=-1).mean(dim=1)
+
+    score("every_step", rollout_every_step_reencode(model, initial_states, horizon))
+    score("no_reencode", rollout_no_reencode(model, initial_states, horizon))
+    for period in periodic_reencode_periods:
+        score(f"periodic_{period}", rollout_periodic_reencode(model, initial_states, horizon, period=period))
+    mean_mses = {mode: curve.mean().item() for mode, curve in mse_curves.items()}
+    best_mode = min(mean_mses, key=mean_mses.get)
+    return {
+        "mse_reencode": mse_curves["every_step"].cpu(),
+        "mse_no_reencode": mse_curves["no_reencode"].cpu(),
+        "l2_reencode": l2_curves["every_step"].cpu(),
+        "l2_no_reencode": l2_curves["no_reencode"].cpu(),
+        "mean_mse_reencode": mean_mses["every_step"],
+        "mean_mse_no_reencode": mean_mses["no_reencode"],
+        "final_mse_reencode": mse_curves["every_step"][-1].item(),
+        "final_mse_no_reencode": mse_curves["no_reencode"][-1].item(),
+        "pred_reencode": predictions["every_step"].cpu(),
+        "pred_no_reencode": predictions["no_reencode"].cpu(),
+        "true": true.cpu(),
+        "mse_curves": {k: v.cpu() for k, v in mse_curves.items()},
+        "l2_curves": {k: v.cpu() for k, v in l2_curves.items()},
+        "mean_mses": mean_mses,
+        "predictions": {k: v.cpu() for k, v in predictions.items()},
+        "best_mode": best_mode,
+        "best_mse": mean_mses[best_mode],
+    }

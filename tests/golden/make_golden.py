@@ -4,6 +4,7 @@ importable in the build container only).  Run:  python tests/golden/make_golden.
 Nothing under tests/ reads /root/reference at test time: the GPU box does not have it.  The fixtures are
 small .npz files; large weights are regenerated from seeds by koopman_mpc_portfolio_rebalancing_b200.synthetic.
 
+  test_sequences_small.npz  FinanceEnv.get_test_sequences / verify_embedding_shift of the data_small env
   data_small.npz       compute_standardization_stats / create_finance_splits / time_delay_embedding
                        (data_finance.py:211-353) on a synthetic business-day frame
   forecast_*.npz       model.encode / step_latent / decode + extract/destandardize rollouts
@@ -71,6 +72,13 @@ def gen_data_small():
     np.savez(os.path.join(HERE, "data_small.npz"), log_returns=frame.values, n_train_days=40, n_val_days=20,
              d=d, mean=stats.mean, std=stats.std, standardized=std_all, embedded=emb, train=tr, val=va, test=te,
              test_len=len(env.test_dataset))
+    # FinanceEnv.get_test_sequences (data_finance.py:672-715) and verify_embedding_shift (:515-540) of the same env
+    i1, f1 = env.get_test_sequences(num_sequences=5, max_length=7)
+    i2, f2 = env.get_test_sequences()                       # defaults: clamped by the 20-row test split
+    np.savez(os.path.join(HERE, "test_sequences_small.npz"), init_5_7=i1.numpy(), future_5_7=f1.numpy(),
+             init_default=i2.numpy(), future_default=f2.numpy(),
+             shift_ok=ref_data.verify_embedding_shift(emb, 3, d),
+             shift_broken=ref_data.verify_embedding_shift(emb[::2], 3, d))
 
 
 def ref_forecast(model, env_like, obs, H):
@@ -253,6 +261,17 @@ def gen_rollouts():
         out[f"{name}::no_reencode"] = ref_eval.rollout_no_reencode(model, x0, 6).numpy()
         out[f"{name}::every_step"] = ref_eval.rollout_every_step_reencode(model, x0, 6).numpy()
         out[f"{name}::periodic2"] = ref_eval.rollout_periodic_reencode(model, x0, 6, 2).numpy()
+        # train.evaluate_finance (train.py:221-300) against a seeded "future": curves of every mode, best mode
+        import train as ref_train
+        fut = np.random.default_rng(77).standard_normal((8, x0.shape[0], x0.shape[1])).astype(np.float32) * 0.5
+        ev = ref_train.evaluate_finance(model, x0, torch.from_numpy(fut), max_horizon=6, periodic_reencode_periods=[2, 3])
+        out[f"{name}::eval_future"] = fut
+        for mode, curve in ev["mse_curves"].items():
+            out[f"{name}::eval_mse::{mode}"] = curve.numpy()
+            out[f"{name}::eval_l2::{mode}"] = ev["l2_curves"][mode].numpy()
+        out[f"{name}::eval_best"] = np.array(list(ev["mse_curves"]).index(ev["best_mode"]))
+        out[f"{name}::eval_scalars"] = np.array([ev["mean_mse_reencode"], ev["mean_mse_no_reencode"],
+                                                 ev["final_mse_reencode"], ev["final_mse_no_reencode"], ev["best_mse"]])
     np.savez(os.path.join(HERE, "rollouts_small.npz"), **out)
     print("rollouts", {k: v.shape for k, v in out.items()})
 
@@ -312,6 +331,9 @@ def gen_checkpoints():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "data":
+        gen_data_small()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoints":
         gen_checkpoints()
         sys.exit(0)

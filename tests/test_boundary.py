@@ -104,3 +104,24 @@ def test_result_frames_and_parquet(tmp_path):
     assert np.array_equal(back["backtest"].values, np.arange(10, 17)) and np.allclose(back[list(bt.METRIC_KEYS)].values, met)
     long = pd.read_parquet(str(tmp_path / "out.history.parquet"))
     assert len(long) == 28 and np.allclose(long[long.backtest == 12][list(bt.HISTORY_COLS)].values, hist[2])
+
+
+def test_test_sequences_and_shift_check_vs_reference(golden):
+    """FinanceEnv.get_test_sequences (data_finance.py:672-715: the feeder of evaluate_finance) and
+    verify_embedding_shift (:515-540) on host tensors, against the reference's own outputs for the data_small env."""
+    import numpy as np
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df
+    g = golden("data_small.npz")
+    r = golden("test_sequences_small.npz")
+    ds = lambda a: df.FinanceDataset(a, None, 1)
+    env = df.FinanceEnv(ds(g["train"]), ds(g["val"]), ds(g["test"]), df.FinanceStats(g["mean"], g["std"], []),
+                        {"n_assets": 3, "embedding_dim": int(g["d"])})
+    i1, f1 = env.get_test_sequences(num_sequences=5, max_length=7)
+    assert np.array_equal(i1.numpy(), r["init_5_7"]) and np.array_equal(f1.numpy(), r["future_5_7"])
+    i2, f2 = env.get_test_sequences()
+    assert np.array_equal(i2.numpy(), r["init_default"]) and np.array_equal(f2.numpy(), r["future_default"])
+    tiny = df.FinanceEnv(ds(g["train"]), ds(g["val"]), ds(g["test"][:2]), env.stats, env.metadata)
+    i3, f3 = tiny.get_test_sequences(3, 5)                  # clamps to what the split holds
+    assert i3.shape == (1, 12) and f3.shape == (1, 1, 12)
+    assert df.verify_embedding_shift(g["embedded"], 3, int(g["d"])) == bool(r["shift_ok"]) is True
+    assert df.verify_embedding_shift(g["embedded"][::2], 3, int(g["d"])) == bool(r["shift_broken"]) is False

@@ -268,3 +268,31 @@ def test_rollout_generators_vs_reference(golden, name):
             assert rowwise_rel(v[h], want[h]) < FORECAST_RTOL, (k, h)
     with pytest.raises(ValueError):
         ev.rollout_periodic_reencode(m, x0, 3, 0)
+
+
+@pytest.mark.parametrize("name", ["generic_small", "lista_linear"])
+def test_evaluate_finance_vs_reference(golden, name):
+    """evaluation.evaluate_finance against train.evaluate_finance of the reference (train.py:221-300) on the same model,
+    initial states and seeded future: per-horizon MSE / L2 curves of every rollout mode, scalars and best mode."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import evaluation as ev
+    g = golden(f"forecast_{name}.npz")
+    r = golden("rollouts_small.npz")
+    meta = golden(f"forecast_{name}_meta.npz") if name.startswith("lista") else None
+    m = build(name, g, meta)
+    m.load_state_dict(sd_from_npz(g))
+    out = ev.evaluate_finance(m, torch.from_numpy(g["obs"]), torch.from_numpy(r[f"{name}::eval_future"]), max_horizon=6,
+                              periodic_reencode_periods=[2, 3])
+    modes = ["every_step", "no_reencode", "periodic_2", "periodic_3"]
+    assert list(out["mse_curves"]) == modes and out["true"].shape == (6,) + g["obs"].shape
+    for mode in modes:
+        assert np.allclose(out["mse_curves"][mode].numpy(), r[f"{name}::eval_mse::{mode}"], rtol=1e-5)
+        assert np.allclose(out["l2_curves"][mode].numpy(), r[f"{name}::eval_l2::{mode}"], rtol=1e-5)
+        assert not out["predictions"][mode].is_cuda
+    assert out["best_mode"] == modes[int(r[f"{name}::eval_best"])]
+    want = r[f"{name}::eval_scalars"]
+    got = [out["mean_mse_reencode"], out["mean_mse_no_reencode"], out["final_mse_reencode"], out["final_mse_no_reencode"],
+           out["best_mse"]]
+    assert np.allclose(got, want, rtol=1e-5)
+    assert torch.equal(out["mse_reencode"], out["mse_curves"]["every_step"])
+    assert torch.equal(out["pred_no_reencode"], out["predictions"]["no_reencode"])
