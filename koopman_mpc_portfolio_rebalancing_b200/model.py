@@ -99,16 +99,19 @@ class KoopmanMachine:
     def _desc(self, n_assets: int, delay: int):
         raise NotImplementedError
 
-    def native(self, n_assets: Optional[int] = None, delay: Optional[int] = None):
+    def native(self, n_assets: Optional[int] = None, delay: Optional[int] = None, raw_step: bool = False):
         """kmpc_model* for a given split of observation_size into (n_assets, delay).  encode/decode do not depend
-        on the split; the in-place window forecast does."""
+        on the split; the in-place window forecast does.  ``raw_step``: the same weights with the latent
+        normalisation switched off (``z @ kmat`` of rollout_latent_discrete, model.py:527-556)."""
         if n_assets is None:
             n_assets, delay = self.observation_size, 1
-        key = (int(n_assets), int(delay))
+        key = (int(n_assets), int(delay), bool(raw_step))
         if key not in self._native:
             if key[0] * key[1] != self.observation_size:
                 raise ValueError(f"n_assets*delay = {key[0] * key[1]} != observation_size {self.observation_size}")
-            desc, keep = self._desc(*key)
+            desc, keep = self._desc(key[0], key[1])
+            if raw_step:
+                desc.norm_fn = 0
             out = C.c_void_p()
             h = _capi.Handle.get(self.device.index or 0)
             _capi.check(_capi.lib().kmpc_model_load(h.ptr, C.byref(desc), C.byref(out)))
@@ -147,6 +150,28 @@ class KoopmanMachine:
             _capi.check(_capi.lib().kmpc_step_latent(self._handle().ptr, self.native(), _capi.ptr(y2), y2.shape[0],
                                                      _capi.ptr(out), _capi.stream_ptr(self.device.index or 0)))
         return out.reshape(*lead, self.target_size)
+
+    def rollout_latent_discrete(self, z0, num_steps: int):
+        """z_{t+k} = z_0 K^k WITHOUT the latent normalisation (model.py:527-556): [batch, num_steps+1, target_size],
+        z0 at index 0."""
+        import torch
+        z, lead = self._rows(z0, self.target_size)
+        traj = [z]
+        for _ in range(int(num_steps)):
+            nxt = torch.empty_like(z)
+            if z.shape[0]:
+                _capi.check(_capi.lib().kmpc_step_latent(self._handle().ptr, self.native(raw_step=True), _capi.ptr(z), z.shape[0],
+                                                         _capi.ptr(nxt), _capi.stream_ptr(self.device.index or 0)))
+            z = nxt
+            traj.append(z)
+        return torch.stack(traj, dim=1)
+
+    def rollout_sequence(self, x0, num_steps: int):
+        """encode once, roll the latent state, decode every state (model.py:558-585): [batch, num_steps+1, observation_size];
+        index 0 is the reconstruction of x0."""
+        z_traj = self.rollout_latent_discrete(self.encode(x0), num_steps)
+        b, n, _ = z_traj.shape
+        return self.decode(z_traj.reshape(b * n, self.target_size)).reshape(b, n, self.observation_size)
 
     def decode(self, y):
         """latent [..., target_size] -> observations [..., observation_size] (model.py:250-259)."""

@@ -11,6 +11,7 @@ small .npz files; large weights are regenerated from seeds by koopman_mpc_portfo
                        (model.py, backtest.py:85-121) for GenericKM (relu/id, tanh/ball, gelu + MLP decoder)
                        and LISTAKM (linear and MLP encoder); weights stored (tiny models)
   forecast_cfg1.npz    finance_sparse preset, TARGET_SIZE=128, N=10, d=20 (BASELINE config 1); weights from seed
+  sequences_small.npz  model.rollout_latent_discrete / rollout_sequence (model.py:527-585) on three tiny models
   rollouts_small.npz   evaluation.rollout_{no,every_step,periodic}_reencode (evaluation.py:44-134) on two tiny models
   markowitz_small.npz  UNMODIFIED reference MarkowitzStrategy + run_backtest (substitute mean-variance solve = fp64 oracle)
   dmd_small.npz        UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small env: fitted K,
@@ -276,6 +277,32 @@ def gen_rollouts():
     print("rollouts", {k: v.shape for k, v in out.items()})
 
 
+def gen_sequences():
+    """reference rollout_latent_discrete / rollout_sequence (model.py:527-585; NO latent normalisation in the unroll,
+    unlike step_latent) on three of the tiny forecast models, the ball-normalised one included."""
+    out = {}
+    for name in ("generic_small", "generic_tanh_ball", "lista_linear"):
+        g = np.load(os.path.join(HERE, f"forecast_{name}.npz"))
+        sd = {k[4:]: g[k] for k in g.files if k.startswith("sd::")}
+        if name == "generic_small":
+            cfg = ref_config.get_config("finance_sparse"); cfg.MODEL.TARGET_SIZE = 8; cfg.MODEL.ENCODER.LAYERS = [16, 16]
+        elif name == "generic_tanh_ball":
+            cfg = ref_config.get_config("generic"); cfg.MODEL.TARGET_SIZE = 8; cfg.MODEL.ENCODER.LAYERS = [16]
+            cfg.MODEL.ENCODER.ACTIVATION = "tanh"; cfg.MODEL.NORM_FN = "ball"
+        else:
+            cfg = ref_config.get_config("lista"); cfg.MODEL.TARGET_SIZE = 16
+            cfg.MODEL.ENCODER.LISTA.L = float(np.load(os.path.join(HERE, "forecast_lista_linear_meta.npz"))["L"])
+        model = ref_model.make_model(cfg, g["obs"].shape[1])
+        model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+        model.eval()
+        with torch.no_grad():
+            x0 = torch.from_numpy(g["obs"])
+            out[f"{name}::latent"] = model.rollout_latent_discrete(model.encode(x0), 4).numpy()
+            out[f"{name}::sequence"] = model.rollout_sequence(x0, 4).numpy()
+    np.savez(os.path.join(HERE, "sequences_small.npz"), **out)
+    print("sequences", {k: v.shape for k, v in out.items()})
+
+
 def gen_dmd():
     """UNMODIFIED reference DMDStrategy (baselines.py:109-187) + run_backtest on a small synthetic env: the fitted K,
     the forecasts it hands to the MPC at every step, the history and the metrics."""
@@ -331,6 +358,9 @@ def gen_checkpoints():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sequences":
+        gen_sequences()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "data":
         gen_data_small()
         sys.exit(0)
@@ -353,4 +383,5 @@ if __name__ == "__main__":
     gen_rollouts()
     gen_markowitz()
     gen_checkpoints()
+    gen_sequences()
     print("golden fixtures written to", HERE)

@@ -296,3 +296,25 @@ def test_evaluate_finance_vs_reference(golden, name):
     assert np.allclose(got, want, rtol=1e-5)
     assert torch.equal(out["mse_reencode"], out["mse_curves"]["every_step"])
     assert torch.equal(out["pred_no_reencode"], out["predictions"]["no_reencode"])
+
+
+@pytest.mark.parametrize("name", ["generic_small", "generic_tanh_ball", "lista_linear"])
+def test_rollout_sequence_vs_reference(golden, name):
+    """model.rollout_latent_discrete / rollout_sequence (model.py:527-585): the unroll is the plain z @ K, without the
+    latent normalisation step_latent applies for NORM_FN='ball'."""
+    import torch
+    g = golden(f"forecast_{name}.npz")
+    r = golden("sequences_small.npz")
+    meta = golden(f"forecast_{name}_meta.npz") if name.startswith("lista") else None
+    m = build(name, g, meta)
+    m.load_state_dict(sd_from_npz(g))
+    x0 = torch.from_numpy(g["obs"]).cuda()
+    lat = m.rollout_latent_discrete(m.encode(x0), 4).cpu().numpy()
+    seq = m.rollout_sequence(x0, 4).cpu().numpy()
+    assert lat.shape == r[f"{name}::latent"].shape and seq.shape == r[f"{name}::sequence"].shape
+    for k in range(5):
+        assert rowwise_rel(lat[:, k], r[f"{name}::latent"][:, k]) < FORECAST_RTOL, k
+        assert rowwise_rel(seq[:, k], r[f"{name}::sequence"][:, k]) < FORECAST_RTOL, k
+    if name == "generic_tanh_ball":                      # step_latent normalises, the discrete unroll does not
+        z1 = m.step_latent(m.encode(x0)).cpu().numpy()
+        assert not np.allclose(z1, lat[:, 1], rtol=1e-3)
