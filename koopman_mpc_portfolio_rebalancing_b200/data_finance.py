@@ -37,6 +37,14 @@ def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def clean_price_data(prices, max_missing_ratio: float = 0.1, max_gap_days: int = 5):
+    """Drop assets with more than ``max_missing_ratio`` missing prices, forward-fill gaps of up to ``max_gap_days``,
+    drop the rows that still hold a NaN (data_finance.py:147-192).  Host pandas, like the reference."""
+    missing = prices.isna().mean()
+    prices = prices[missing[missing <= max_missing_ratio].index].copy()
+    return prices.ffill(limit=max_gap_days).dropna()
+
+
 def compute_log_returns(prices):
     """y_t = log(p_t) - log(p_{t-1}), first row dropped (data_finance.py:195-208).  DataFrame or ndarray."""
     if hasattr(prices, "iloc"):
@@ -303,3 +311,15 @@ def create_finance_env_from_returns(log_returns, train_end=None, val_end=None, e
                 "observation_size": train_ds.observation_size, "train_samples": len(train_ds),
                 "val_samples": len(val_ds), "test_samples": len(test_ds), "log_returns_shape": values.shape}
     return FinanceEnv(train_ds, val_ds, test_ds, stats, metadata, series_std=z, test_row0=c0)
+
+
+def create_finance_env(prices, train_end: str, val_end: str, embedding_dim: int = 20, sequence_length: int = 1,
+                       device="cuda") -> FinanceEnv:
+    """``load_finance_data`` + ``create_finance_env`` of the reference (data_finance.py:427-507, 745-792) from a frame of
+    adjusted close prices the caller already holds: clean -> log-returns -> train-only statistics -> standardise ->
+    embed -> date splits.  The yfinance download in front of it (data_finance.py:90-144) is outside this library."""
+    log_returns = compute_log_returns(clean_price_data(prices))
+    env = create_finance_env_from_returns(log_returns, train_end=train_end, val_end=val_end, embedding_dim=embedding_dim,
+                                          sequence_length=sequence_length, device=device)
+    env.metadata["prices_shape"] = tuple(prices.shape)
+    return env

@@ -11,6 +11,7 @@ small .npz files; large weights are regenerated from seeds by koopman_mpc_portfo
                        (model.py, backtest.py:85-121) for GenericKM (relu/id, tanh/ball, gelu + MLP decoder)
                        and LISTAKM (linear and MLP encoder); weights stored (tiny models)
   forecast_cfg1.npz    finance_sparse preset, TARGET_SIZE=128, N=10, d=20 (BASELINE config 1); weights from seed
+  prices_small.npz     clean_price_data -> compute_log_returns -> stats -> splits from a price frame with gaps
   sequences_small.npz  model.rollout_latent_discrete / rollout_sequence (model.py:527-585) on three tiny models
   rollouts_small.npz   evaluation.rollout_{no,every_step,periodic}_reencode (evaluation.py:44-134) on two tiny models
   markowitz_small.npz  UNMODIFIED reference MarkowitzStrategy + run_backtest (substitute mean-variance solve = fp64 oracle)
@@ -277,6 +278,32 @@ def gen_rollouts():
     print("rollouts", {k: v.shape for k, v in out.items()})
 
 
+def gen_prices():
+    """reference clean_price_data -> compute_log_returns -> compute_standardization_stats -> create_finance_splits
+    (data_finance.py:147-353) on a synthetic price frame with gaps (short gaps are filled, a 7-day gap and a leading
+    NaN drop rows, one asset with 20 % missing is dropped)."""
+    rng = np.random.default_rng(21)
+    T, N, d = 90, 4, 3
+    lr = synthetic.gbm_log_returns(21, T, N)
+    prices = pd.DataFrame(100.0 * np.exp(np.cumsum(lr, axis=0)), index=pd.bdate_range("2015-01-05", periods=T),
+                          columns=[f"P{i}" for i in range(N)])
+    prices.iloc[10:12, 0] = np.nan            # 2-day gap: forward-filled
+    prices.iloc[30:37, 1] = np.nan            # 7-day gap: 5 filled, 2 rows dropped
+    prices.iloc[0, 2] = np.nan                # nothing to fill from: row dropped
+    prices.iloc[rng.choice(T, 18, replace=False), 3] = np.nan     # 20 % missing: asset dropped
+    clean = ref_data.clean_price_data(prices)
+    logret = ref_data.compute_log_returns(clean)
+    train_end, val_end = str(logret.index[49].date()), str(logret.index[69].date())
+    stats = ref_data.compute_standardization_stats(logret, train_end)
+    tr, trd, va, vad, te, ted = ref_data.create_finance_splits(logret, stats, train_end, val_end, d)
+    np.savez(os.path.join(HERE, "prices_small.npz"), prices=prices.values, clean=clean.values,
+             clean_rows=np.array([prices.index.get_loc(i) for i in clean.index]),
+             clean_cols=np.array([list(prices.columns).index(c) for c in clean.columns]),
+             log_returns=logret.values, train_end=train_end, val_end=val_end, d=d, mean=stats.mean, std=stats.std,
+             train=tr, val=va, test=te)
+    print("prices", prices.shape, "->", clean.shape, tr.shape, va.shape, te.shape)
+
+
 def gen_sequences():
     """reference rollout_latent_discrete / rollout_sequence (model.py:527-585; NO latent normalisation in the unroll,
     unlike step_latent) on three of the tiny forecast models, the ball-normalised one included."""
@@ -358,6 +385,9 @@ def gen_checkpoints():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "prices":
+        gen_prices()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sequences":
         gen_sequences()
         sys.exit(0)
@@ -384,4 +414,5 @@ if __name__ == "__main__":
     gen_markowitz()
     gen_checkpoints()
     gen_sequences()
+    gen_prices()
     print("golden fixtures written to", HERE)

@@ -125,3 +125,25 @@ def test_test_sequences_and_shift_check_vs_reference(golden):
     assert i3.shape == (1, 12) and f3.shape == (1, 1, 12)
     assert df.verify_embedding_shift(g["embedded"], 3, int(g["d"])) == bool(r["shift_ok"]) is True
     assert df.verify_embedding_shift(g["embedded"][::2], 3, int(g["d"])) == bool(r["shift_broken"]) is False
+
+
+def _price_frame(g):
+    import pandas as pd
+    return pd.DataFrame(g["prices"], index=pd.bdate_range("2015-01-05", periods=g["prices"].shape[0]),
+                        columns=[f"P{i}" for i in range(g["prices"].shape[1])])
+
+
+def test_clean_prices_and_log_returns_vs_reference(golden):
+    """clean_price_data / compute_log_returns (data_finance.py:147-208) bit-exact against the reference on a price frame
+    with short gaps (filled), a long gap and a leading NaN (rows dropped) and a sparse asset (dropped)."""
+    import numpy as np
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df
+    g = golden("prices_small.npz")
+    prices = _price_frame(g)
+    clean = df.clean_price_data(prices)
+    assert np.array_equal(clean.values, g["clean"])
+    assert [prices.index.get_loc(i) for i in clean.index] == list(g["clean_rows"])
+    assert [list(prices.columns).index(c) for c in clean.columns] == list(g["clean_cols"])
+    assert np.array_equal(df.compute_log_returns(clean).values, g["log_returns"])
+    st = df.compute_standardization_stats(df.compute_log_returns(clean), str(g["train_end"]))
+    assert np.array_equal(st.mean, g["mean"]) and np.array_equal(st.std, g["std"])

@@ -58,3 +58,17 @@ def test_batched_embedding_large_ragged():
     emb = df.embed_device(z, d, n_assets=N).cpu().numpy()
     for b in range(B):
         assert np.array_equal(emb[b], do.time_delay_embedding(z[b, :, :N].cpu().numpy(), d))
+
+
+def test_env_from_price_frame_vs_reference(golden):
+    """create_finance_env(prices, ...): clean -> log-returns -> train-only statistics -> standardise -> embed -> date
+    splits, bit-exact against the reference pipeline (data_finance.py:147-353) on the prices_small frame."""
+    from test_boundary import _price_frame
+    from koopman_mpc_portfolio_rebalancing_b200 import data_finance as df
+    g = golden("prices_small.npz")
+    env = df.create_finance_env(_price_frame(g), str(g["train_end"]), str(g["val_end"]), embedding_dim=int(g["d"]))
+    assert env.n_assets == 3 and env.metadata["tickers"] == ["P0", "P1", "P2"] and env.metadata["prices_shape"] == (90, 4)
+    assert np.array_equal(env.train_dataset.data.cpu().numpy(), g["train"])
+    assert np.array_equal(env.val_dataset.data.cpu().numpy(), g["val"])
+    assert np.array_equal(env.test_dataset.data.cpu().numpy(), g["test"])
+    assert df.verify_embedding_shift(env.test_dataset.data, 3, int(g["d"]))
