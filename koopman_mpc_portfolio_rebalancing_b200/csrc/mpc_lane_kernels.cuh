@@ -15,7 +15,7 @@
 #define KMPC_LANE_BT_ATTR(threads) __launch_bounds__(threads, 1)
 #endif
 #ifndef KMPC_LANE_SYNC_EVERY
-#define KMPC_LANE_SYNC_EVERY 4    // block barrier every 4th trip (measured 2: 204 ms, 4: 196, 8: 201; before the start-up code shrank 1: 215, 4: 208, 16: 215, 64: 231)
+#define KMPC_LANE_SYNC_EVERY 4    // block barrier every 4th trip (measured per config-2 step, final code: 3: 195.3 ms, 4: 193.0, 6: 196.5; earlier 2: 204, 4: 196, 8: 201; before the start-up code shrank 1: 215, 4: 208, 16: 215, 64: 231)
 #endif
 #ifndef KMPC_LANE_MINB
 #define KMPC_LANE_MINB 1      // resident blocks per SM the register allocation is sized for (0/1 = no cap)
