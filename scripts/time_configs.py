@@ -47,3 +47,23 @@ m = km.make_model(km.model_config("GenericKM", Z, [1024, 1024], enc_bias=True), 
 m.load_state_dict(synthetic.generic_km_weights(0, N * d, [1024, 1024], Z))
 eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H), bt.BacktestConfig(horizon=H))
 run("cfg5 (GenericKM 100 assets, bootstrap paths)", eng, paths, mean, std, rows)
+del eng, m, paths
+torch.cuda.empty_cache()
+# config 4: sweep grid on ONE price path: 16 weight sets x 64 lambda x 64 tau = 65 536 backtests sharing 16 forecast sets
+b4 = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+N, d, H, Z, rows = 50, 20, 5, 1024, 252
+T = rows + d - 1
+lr1 = synthetic.gbm_log_returns(0, T, N)
+models = []
+for s_ in range(16):
+    mm = km.make_model(km.model_config("GenericKM", Z, [1024, 1024], enc_bias=True), N * d)
+    mm.load_state_dict(synthetic.generic_km_weights(s_, N * d, [1024, 1024], Z))
+    models.append(mm)
+lam_grid = np.logspace(-5, -1, b4); tau_grid = np.linspace(0.01, 1.0, b4)
+for _ in range(2):
+    torch.cuda.synchronize(); t0 = time.time()
+    out = engine.run_grid(models, N, d, lr1, lr1.mean(axis=0), np.maximum(lr1.std(axis=0, ddof=1), 1e-8), lam_grid, tau_grid, rows=rows, horizon=H)
+    torch.cuda.synchronize(); dt = time.time() - t0
+st = out["stats"].cpu().numpy(); nb = st.shape[0]; ns = rows - 1 - H
+print(f"cfg4 (grid 16 x {b4} x {b4} on one path): {nb} backtests x {ns} decisions in {dt * 1e3:.0f} ms wall -> {nb * ns / dt:.3e} decisions/s; "
+      f"iterations/decision {st[:, 3].sum() / (nb * ns):.1f}, optimal {st[:, 0].sum()}, inaccurate {st[:, 1].sum()}, fallback {st[:, 2].sum()}")
