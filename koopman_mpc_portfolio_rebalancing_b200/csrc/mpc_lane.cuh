@@ -122,7 +122,7 @@ struct LaneIpm {
   double lam, tau, delta;
   // state of the solve in progress (begin / check / factor_a / factor_b / newton_phase)
   double w0_, mu_, gap_, mcount_, kkt_[3];
-  int it_;
+  int it_, nretry_;
 
   // `slot`: which of the problems that share this thread block (its threads are [slot*NT, (slot+1)*NT), its
   // named barrier is 1 + slot; barrier 0 stays free for block-wide lockstep points of the caller).
@@ -606,7 +606,7 @@ struct LaneIpm {
     has_u_ = uni((lam > 0.0) || (tau > 0.0));
     has_c_ = has_u_ && uni(tau > 0.0);
     has_w_ = !allow_short; allow_short_ = allow_short;
-    it_ = 0; fact_ok_ = true;
+    it_ = 0; fact_ok_ = true; nretry_ = 0;
     kkt_[0] = kkt_[1] = kkt_[2] = CUDART_NAN;
     if (!valid) {
       w0 = 0.0;
@@ -707,7 +707,17 @@ struct LaneIpm {
   }
 
   __device__ __forceinline__ int check(const IpmOptions& opt) {
-    if (!fact_ok_) return finish(ST_FAILED);               // the previous factorisation broke down
+    if (!fact_ok_) {
+      // The border factorisation met a non-positive pivot (barrier weights spanning > 20 decades next to the optimum,
+      // usually after the endgame has shrunk delta).  The iterate is untouched: accept it if it already meets the loose
+      // bar, otherwise retry a few times with a stronger proximal term — a damped but well-conditioned Newton step —
+      // before giving up.
+      const bool loose = isfinite(kkt_[1] + kkt_[2]) && kkt_[0] < kLoosePres && kkt_[1] < kLooseDres && kkt_[2] < kLooseGap;
+      if (loose || nretry_ >= kMaxFactorRetries) return finish(ST_FAILED);
+      ++nretry_;
+      delta = fmin(fmax(delta, opt.delta) * 30.0, 1e-2);
+      fact_ok_ = true;
+    }
     ++it_;
     double gap, pres;
     {
