@@ -59,7 +59,7 @@ constexpr double kLoosePres = 1e-8, kLooseDres = 1e-4, kLooseGap = 1e-7;
 // Mehrotra's second-order term is scaled by min(1, affine step / kCorrFull): see oracle/mpc_oracle.py (CORRECTOR_FULL_STEP)
 constexpr double kCorrFull = 0.3;
 // lane kernel: factorisation breakdowns answered by a stronger proximal term before the decision falls back
-constexpr int kMaxFactorRetries = 3;
+constexpr int kMaxFactorRetries = 4;
 
 constexpr unsigned kFull = 0xffffffffu;
 

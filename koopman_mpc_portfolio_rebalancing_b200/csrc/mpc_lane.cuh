@@ -709,11 +709,12 @@ struct LaneIpm {
   __device__ __forceinline__ int check(const IpmOptions& opt) {
     if (!fact_ok_) {
       // The border factorisation met a non-positive pivot (barrier weights spanning > 20 decades next to the optimum,
-      // usually after the endgame has shrunk delta).  The iterate is untouched: accept it if it already meets the loose
-      // bar, otherwise retry a few times with a stronger proximal term — a damped but well-conditioned Newton step —
-      // before giving up.
+      // usually after the endgame has shrunk delta).  The iterate is untouched: retry a few times with a stronger
+      // proximal term — a damped but well-conditioned Newton step — before giving up.
+      // The first breakdown is always retried (most such iterates then reach the tolerances); from the second one on
+      // an iterate that meets the loose bar is accepted as it is (finish() applies the loose acceptance).
       const bool loose = isfinite(kkt_[1] + kkt_[2]) && kkt_[0] < kLoosePres && kkt_[1] < kLooseDres && kkt_[2] < kLooseGap;
-      if (loose || nretry_ >= kMaxFactorRetries) return finish(ST_FAILED);
+      if (nretry_ >= kMaxFactorRetries || (nretry_ > 0 && loose)) return finish(ST_FAILED);
       ++nretry_;
       delta = fmin(fmax(delta, opt.delta) * 30.0, 1e-2);
       fact_ok_ = true;

@@ -42,7 +42,7 @@ import numpy as np
 # loose acceptance ("optimal_inaccurate") of an iterate that could not be pushed to the tolerances; same constants as
 # csrc/mpc_ipm.cuh (kLoosePres / kLooseDres / kLooseGap), see the comment there
 LOOSE_PRES, LOOSE_DRES, LOOSE_GAP = 1e-8, 1e-4, 1e-7
-MAX_FACTOR_RETRIES = 3        # kMaxFactorRetries of csrc/mpc_ipm.cuh
+MAX_FACTOR_RETRIES = 4        # kMaxFactorRetries of csrc/mpc_ipm.cuh
 CORRECTOR_FULL_STEP = 0.3   # affine step below which the corrector's second-order term is scaled down (kCorrFull)
 STATUS_OPTIMAL = 0
 STATUS_INACCURATE = 1
@@ -499,10 +499,10 @@ def solve_structured(w_cur, yhat, lam, tau, allow_short=False, *, R=None, tol=1e
             Kc = np.linalg.cholesky(K)
         except np.linalg.LinAlgError:
             # breakdown of the border factorisation (barrier weights spanning > 20 decades): the iterate is untouched;
-            # stop if it already meets the loose bar, else retry with a stronger proximal term (same rule as
+            # retry with a stronger proximal term; from the second breakdown on stop if the loose bar is met (same rule as
             # LaneIpm::check in csrc/mpc_lane.cuh) before giving up
             loose = np.isfinite(res[1] + res[2]) and res[0] < LOOSE_PRES and res[1] < LOOSE_DRES and res[2] < LOOSE_GAP
-            if loose or n_retry >= MAX_FACTOR_RETRIES:
+            if n_retry >= MAX_FACTOR_RETRIES or (n_retry > 0 and loose):      # the first breakdown is always retried
                 break
             n_retry += 1
             delta = min(max(delta, delta0) * 30.0, 1e-2)
