@@ -6,13 +6,19 @@
 
 One *step* = one whole pass of the hot path over one batch of synthetic scenario backtests:
 standardise -> (in-place) delay embedding -> Koopman forecast of every rebalancing step -> persistent MPC +
-portfolio loop -> metrics [B,5] (+ the NCCL metric gather when N > 1).  Workload at any N: BASELINE config 2 per
-GPU (GenericKM finance_sparse architecture 1000->1024->1024->1024, 50 assets, d=20, H=5, 4096 backtests x 246
+portfolio loop -> metrics [B,5] (+ the NCCL metric gather when N > 1).  Headline workload at any N: BASELINE config 2
+per GPU (GenericKM finance_sparse architecture 1000->1024->1024->1024, 50 assets, d=20, H=5, 4096 backtests x 246
 decisions), i.e. weak scaling: independent backtests shard across ranks with no data-path collective.
 
 `value`  : decisions/s with the inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through the public API with HOST (pinned) inputs: H2D of the log-returns and statistics and
            D2H of the metrics inside the timed region.
+`roofline`: the dominant kernel (the persistent MPC + portfolio kernel) against its bound, SM instruction issue:
+           warp instructions per decision (ncu capture of this code, profiles/r2_solver_counters.json) x decisions /
+           live kernel time / (SMs x live SM clock), peak 4 per SM and clock.  HBM and tensor figures ride along.
+`other_configs`: a short timed pass of BASELINE configs 3, 4 and 5 (N = 1: cfg3 at 148 backtests, cfg4 at its full
+           65 536-backtest grid, cfg5 at 32 768 bootstrap paths; N > 1: cfg4 STRONG-scaled over the ranks and cfg5 at
+           10^6 / N paths per rank), each with iterations, status counts and decisions/s.
 """
 from __future__ import annotations
 
@@ -40,7 +46,15 @@ WORKLOADS = {
     "cfg1": dict(N=10, d=20, H=5, enc=[1024, 1024], Z=128, B=1, rows=252,
                  desc="cfg1: finance_sparse SparseKM target_size=128, 10 assets, single backtest x 246 decisions"),
     "tiny": dict(N=10, d=6, H=5, enc=[64, 64], Z=32, B=64, rows=40, desc="tiny smoke workload"),
+    # BASELINE configs 3-5: run by other_configs(), not as headline workloads
+    "cfg3": dict(N=500, d=10, H=10, Z=2048, B=1024, rows=252, lista_loops=10,
+                 desc="cfg3: LISTAKM linear encoder 5000->2048 + 10 loops, 500 assets, d=10, H=10, tau=0.2"),
+    "cfg4": dict(N=50, d=20, H=5, enc=[1024, 1024], Z=1024, rows=252, S=16, L=64, T=64,
+                 desc="cfg4: sweep grid 16 weight sets x 64 lambda x 64 tau = 65536 backtests on one price path"),
+    "cfg5": dict(N=100, d=20, H=5, enc=[1024, 1024], Z=1024, rows=252, B=1_000_000,
+                 desc="cfg5: Monte-Carlo stress test, bootstrap paths of one 3000-day block x 100 assets, H=5"),
 }
+HEADLINE = ("cfg2", "cfg1", "tiny")
 
 
 def flops_per_decision(w, folded=False):
@@ -96,7 +110,11 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# host-CPU baseline: the oracle port (forecast in numpy fp32, structured fp64 IPM, reference loop arithmetic)
+# host-CPU baselines
+#   port           : the oracle port (forecast in numpy fp32, structured fp64 IPM, reference loop arithmetic)
+#   reference loop : the UNMODIFIED reference run_backtest + KoopmanMPCStrategy + torch model (baseline/_ref, a copy of
+#                    /root/reference made by __graft_entry__.build()) on config 1, with the substitute `mpc` module of
+#                    tests/golden/_shims (cvxpy / SCS cannot be installed offline) -> oracle solver
 # ------------------------------------------------------------------------------------------------------------------
 
 def _cpu_worker(args):
@@ -109,7 +127,6 @@ def _cpu_worker(args):
         except Exception:
             pass
     from oracle import backtest_oracle as bo, data_oracle as do, forecast_oracle as fo
-    from koopman_mpc_portfolio_rebalancing_b200 import synthetic
     w = WORKLOADS[wname]
     sd = _cpu_weights(wname)
     lr, mean, std, T = make_inputs(w, 1, seed)
@@ -141,6 +158,23 @@ def cpu_baseline_single(wname, n_dec, scenarios):
     return scenarios * n_dec / dt, dt
 
 
+def reference_loop_baseline(timeout_s=240):
+    """Config 1 through the reference's own loop (backtest.py:67-219, unmodified, from baseline/_ref) in a child
+    process; returns the cpu_baseline-style dict or {"unavailable": why}."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "backtest.py")):
+        return {"unavailable": "baseline/_ref is empty (the reference is copied there by __graft_entry__.build() where /root/reference exists)"}
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_loop.py")], capture_output=True, text=True,
+                           timeout=timeout_s, cwd=ROOT)
+        for line in reversed(p.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"unavailable": ("reference loop failed: " + (p.stderr.strip().splitlines() or ["no output"])[-1])[:300]}
+    except Exception as e:                                   # noqa: BLE001 — reported, never fatal for the bench line
+        return {"unavailable": f"reference loop failed: {type(e).__name__}: {e}"[:300]}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU path (the oracle port: cvxpy/SCS cannot be installed offline, so the
     solver is the fp64 structured IPM; forecast and loop arithmetic are the reference's) on all host cores."""
@@ -170,11 +204,159 @@ def run_reference_arm(args):
             "vs_baseline": None, "dtype": "f32 forecast + f64 solver", "data": "synthetic",
             "config": {"workload": w["desc"], "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline_reference_loop": reference_loop_baseline(),
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# BASELINE configs 3, 4, 5 (short timed passes beside the headline)
+# ------------------------------------------------------------------------------------------------------------------
+
+def _stats_dict(stats, n_dec):
+    st = stats.sum(dim=0).cpu().numpy() if hasattr(stats, "sum") and stats.dim() == 2 else np.asarray(stats)
+    return {"iterations_per_decision": float(st[3]) / max(1, n_dec), "optimal": int(st[0]), "inaccurate": int(st[1]),
+            "fallback": int(st[2])}
+
+
+def other_configs(dev, rank, world, barrier, which=("cfg3", "cfg4", "cfg5"), cfg5_paths_n1=32768):
+    """One warm-up and one timed pass of each of BASELINE configs 3-5 on this rank's GPU.  Returns a dict (all ranks
+    compute, the caller prints rank 0's).  Times are CUDA events on the current stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt, engine, model as km, synthetic
+
+    def max_ms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_vec(v):
+        t = torch.as_tensor(np.asarray(v, dtype=np.float64), device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    res = {}
+    # ---- config 3: LISTAKM 500 assets, H = 10 (weak: 148 backtests per GPU) ------------------------------------
+    if "cfg3" in which:
+        w = WORKLOADS["cfg3"]
+        N, d, H, Z, rows = w["N"], w["d"], w["H"], w["Z"], w["rows"]
+        b3 = 148
+        T = rows + d - 1
+        lr = synthetic.gbm_log_returns_batch(1000 + rank, b3, T, N)
+        mean = lr.mean(axis=1); std = np.maximum(lr.std(axis=1, ddof=1), 1e-8)
+        sd, L = synthetic.lista_km_weights(0, N * d, Z)
+        m = km.make_model(km.model_config("LISTAKM", Z, lista_loops=w["lista_loops"], lista_L=L, lista_alpha=5e-3, lista_linear=True),
+                          N * d, device=dev)
+        m.load_state_dict(sd)
+        eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H, cost_coeff=1e-3, max_turnover=0.2),
+                                       bt.BacktestConfig(horizon=H), device=dev)
+        lr_d, mean_d, std_d = (torch.from_numpy(x).to(dev) for x in (lr, mean, std))
+        ns = eng.n_steps(rows)
+        eng.run_device(lr_d, mean_d, std_d, 0, rows)
+        barrier()
+        tm = {}
+        out = eng.run_device(lr_d, mean_d, std_d, 0, rows, timings=tm)
+        barrier()
+        ev = tm["_events"]
+        ms = max_ms(ev[0].elapsed_time(ev[3]))
+        st = sum_vec(out["stats"].sum(dim=0).cpu().numpy())
+        res["cfg3"] = {"workload": w["desc"], "backtests": b3 * world, "decisions": b3 * world * ns, "scaling": "weak",
+                       "ms": ms, "decisions_per_s": b3 * world * ns / (ms * 1e-3),
+                       "stages_ms": {"forecast": ev[1].elapsed_time(ev[2]), "mpc+portfolio": ev[2].elapsed_time(ev[3])},
+                       "solver": _stats_dict(st, b3 * world * ns)}
+        del eng, m, lr_d, out
+        torch.cuda.empty_cache()
+    # ---- config 4: sweep grid, STRONG-scaled over the ranks --------------------------------------------------
+    if "cfg4" in which:
+        w = WORKLOADS["cfg4"]
+        N, d, H, Z, rows = w["N"], w["d"], w["H"], w["Z"], w["rows"]
+        T = rows + d - 1
+        lr1 = synthetic.gbm_log_returns(0, T, N)
+        models = []
+        for s_ in range(w["S"]):
+            mm = km.make_model(km.model_config("GenericKM", Z, w["enc"], enc_bias=True), N * d, device=dev)
+            mm.load_state_dict(synthetic.generic_km_weights(s_, N * d, w["enc"], Z))
+            models.append(mm)
+        lam_grid = np.logspace(-5, -1, w["L"]); tau_grid = np.linspace(0.01, 1.0, w["T"])
+        n_total = w["S"] * w["L"] * w["T"]
+        ns = rows - 1 - H
+        args4 = (models, N, d, lr1, lr1.mean(axis=0), np.maximum(lr1.std(axis=0, ddof=1), 1e-8), lam_grid, tau_grid)
+        kw4 = dict(rows=rows, horizon=H, shard=(rank, world), device=dev)
+        engine.run_grid(*args4, **kw4)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = engine.run_grid(*args4, **kw4)
+        allm = engine.gather_metrics(out["metrics"], n_total, rank, world)
+        e1.record()
+        barrier()
+        ms = max_ms(e0.elapsed_time(e1))
+        st = sum_vec(out["stats"].sum(dim=0).cpu().numpy())
+        res["cfg4"] = {"workload": w["desc"], "backtests": n_total, "decisions": n_total * ns, "scaling": "strong",
+                       "ms": ms, "decisions_per_s": n_total * ns / (ms * 1e-3), "solver": _stats_dict(st, n_total * ns),
+                       "note": "16 forecast sets computed on every rank (replicated), backtest ids sharded contiguously, "
+                               "metric all_gather inside the timed region",
+                       "mean_final_value": float(allm[:, 3].mean().item())}
+        del models, out, allm
+        torch.cuda.empty_cache()
+    # ---- config 5: bootstrap paths; N = 1: a 32 768-path sample, N > 1: 10^6 / N paths per rank ------------------
+    if "cfg5" in which:
+        w = WORKLOADS["cfg5"]
+        N, d, H, Z, rows = w["N"], w["d"], w["H"], w["Z"], w["rows"]
+        T = rows + d - 1
+        hist = synthetic.gbm_log_returns(0, 3000, N)
+        total = w["B"] if world > 1 else cfg5_paths_n1
+        lo, hi = engine.shard_range(total, rank, world)
+        m = km.make_model(km.model_config("GenericKM", Z, w["enc"], enc_bias=True), N * d, device=dev)
+        m.load_state_dict(synthetic.generic_km_weights(0, N * d, w["enc"], Z))
+        eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H), bt.BacktestConfig(horizon=H), device=dev)
+        mean_d = torch.from_numpy(hist.mean(axis=0)).to(dev); std_d = torch.from_numpy(hist.std(axis=0, ddof=1)).to(dev)
+        hist_d = torch.from_numpy(hist).to(dev)
+        ns = eng.n_steps(rows)
+        chunk = 32768                                                   # paths per pass: 16 GB of forecasts
+        wp, _ = engine.bootstrap_paths(hist_d, 1184, T, seed=1234, device=dev, offset=lo)
+        eng.run_device(wp, mean_d, std_d, 0, rows)                      # warm-up on a small sample
+        del wp
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = np.zeros(4)
+        mets = []
+        e0.record()
+        for c0 in range(lo, hi, chunk):                                 # path generation is part of the job
+            nb = min(chunk, hi - c0)
+            paths, _ = engine.bootstrap_paths(hist_d, nb, T, seed=1234, device=dev, offset=c0)
+            out = eng.run_device(paths, mean_d, std_d, 0, rows)
+            mets.append(out["metrics"].clone())
+            st = st + out["stats"].sum(dim=0).cpu().numpy()
+        local = torch.cat(mets, dim=0)
+        allm = engine.gather_metrics(local, total, rank, world)         # the NCCL metric gather of BASELINE config 5
+        e1.record()
+        barrier()
+        ms = max_ms(e0.elapsed_time(e1))
+        st = sum_vec(st)
+        res["cfg5"] = {"workload": w["desc"], "backtests": total, "decisions": total * ns,
+                       "scaling": "strong (10^6 paths over the ranks)" if world > 1 else "one-GPU sample of the 10^6 paths",
+                       "ms": ms, "decisions_per_s": total * ns / (ms * 1e-3), "solver": _stats_dict(st, total * ns),
+                       "note": f"bootstrap index generation + gather of the paths inside the timed region, chunks of {chunk} paths, "
+                               "metric all_gather at the end",
+                       "mean_final_value": float(allm[:, 3].mean().item())}
+        del eng, m, mets, local, allm
+        torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+
+def solver_counters():
+    """warp instructions per decision of the persistent MPC kernel, from the committed ncu capture of this code"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_solver_counters.json")))
+    except Exception:
+        return None
+
 
 def run_gpu_arm(args):
     import torch
@@ -205,7 +387,6 @@ def run_gpu_arm(args):
     lr_h = torch.from_numpy(lr).pin_memory(); mean_h = torch.from_numpy(mean).pin_memory(); std_h = torch.from_numpy(std).pin_memory()
     lr_d, mean_d, std_d = lr_h.to(dev), mean_h.to(dev), std_h.to(dev)
     handle = _capi.Handle.get(local)
-    _capi.lib().kmpc_set_mpc_kernel({"lane": 2, "cta": 1, "warp": 0}[args.mpc_kernel])
     _capi.lib().kmpc_set_gemm_fp16_pairs(1 if args.gemm == "fp16" else 0)
     B_total = B * world
 
@@ -270,6 +451,13 @@ def run_gpu_arm(args):
     h2d = lr_h.numel() * 8 + mean_h.numel() * 8 + std_h.numel() * 8
     d2h = B * 5 * 8 + B * 4 * 8
 
+    others = None
+    if args.workload == "cfg2" and not args.no_other_configs and not args.paths:
+        del lr_d
+        eng._buf.clear()
+        torch.cuda.empty_cache()
+        others = other_configs(dev, rank, world, barrier)
+
     if rank == 0:
         peaks = {}
         try:
@@ -285,48 +473,60 @@ def run_gpu_arm(args):
         tensor_peak = bf16 / 3.0 if args.gemm == "fp16" else bf16 / 2.0 / 3.0
         hbm_bytes_bt = (8 * N + 8 * H * N + 32) * decisions_per_step_rank
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        dominant = "backtest_kernel" if st_bt >= st_fc else "forecast_gemm_chain"
         roof_fc = {"kernel": "forecast GEMM chain (gemm_tc16_kernel, tcgen05 fp16 pairs: encoder 3 GEMMs + folded multi-horizon read-out)", "bound": "tensor", "achieved": fc_tflops,
                    "peak": tensor_peak, "unit": "TFLOP/s", "frac": fc_tflops / tensor_peak, "traffic": None,
                    "peak_source": f"{peak_src} bf16 sustained / 3 (three fp16 MMAs per fp32-accurate product)",
                    "flops_per_decision": fpd, "flops_per_decision_unfolded": flops_per_decision(w), "ms": st_fc}
+        # The solver's bound is SM instruction issue: 4 warp instructions per clock and SM.
+        cnt = solver_counters() if args.workload == "cfg2" else None
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         bt_gbs = hbm_bytes_bt / (st_bt * 1e-3) / 1e9
-        # ncu --set full (profiles/r1_backtest_lane_kernel.txt): dram read+write 1263 B per decision
-        roof_bt = {"kernel": f"backtest_{args.mpc_kernel}_kernel (fp64 interior-point MPC + portfolio step, persistent)", "bound": "hbm",
-                   "achieved": bt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bt_gbs / hbm_peak,
-                   "traffic": 1263.0 * decisions_per_step_rank if args.mpc_kernel == "lane" else None,
-                   "bytes_per_decision": 8 * N + 8 * H * N + 32,
-                   "note": "the solver streams 1.2 KB per decision and is bound by instruction issue / dependency latency, not by HBM; "
-                           "see `compute` (ncu --set full capture in profiles/r1_backtest_lane_kernel.txt) and solver.iterations_per_decision",
-                   "compute": {"source": "ncu capture of the same kernel, profiles/r1_backtest_lane_kernel.txt (not measured live)",
-                               "fp64_pipe_busy_pct": 23.9, "issue_slots_busy_pct": 27.0, "ipc_per_sm": 1.08,
-                               "shared_memory_pipe_busy_pct": 46.9,
-                               "warp_instructions_per_decision": 54100, "warps_per_sm": 8, "registers_per_thread": 255},
-                   "ms": st_bt}
+        hbm_side = {"bound": "hbm", "achieved": bt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": bt_gbs / hbm_peak,
+                    "bytes_per_decision": 8 * N + 8 * H * N + 32,
+                    "note": "secondary: the solver streams ~2.4 KB per decision; HBM does not bound it"}
+        if cnt:
+            ipc = cnt["warp_instructions_per_decision"] * decisions_per_step_rank / (st_bt * 1e-3) / (sm_count * clk_mhz * 1e6)
+            roof_bt = {"kernel": "backtest_lane_kernel (fp64 interior-point MPC + portfolio step, persistent)",
+                       "bound": "sm_issue", "achieved": ipc, "peak": 4.0, "unit": "warp-instructions/clk/SM", "frac": ipc / 4.0,
+                       "traffic": cnt.get("dram_bytes_per_decision", 0) * decisions_per_step_rank or None,
+                       "warp_instructions_per_decision": cnt["warp_instructions_per_decision"],
+                       "counter_source": cnt.get("source"), "sm_count": sm_count, "sm_clock_mhz": clk_mhz,
+                       "ms": st_bt, "hbm": hbm_side}
+        else:
+            roof_bt = dict(hbm_side, kernel="backtest_lane_kernel (fp64 interior-point MPC + portfolio step, persistent)",
+                           traffic=None, ms=st_bt,
+                           note="no instruction counters committed for this workload: only the HBM side is reported; the "
+                                "kernel is bound by SM instruction issue")
+        dominant_bt = st_bt >= st_fc
         cpu = None
+        ref_loop = None
         if world == 1 and not args.no_cpu_baseline:
             n_dec = min(args.cpu_decisions, ns)
             v, dt = cpu_baseline_single(args.workload, n_dec, args.cpu_scenarios)
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{args.cpu_scenarios} scenarios x {n_dec} decisions of the same workload (oracle port: numpy fp32 forecast with "
                              f"{os.cpu_count()} BLAS threads available, scalar fp64 structured IPM), {dt:.1f} s"}
+            ref_loop = reference_loop_baseline()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 forecast + f64 solver", "data": "synthetic",
             "config": {"workload": w["desc"], "backtests_per_gpu": B, "decisions_per_step": world * decisions_per_step_rank,
-                       "l2": f"inputs larger than L2: {lr_d.numel() * 8 / 2**20:.0f} MiB of log-returns + "
+                       "l2": f"inputs larger than L2: {B * T * N * 8 / 2**20:.0f} MiB of log-returns + "
                              f"{B * ns * H * N * 4 / 2**20:.0f} MiB of forecasts per step vs 126 MiB L2"},
-            "roofline": roof_bt if dominant == "backtest_kernel" else roof_fc,
-            "roofline_other": roof_fc if dominant == "backtest_kernel" else roof_bt,
+            "roofline": roof_bt if dominant_bt else roof_fc,
+            "roofline_other": roof_fc if dominant_bt else roof_bt,
             "stages_ms": {"standardize+returns": st_data, "forecast": st_fc, "mpc+portfolio": st_bt},
             "solver": {"iterations_per_decision": float(stats[:, 3].sum() / max(1, B * ns)),
                        "optimal": int(stats[:, 0].sum()), "inaccurate": int(stats[:, 1].sum()), "fallback": int(stats[:, 2].sum())},
             "cpu_baseline": cpu,
+            "cpu_baseline_reference_loop": ref_loop,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "result_check": {"mean_final_value": float(np.mean(metrics_host[:, 3])), "mean_sharpe": float(np.mean(metrics_host[:, 0]))},
+            "other_configs": others,
         }
         print(json.dumps(line))
     if world > 1:
@@ -339,13 +539,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=list(HEADLINE))
     ap.add_argument("--paths", type=int, default=0, help="backtests per GPU (default: the workload's)")
     ap.add_argument("--cpu-decisions", type=int, default=246, help="decisions per scenario in the bounded CPU sample")
     ap.add_argument("--cpu-scenarios", type=int, default=10, help="scenarios in the rank-0 cpu_baseline sample (~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short passes of BASELINE configs 3-5")
     ap.add_argument("--gemm", default="fp16", choices=["fp16", "tf32"], help="forecast tensor-core kernel (diagnostics)")
-    ap.add_argument("--mpc-kernel", default="lane", choices=["lane", "cta", "warp"], help="MPC kernel layout (diagnostics)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

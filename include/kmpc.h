@@ -62,10 +62,12 @@ int kmpc_destroy(kmpc_handle* h);
 int64_t kmpc_launch_count(const kmpc_handle* h);
 /* 1 if an MPC kernel variant for (H, N) is compiled in */
 int kmpc_mpc_supported(int H, int N);
-/* diagnostics: MPC kernel layout, process-wide: 2 = one block per problem, thread = asset, stages in registers
- * [default]; 1 = one block per problem, thread = (stage, asset); 0 = one warp per problem.  Same central path and
- * results within the parity tolerances in all three. */
-int kmpc_set_mpc_kernel(int mode);
+/* Solver options of this handle (defaults: csrc/mpc_common.cuh default_ipm_options).  Tuning / diagnostics only:
+ * the parity tests run with the defaults.  KMPC_PARAM_DUAL_INIT = 0 selects the mu0-based starting point. */
+enum { KMPC_PARAM_RESET = 0, KMPC_PARAM_STEP_FRAC = 1, KMPC_PARAM_DUAL_INIT = 2, KMPC_PARAM_MAX_ITER = 3,
+       KMPC_PARAM_CLIP_FIRST_TRADE = 4 /* 1 [default]: an optimal_inaccurate plan whose first trade sits outside the
+                                          turnover cap (by <= 2e-5, a few decisions per million) is scaled back onto it */ };
+int kmpc_set_solver_param(kmpc_handle* h, int which, double value);
 
 /* ---------------------------------------------------------------------------------------------
  * Data side — replaces data_finance.py
@@ -162,8 +164,9 @@ int kmpc_set_gemm_mode(int use_tensor_cores);
 int kmpc_set_forecast_fold(int on);
 /* 1 [default]: the GenericKM encoder + folded read-out of kmpc_forecast run on the fp16-pair tensor-core kernel
  * (an fp32 value travels as fp16(x) and fp16((x - hi) * 2^11): 22 significant bits like the 3xTF32 pair at half the
- * operand bytes and twice the MMA rate).  kmpc_forecast then synchronises the stream once to read a range flag and
- * re-runs the 3xTF32 chain if any value left the fp16 range (|x| > 65504).  0: always the 3xTF32 chain. */
+ * operand bytes and twice the MMA rate).  Its epilogues raise a device flag when a value leaves the fp16 range
+ * (|x| > 65504); the 3xTF32 chain is queued behind it gated on that flag (its kernels exit at once otherwise), so the
+ * call stays asynchronous on `stream`.  0: always the 3xTF32 chain. */
 int kmpc_set_gemm_fp16_pairs(int on);
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode);
 

@@ -54,7 +54,7 @@ SIGNATURES = {
     "kmpc_destroy": (C.c_int, [vp]),
     "kmpc_launch_count": (C.c_int64, [vp]),
     "kmpc_mpc_supported": (C.c_int, [C.c_int, C.c_int]),
-    "kmpc_set_mpc_kernel": (C.c_int, [C.c_int]),
+    "kmpc_set_solver_param": (C.c_int, [vp, C.c_int, C.c_double]),
     "kmpc_standardize": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
     "kmpc_embed_gather": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kmpc_embed_index_host": (C.c_int, [C.c_int, C.c_int, C.c_int, vp]),

@@ -4,7 +4,6 @@
 #include <stdarg.h>
 #include "../../include/kmpc.h"
 #include "kmpc_internal.cuh"
-#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -49,6 +48,9 @@ int kmpc_create(int device, kmpc_handle** out) {
   h->launches = 0;
   h->scratch = nullptr;
   h->scratch_bytes = 0;
+  h->stats32 = nullptr;
+  h->stats32_cap = 0;
+  h->ipm = kmpc::default_ipm_options();
   e = cudaMalloc(&h->work_counter, 4 * sizeof(int));      // [0] backtest work counter, [2] structure-flag scratch
   if (e != cudaSuccess) { delete h; return kmpc_fail_cuda(e, "cudaMalloc(work_counter)"); }
   *out = h;
@@ -60,15 +62,33 @@ int kmpc_destroy(kmpc_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->work_counter);
   if (h->scratch) cudaFree(h->scratch);
+  if (h->stats32) cudaFree(h->stats32);
   delete h;
   return KMPC_OK;
 }
 
 int64_t kmpc_launch_count(const kmpc_handle* h) { return h ? h->launches : 0; }
 int kmpc_mpc_supported(int H, int N) { return kmpc::mpc_variant_supported(H, N); }
-int kmpc_set_mpc_kernel(int mode) {
-  if (mode < 0 || mode > 2) return fail(KMPC_E_INVALID, "kmpc_set_mpc_kernel: mode must be 0, 1 or 2");
-  kmpc::set_mpc_mode(mode);
+int kmpc_set_solver_param(kmpc_handle* h, int which, double value) {
+  if (!h) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: NULL handle");
+  if (!(value == value)) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: NaN");
+  switch (which) {
+    case KMPC_PARAM_STEP_FRAC:
+      if (!(value > 0.0 && value < 1.0)) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: step_frac must be in (0,1)");
+      h->ipm.step_frac = value; break;
+    case KMPC_PARAM_DUAL_INIT:
+      if (value < 0.0) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: dual_init must be >= 0");
+      h->ipm.dual_init = value; break;
+    case KMPC_PARAM_MAX_ITER:
+      if (value < 1.0 || value > 1000.0) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: max_iter must be in [1,1000]");
+      h->ipm.max_iter = (int)value; break;
+    case KMPC_PARAM_CLIP_FIRST_TRADE:
+      h->ipm.clip_first_trade = (value != 0.0) ? 1 : 0; break;
+    case KMPC_PARAM_RESET:
+      h->ipm = kmpc::default_ipm_options(); break;
+    default:
+      return fail(KMPC_E_INVALID, "kmpc_set_solver_param: unknown parameter %d", which);
+  }
   return KMPC_OK;
 }
 
@@ -117,18 +137,6 @@ int kmpc_current_returns(kmpc_handle* h, const float* z, int ld_z, const double*
   return KMPC_OK;
 }
 
-// solver options: the defaults of mpc_ipm.cuh, with two tuning overrides read once from the environment
-// (KMPC_STEP_FRAC, KMPC_DUAL_INIT; experiments only, the tests run with the defaults)
-static kmpc::IpmOptions ipm_options() {
-  static kmpc::IpmOptions o = [] {
-    kmpc::IpmOptions v = kmpc::default_ipm_options();
-    if (const char* e = getenv("KMPC_STEP_FRAC")) v.step_frac = atof(e);
-    if (const char* e = getenv("KMPC_DUAL_INIT")) v.dual_init = atof(e);
-    return v;
-  }();
-  return o;
-}
-
 int kmpc_mpc_solve(kmpc_handle* h, const float* yhat, const double* yhat64, const double* w_cur, const double* lam,
                    const double* tau, double lam0, double tau0, int allow_short, int P, int H, int N, double* w_out,
                    double* obj, double* kkt, int32_t* status, int32_t* iters, void* stream) {
@@ -141,7 +149,7 @@ int kmpc_mpc_solve(kmpc_handle* h, const float* yhat, const double* yhat64, cons
   kmpc::MpcSolveArgs A;
   A.yhat = yhat; A.yhat64 = yhat64; A.w_cur = w_cur; A.lam = lam; A.tau = tau; A.lam0 = lam0; A.tau0 = tau0;
   A.allow_short = allow_short; A.P = P; A.N = N; A.w_out = w_out; A.obj = obj; A.kkt = kkt; A.status = status;
-  A.iters = iters; A.fix_flag = h->work_counter + 2; A.opt = ipm_options();
+  A.iters = iters; A.fix_flag = h->work_counter + 2; A.opt = h->ipm;
   int rc = kmpc::dispatch_mpc_solve(A, H, h->sm_count, (cudaStream_t)stream);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_solve: unsupported shape");
@@ -259,7 +267,7 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   A.lam0 = D->lam0; A.tau0 = D->tau0; A.cost_coeff0 = D->cost_coeff0; A.capital0 = D->capital0;
   A.allow_short = D->allow_short; A.B = D->B; A.N = D->N;
   A.history = D->history; A.metrics = D->metrics; A.solve_stats = (long long*)D->solve_stats;
-  A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = ipm_options();
+  A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = h->ipm;
   int rc = kmpc::dispatch_backtest(A, D->H, h->sm_count, st);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_backtest_run: unsupported shape");

@@ -165,15 +165,17 @@ static int ensure_fold(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st);
 // Runs the whole chain for `M` rows.  out_mode 0: latent z0 -> out [M,Z];  1: yhat de-standardised [M,H,N];
 // 2: standardised decoder output, first n_cols columns [M,H,n_cols].
 static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M, int H, int out_mode, int n_cols,
-                     const float* std32, const float* mean32, int stat_rows_per_group, float* out, cudaStream_t st) {
+                     const float* std32, const float* mean32, int stat_rows_per_group, float* out, cudaStream_t st,
+                     const int* gate = nullptr) {
   const int Z = m->Z;
+  auto gated_args = [&] { GemmArgs g = base_args(); g.gate = gate; return g; };
   int maxw = Z;
   for (int v : m->enc_dims) if (v > maxw) maxw = v;
   for (int v : m->dec_dims) if (v > maxw) maxw = v;
   // Row chunks: 4 ping-pong activation buffers + their residual twins.  The chain is compute bound (activation
   // traffic is ~16 KB per row and layer against ~2 MFLOP), so the chunk is sized for full waves of 128-row tiles,
   // not for L2 residency; window views are chunked in whole paths so that tiles never straddle two paths.
-  long long ch = 32768;
+  long long ch = gate ? 8192 : 32768;     // a gated (fallback) chain is rare and slow anyway: keep its scratch small
   if (av.window && av.rows_per_group < M) {
     ch = (ch / av.rows_per_group) * av.rows_per_group;
     if (ch < av.rows_per_group) ch = av.rows_per_group;
@@ -215,7 +217,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
     const bool mlp_enc = (m->kind == KMPC_MODEL_GENERIC) || !m->lista_linear;
     if (mlp_enc) {
       for (int li = 0; li < m->n_enc; ++li) {
-        GemmArgs g = base_args();
+        GemmArgs g = gated_args();
         const bool last = (li == m->n_enc - 1);
         if (li == 0) {
           g.A = av.A; g.A_lo = av.A_lo; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda;
@@ -234,7 +236,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
         x = o; xld = g.Nout;
       }
     } else {   // LISTA linear encoder: c = x @ We^T
-      GemmArgs g = base_args();
+      GemmArgs g = gated_args();
       g.A = av.A; g.A_lo = av.A_lo; g.a_group_stride = av.group_stride; g.a_rows_per_group = av.rows_per_group; g.lda = av.lda; g.row0 = r0;
       g.K = av.K; g.W = av.window ? m->enc_w0_win : m->enc_w[0]; g.W_lo = av.window ? m->enc_w0_win_lo : m->enc_w_lo[0]; g.ldw = av.K;
       g.M = rows; g.Nout = Z; g.n_store = Z; g.C = cbuf; g.ldc = Z;
@@ -246,7 +248,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
       shrink_kernel<<<blocks, 256, 0, st>>>(cbuf, zcur, lo_of_buf(zcur), n, m->lista_thr); h->launches++;
       float* zalt = buf[0];
       for (int it = 0; it < m->lista_loops; ++it) {          // z = shrink(z @ S + c)
-        GemmArgs g = base_args();
+        GemmArgs g = gated_args();
         g.A = zcur; g.A_lo = lo_of_buf(zcur); g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->lista_ST; g.W_lo = m->lista_ST_lo; g.ldw = Z;
         g.M = rows; g.Nout = Z; g.n_store = Z; g.addend = cbuf; g.ld_add = Z; g.act = EPI_SHRINK; g.shrink_thr = m->lista_thr;
         g.C = zalt; g.C_lo = lo_of_buf(zalt); g.ldc = Z;
@@ -265,7 +267,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
     }
     // ---------------- folded read-out: all horizons in one GEMM [rows, Z] x [H*N, Z]^T ----------------
     if (fold) {
-      GemmArgs d = base_args();
+      GemmArgs d = gated_args();
       d.A = zcur; d.A_lo = lo_of_buf(zcur); d.a_rows_per_group = rows; d.lda = Z; d.K = Z;
       d.W = m->fold_w; d.W_lo = m->fold_w_lo; d.ldw = Z;
       d.M = rows; d.Nout = H * m->N; d.n_store = H * m->N; d.bias = m->fold_b;
@@ -279,7 +281,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
     float* znext = (zcur == buf[2]) ? buf[0] : buf[2];
     float* hbuf[2] = {buf[1], buf[3]};
     for (int k = 0; k < H; ++k) {
-      GemmArgs g = base_args();
+      GemmArgs g = gated_args();
       g.A = zcur; g.A_lo = lo_of_buf(zcur); g.a_rows_per_group = rows; g.lda = Z; g.K = Z; g.W = m->kmatT; g.W_lo = m->kmatT_lo; g.ldw = Z;
       g.M = rows; g.Nout = Z; g.n_store = Z; g.C = znext; g.C_lo = lo_of_buf(znext); g.ldc = Z;
       if ((rc = launch_gemm(g, st, &h->launches))) return rc;
@@ -292,7 +294,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
       if (m->kind == KMPC_MODEL_GENERIC) {
         const float* xx = zcur; int xl = Z;
         for (int li = 0; li < m->n_dec; ++li) {
-          GemmArgs d = base_args();
+          GemmArgs d = gated_args();
           const bool last = (li == m->n_dec - 1);
           d.A = xx; d.A_lo = lo_of_buf(xx); d.a_rows_per_group = rows; d.lda = xl; d.K = m->dec_dims[li]; d.W = m->dec_w[li]; d.W_lo = m->dec_w_lo[li]; d.ldw = m->dec_dims[li];
           d.M = rows; d.bias = m->dec_b[li];
@@ -306,7 +308,7 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
           xx = d.C; xl = d.Nout;
         }
       } else {
-        GemmArgs d = base_args();
+        GemmArgs d = gated_args();
         d.A = zcur; d.A_lo = lo_of_buf(zcur); d.a_rows_per_group = rows; d.lda = Z; d.K = Z; d.W = m->lista_wdT; d.W_lo = m->lista_wdT_lo; d.ldw = Z;
         d.M = rows; d.Nout = ncol; d.n_store = ncol; d.C = dst; d.ldc = (long long)H * ncol;
         if (out_mode == 1) { d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = m->N; d.stat_row0 = r0; }
@@ -419,8 +421,9 @@ static int ensure_tc16(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st) {
   return 0;
 }
 
-// GenericKM forecast with fp16-pair operands: encoder MLP + folded read-out, all rows of all paths.
-// Returns 1 when a value left the fp16 range (the caller re-runs the TF32 chain), 0 on success, < 0 on error.
+// GenericKM forecast with fp16-pair operands: encoder MLP + folded read-out, all rows of all paths.  Asynchronous:
+// returns 0 once everything is queued (m->ovf_flag is raised on the device if a value left the fp16 range; the caller
+// queues the 3xTF32 chain behind it, gated on that flag), 1 when a launch turned out not to be eligible, < 0 on error.
 static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int T, int row0, int t0, int t1, int H,
                        const float* std32, const float* mean32, int stat_rows_per_group, float* out, cudaStream_t st) {
   int rc;
@@ -496,9 +499,7 @@ static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int
     if (rc == -100) return 1;
     if (rc) return kmpc_fail_cuda((cudaError_t)rc, "gemm_tc16(read-out)");
   }
-  if ((e = cudaMemcpyAsync(m->ovf_host, m->ovf_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return kmpc_fail_cuda(e, "copy ovf");
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return kmpc_fail_cuda(e, "forecast (fp16-pair chain)");
-  return *m->ovf_host ? 1 : 0;
+  return 0;
 }
 }  // namespace kmpc
 
@@ -630,14 +631,14 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
 }
 
 static int stats_to_f32(kmpc_handle* h, const double* mean, const double* std, int n, float** std32, float** mean32, cudaStream_t st) {
-  // small per-call conversion buffer kept at the tail of the handle (re-allocated if the size grows)
-  static thread_local float* buf = nullptr; static thread_local int cap = 0;
-  if (cap < 2 * n) {
-    if (buf) cudaFree(buf);
-    cudaError_t e = cudaMalloc(&buf, (size_t)2 * n * sizeof(float));
-    if (e != cudaSuccess) { buf = nullptr; cap = 0; return kmpc_fail_cuda(e, "cudaMalloc(stats)"); }
-    cap = 2 * n;
+  // small per-call conversion buffer owned by the handle (hence on the handle's device; re-allocated if it grows)
+  if (h->stats32_cap < 2 * n) {
+    if (h->stats32) cudaFree(h->stats32);
+    cudaError_t e = cudaMalloc(&h->stats32, (size_t)2 * n * sizeof(float));
+    if (e != cudaSuccess) { h->stats32 = nullptr; h->stats32_cap = 0; return kmpc_fail_cuda(e, "cudaMalloc(stats)"); }
+    h->stats32_cap = 2 * n;
   }
+  float* buf = h->stats32;
   int blocks = (n + 255) / 256;
   kmpc::f64_to_f32_kernel<<<blocks, 256, 0, st>>>(std, buf, n);
   kmpc::f64_to_f32_kernel<<<blocks, 256, 0, st>>>(mean, buf + n, n);
@@ -659,10 +660,14 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
   if (rc) return rc;
   const int rpp = t1 - t0;
   kmpc_model* mm = const_cast<kmpc_model*>(m);
+  const int* gate = nullptr;
   if (kmpc::tc16_eligible(m) && rpp >= 1 && B * rpp >= 128) {
-    // fp16-pair tensor-core chain (gemm_tc16.cu); synchronises the stream to read the range flag
+    // fp16-pair tensor-core chain (gemm_tc16.cu).  Its epilogues raise mm->ovf_flag on the device when a value leaves
+    // the fp16 range (|x| > 65504); the 3xTF32 chain is queued behind it with that flag as its gate and overwrites the
+    // forecasts in that case only: no host synchronisation, the call stays asynchronous on `stream`.
     rc = kmpc::run_chain16(h, mm, z, B, T, row0, t0, t1, H, std32, mean32, stats_per_path ? rpp : 0, yhat, st);
-    if (rc <= 0) return rc;
+    if (rc < 0) return rc;
+    if (rc == 0) gate = mm->ovf_flag;
   }
   // residual twin of the series for the 3xTF32 operand split of the first layer
   const size_t zn = (size_t)B * T * ld_z;
@@ -673,14 +678,14 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
     if (e != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(z_lo)");
     mm->z_lo_cap = zn;
   }
-  rc = kmpc::launch_split_lo(z, mm->z_lo, (long long)zn, st);
+  rc = kmpc::launch_split_lo(z, mm->z_lo, (long long)zn, st, gate);
   h->launches++;
   if (rc) return kmpc_fail_cuda((cudaError_t)rc, "split_lo(series)");
   kmpc::AView av;
   av.A = z + (size_t)(row0 + t0) * ld_z; av.A_lo = mm->z_lo + (size_t)(row0 + t0) * ld_z;
   av.group_stride = (long long)T * ld_z; av.rows_per_group = rpp; av.lda = ld_z;
   av.K = m->d * ld_z; av.window = true;
-  return kmpc::run_chain(h, m, av, B * rpp, H, 1, m->N, std32, mean32, stats_per_path ? rpp : 0, yhat, st);
+  return kmpc::run_chain(h, m, av, B * rpp, H, 1, m->N, std32, mean32, stats_per_path ? rpp : 0, yhat, st, gate);
 }
 
 int kmpc_encode(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, float* latent, void* stream) {

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "per_device.cuh"
 
 namespace kmpc {
 
@@ -42,6 +43,9 @@ struct GemmArgs {
   int n_store;
   // optional second output holding the fp32 residual of the TF32 rounding of C (3xTF32 operand split)
   float* C_lo;
+  // optional device flag: the kernel does nothing unless *gate != 0 (the 3xTF32 chain queued behind the fp16-pair
+  // chain runs only when that chain raised its range flag; no host synchronisation in between)
+  const int* gate;
 };
 
 // fp16-pair tensor-core path (gemm_tc16.cu): an fp32 value x travels as hi = fp16(x), lo = fp16((x - hi) * 2^11)
@@ -73,7 +77,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 // tcgen05 3xTF32 path; returns -100 when the launch is not eligible (shape, alignment, missing twins)
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 void set_gemm_tc_mode(int on);
-int launch_split_lo(const float* x, float* lo, long long n, cudaStream_t st);
+int launch_split_lo(const float* x, float* lo, long long n, cudaStream_t st, const int* gate = nullptr);
 int launch_gemm(const GemmArgs& g, cudaStream_t st, long long* launches);
 
 __device__ __forceinline__ float epilogue_apply(float x, int act, float thr) {

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Ws[2][BK][BN + 4];
   const int tid = threadIdx.x;
+  if (g.gate && *g.gate == 0) return;           // gated launch (see GemmArgs::gate)
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   // loader mapping: each thread loads 2 rows x 4 k of A and of W per k-tile (128 rows x 16 k = 512 float4)
   const int lr = tid >> 2;            // 0..63

@@ -49,6 +49,7 @@ struct Params {
   int act; float shrink_thr;
   const float* std32; const float* mean32; int stat_rows_per_group; int stat_ld; int row0; int stat_mod;   // de-standardise epilogue
   float* C; float* C_lo; long long ldc; int n_store;
+  const int* gate;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,6 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.gate && *p.gate == 0) return;           // gated launch (see GemmArgs::gate): uniform over the grid
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -416,6 +418,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.bias = g.bias; p.addend = g.addend; p.ld_add = g.ld_add; p.act = g.act; p.shrink_thr = g.shrink_thr;
   p.C = g.C; p.C_lo = g.C_lo; p.ldc = g.ldc; p.n_store = g.n_store < g.Nout ? g.n_store : g.Nout;
   p.std32 = g.std32; p.mean32 = g.mean32; p.stat_rows_per_group = g.stat_rows_per_group; p.stat_ld = g.stat_ld; p.row0 = g.stat_row0; p.stat_mod = g.stat_mod;
+  p.gate = g.gate;
 
   const long long a_off = flat ? (long long)g.row0 * g.lda
                                : (long long)(g.row0 / g.a_rows_per_group) * g.a_group_stride;
@@ -435,33 +438,33 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (!encode(&mW, g.W, 2, dims, strides, box)) return -100;
     if (!encode(&mWlo, g.W_lo, 2, dims, strides, box)) return -100;
   }
-  static int sm_count = 0;
-  static bool attr_set = false;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
-  if (!attr_set) {
-    int dev = 0;
+  static PerDeviceInt sm_table;           // SM count; the shared-memory attribute is set on the same first use
+  const int sm_count = sm_table.get([&] {
+    int dev = 0, n = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+    return n;
+  });
   int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
   gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mA, mAlo, mW, mWlo, p);
   return (int)cudaGetLastError();
 }
 
 // x_lo = x - top19bits(x) for a whole buffer (weights at load time, the standardised series per forecast call)
-__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n, const int* __restrict__ gate) {
+  if (gate && *gate == 0) return;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
     lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
   }
 }
-int launch_split_lo(const float* x, float* lo, long long n, cudaStream_t st) {
+int launch_split_lo(const float* x, float* lo, long long n, cudaStream_t st, const int* gate) {
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  split_lo_kernel<<<(int)blocks, 256, 0, st>>>(x, lo, n);
+  split_lo_kernel<<<(int)blocks, 256, 0, st>>>(x, lo, n, gate);
   return (int)cudaGetLastError();
 }
 

@@ -459,16 +459,15 @@ int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st) {
     if (!encode(&mW, g.W_hi, 2, dims, strides, box)) return -100;
     if (!encode(&mWlo, g.W_lo, 2, dims, strides, box)) return -100;
   }
-  static int sm_count = 0;
-  static bool attr_set = false;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
-  if (!attr_set) {
-    int dev = 0;
+  static PerDeviceInt sm_table;           // SM count; the shared-memory attribute is set on the same first use
+  const int sm_count = sm_table.get([&] {
+    int dev = 0, n = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(gemm_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+    return n;
+  });
   int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
   gemm_tc16_kernel<<<grid, NUM_THREADS, smem, st>>>(mA, mAlo, mW, mWlo, p);
   return (int)cudaGetLastError();

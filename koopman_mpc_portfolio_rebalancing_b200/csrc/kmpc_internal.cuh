@@ -2,7 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "mpc_ipm.cuh"
+#include "per_device.cuh"
+#include "mpc_common.cuh"
 
 namespace kmpc {
 
@@ -53,8 +54,6 @@ int mv_supported(int H, int N);
 int launch_mpc_mv(const double* mu, const double* sigma, long long sigma_stride, const double* w_cur, double gamma, double lam,
                   int allow_short, int P, int H, int N, double* w_out, double* obj, double* kkt, int* status, int* iters,
                   int sm_count, cudaStream_t st);
-void set_mpc_mode(int mode);
-int get_mpc_mode();
 int launch_standardize(const double* y, const double* mean, const double* sd, int spp, int B, int T, int N, float* out,
                        int ld, int sm_count, cudaStream_t st);
 int launch_embed_gather(const float* data, int ld, int B, int T, int N, int d, float* out, int sm_count, cudaStream_t st);
@@ -69,4 +68,7 @@ struct kmpc_handle {
   int* work_counter;      // device int for the persistent backtest kernel
   void* scratch;          // device workspace (forecast activations), grown on demand
   size_t scratch_bytes;
+  float* stats32;         // device [stats32_cap] fp32 copies of (std, mean) for the forecast epilogue
+  int stats32_cap;
+  kmpc::IpmOptions ipm;   // solver options of this handle (kmpc_set_solver_param)
 };

@@ -1,5 +1,5 @@
 // Lane-per-asset layout of the fp64 interior-point MPC solver (same central path and Newton system as
-// mpc_ipm.cuh / oracle/mpc_oracle.py::solve_structured(apply="sweep"); see mpc_ipm.cuh for the program).
+// oracle/mpc_oracle.py::solve_structured(apply="sweep"); see mpc_common.cuh for the program).
 //
 // Why a third layout (profiles/r1_backtest_cta_kernel.txt): the warp- and CTA-per-problem kernels execute
 // ~350 k warp instructions per decision of which 17 % are fp64 math; the rest is predication on a runtime stage
@@ -30,7 +30,7 @@
 //   pieces    = begin / check / factor_a / factor_b / newton_phase, so that the persistent backtest kernel
 //               (mpc_lane_kernels.cuh) can walk several problems of one SM through an iteration together.
 #pragma once
-#include "mpc_ipm.cuh"
+#include "mpc_common.cuh"
 
 namespace kmpc {
 
@@ -771,7 +771,8 @@ struct LaneIpm {
     gap_ = gap;
     if (uni(!isfinite(gap) || (near && !isfinite(dres)))) return finish(ST_FAILED);
     if (uni(pres < opt.tol && dres < opt.tol_dual && gap < opt.tol)) return ST_OPTIMAL;
-    // flat directions (curvature << delta): see mpc_ipm.cuh
+    // flat directions (curvature << delta): the dual residual crawls at ~delta*|dx| while the gap has long
+    // collapsed; the objective is converged -> "optimal_inaccurate" instead of iterating into round-off
     if (uni(pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6)) return ST_INACCURATE;
     if (it_ == opt.max_iter + 1) return finish(ST_FAILED);
     mu_ = div_fast(gap, fmax(mcount_, 1.0));

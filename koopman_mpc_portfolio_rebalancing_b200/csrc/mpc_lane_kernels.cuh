@@ -1,11 +1,10 @@
-// Kernels around the lane-per-asset IPM solver (mpc_lane.cuh): same entry points and semantics as
-// mpc_kernels.cuh (mpc_solve = mpc.py:27-117, backtest = backtest.py:173-249).  mpc_solve: one block of G warps per
+// Kernels around the lane-per-asset IPM solver (mpc_lane.cuh): mpc_solve = mpc.py:27-117, backtest =
+// backtest.py:173-249.  mpc_solve: one block of G warps per
 // problem; backtest: a persistent block hosts several backtests ("slots" of G warps each) that walk through the
 // Newton iteration together.  Thread i of a slot = asset i, all stages of an asset in that thread's registers.
 #pragma once
 #include "kmpc_internal.cuh"
 #include "mpc_lane.cuh"
-#include <stdlib.h>
 #include <stdio.h>
 
 // register budget of the backtest kernel: __maxnreg__ and __launch_bounds__ are mutually exclusive
@@ -67,7 +66,7 @@ mpc_solve_lane_kernel(MpcSolveArgs A, int want) {
     int iters; double kkt[3];
     const int st = s.solve(w0, N, lam, tau, A.allow_short != 0, opt, iters, kkt);
     double val = CUDART_NAN;
-    if (st <= ST_INACCURATE) { s.clip_first_trade(w0); val = s.objective(w0); }
+    if (st <= ST_INACCURATE) { if (opt.clip_first_trade) s.clip_first_trade(w0); val = s.objective(w0); }
     if (s.valid) {
 #pragma unroll
       for (int k = 0; k < H; ++k) A.w_out[((size_t)p * H + k) * N + s.tid] = s.w[k];
@@ -163,7 +162,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         s.template block_sum<3>(v, T);
         double turnover = T[0];
         double port_ret = market ? T[1] : 0.0;
-        if (s.tau > 0.0 && turnover > s.tau) {
+        if (opt.clip_first_trade && s.tau > 0.0 && turnover > s.tau) {
           // An iterate accepted after the factorisation broke down next to the optimum (status optimal_inaccurate)
           // can sit ~1e-5 outside the turnover cap, whose slack the iteration does not re-derive from w: pull the
           // trade back onto the cap along its own direction (budget and sign constraints are kept).
@@ -286,8 +285,9 @@ static int lane_fix_plan(const double* lam, const double* tau, double lam0, doub
 template <int H, int G>
 static int launch_mpc_lane(const MpcSolveArgs& A, int sm_count, cudaStream_t st) {
   const size_t smem = (size_t)LaneIpm<H, G, (G > 4 || H > 5), false>::SMEM_DOUBLES * sizeof(double);
-  static const int bps0 = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, false>, 32 * G, smem);
-  static const int bps1 = lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, true>, 32 * G, smem);
+  static PerDeviceInt t0, t1;          // blocks per SM (and the shared-memory attribute) of the two instantiations
+  const int bps0 = t0.get([&] { return lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, false>, 32 * G, smem); });
+  const int bps1 = t1.get([&] { return lane_blocks_per_sm(mpc_solve_lane_kernel<H, G, true>, 32 * G, smem); });
   const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.P, A.fix_flag, st);
   auto nblocks = [&](int bps) { int b = A.P < sm_count * bps ? A.P : sm_count * bps; return b < 1 ? 1 : b; };
   if (plan != 0) mpc_solve_lane_kernel<H, G, true><<<nblocks(bps1), 32 * G, smem, st>>>(A, plan == 2 ? 1 : -1);
@@ -296,12 +296,11 @@ static int launch_mpc_lane(const MpcSolveArgs& A, int sm_count, cudaStream_t st)
 }
 template <int H, int G>
 static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) {
-  // KMPC_LANE_PAD_KB (tuning experiments only): extra dynamic shared memory per block, lowers the blocks per SM
-  static const size_t pad = getenv("KMPC_LANE_PAD_KB") ? (size_t)atoi(getenv("KMPC_LANE_PAD_KB")) * 1024 : 0;
   constexpr int P = LaneSlots<G>::P;
-  const size_t smem = (size_t)P * LaneIpm<H, G, (G > 4 || H > 5), false>::SMEM_DOUBLES * sizeof(double) + pad;
-  static const int bps0 = lane_blocks_per_sm(backtest_lane_kernel<H, G, P, false>, 32 * G * P, smem);
-  static const int bps1 = lane_blocks_per_sm(backtest_lane_kernel<H, G, P, true>, 32 * G * P, smem);
+  const size_t smem = (size_t)P * LaneIpm<H, G, (G > 4 || H > 5), false>::SMEM_DOUBLES * sizeof(double);
+  static PerDeviceInt t0, t1;
+  const int bps0 = t0.get([&] { return lane_blocks_per_sm(backtest_lane_kernel<H, G, P, false>, 32 * G * P, smem); });
+  const int bps1 = t1.get([&] { return lane_blocks_per_sm(backtest_lane_kernel<H, G, P, true>, 32 * G * P, smem); });
   const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.B, A.fix_flag, st);
   const int want = (A.B + P - 1) / P;
   auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };

@@ -6,7 +6,7 @@
 // Same fp64 primal-dual interior point as the log-utility solver (Mehrotra predictor-corrector, split steps,
 // epigraph u >= |w_t - w_{t-1}| eliminated per asset, proximal term delta, loose acceptance), but the stage cost has a
 // DENSE Hessian 2 gamma Sigma, so the reduced Newton matrix  M = blockdiag(2 gamma Sigma) + T  (T = the per-asset
-// tridiagonal of mpc_ipm.cuh) is factorised densely: one warp per problem, M (n x n, n = H N <= 160) in the warp's
+// tridiagonal of mpc_lane.cuh) is factorised densely: one warp per problem, M (n x n, n = H N <= 160) in the warp's
 // slice of shared memory, in-place Cholesky, triangular solves for the right-hand side and the H budget columns, an
 // H x H Schur complement for the budget multipliers.  Lane l owns variables l, l+32, ... (v = t N + i).
 // The reference's only caller is MarkowitzStrategy (baselines.py:24-106) with H = 1, N assets: n = N.
@@ -89,7 +89,7 @@ mpc_mv_kernel(MvArgs A) {
     int status = ST_FAILED, iters = 0;
     double kkt[3] = {CUDART_NAN, CUDART_NAN, CUDART_NAN};
     if (__any_sync(kFull, bad)) status = ST_NONFINITE;
-    // ---- initial point (oracle _initial_point with tau = 0; dual-feasible start as in mpc_ipm.cuh) -------------
+    // ---- initial point (oracle _initial_point with tau = 0; dual-feasible start as in mpc_lane.cuh) -------------
     double delta = opt.delta;
     if (status != ST_NONFINITE) {
       double sb = 0.0;
@@ -431,11 +431,18 @@ int launch_mpc_mv(const double* mu, const double* sigma, long long sigma_stride,
   A.iters = iters; A.opt = default_ipm_options();
   const int n = H * N, ldm = n | 1;
   const size_t smem = ((size_t)n * ldm + (size_t)(H + 1) * n + n + (size_t)H * (H + 1) + 8) * sizeof(double);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(mpc_mv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
+  // the attribute is per device and monotone: raise it whenever this device has not seen a request this large
+  static int attr_smem[PerDeviceInt::kMaxDevices] = {};
+  static std::mutex attr_mu;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(attr_mu);
+    if (dev < 0 || dev >= PerDeviceInt::kMaxDevices || (int)smem > attr_smem[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(mpc_mv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      if (dev >= 0 && dev < PerDeviceInt::kMaxDevices) attr_smem[dev] = (int)smem;
+    }
   }
   int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
   if (per_sm < 1) per_sm = 1;

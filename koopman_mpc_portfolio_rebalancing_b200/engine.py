@@ -202,20 +202,33 @@ def run_grid(models, n_assets: int, delay: int, log_returns, mean, std, lam_grid
     return out
 
 
+def bootstrap_indices(n_paths: int, length: int, n_hist: int, seed: int, offset: int = 0, device="cpu"):
+    """Row indices of the iid bootstrap: idx[p, t] = mix64(seed, offset + p, t) mod n_hist, a counter-based generator
+    (the splitmix64 finaliser on a per-(path, day) counter) evaluated for all paths at once.  Path `offset + p` gets the
+    same indices whatever the shard boundaries are, on any device, so a rank regenerates exactly its own shard."""
+    import torch
+    dev = torch.device(device)
+    p = torch.arange(offset, offset + n_paths, dtype=torch.int64, device=dev).unsqueeze(1)
+    t = torch.arange(length, dtype=torch.int64, device=dev).unsqueeze(0)
+    # int64 arithmetic wraps modulo 2^64 (two's complement): exactly splitmix64 on unsigned counters
+    x = (p * 0x100000001B3 + t) * (-7046029254386353131) + (int(seed) * 2 + 1) * 0x632BE59BD9B4E019 % (1 << 63)
+    def shr(v, k):                                   # logical shift right of a signed int64
+        return (v >> k) & ((1 << (64 - k)) - 1)
+    x = (x ^ shr(x, 30)) * (-4658895280553007687)    # 0xBF58476D1CE4E5B9
+    x = (x ^ shr(x, 27)) * (-7723592293110705685)    # 0x94D049BB133111EB
+    x = x ^ shr(x, 31)
+    return shr(x, 1) % int(n_hist)                   # 63 uniform bits; modulo bias < n_hist / 2^63
+
+
 def bootstrap_paths(hist_log_returns, n_paths: int, length: int, seed: int, device="cuda", offset: int = 0):
     """Monte-Carlo stress paths (BASELINE config 5): iid row bootstrap of one historical block [T_hist, N].
-    Indices come from a Philox generator seeded with ``seed`` and advanced by ``offset`` paths, so that a rank can
-    regenerate exactly its own shard (no scatter).  Returns (log_returns [n_paths, length, N] f64 CUDA, idx int64)."""
+    Indices come from the counter-based generator of ``bootstrap_indices`` (seed, path number, day), so that a rank
+    regenerates exactly its own shard with ``offset`` = its first path (no scatter).  Returns (log_returns
+    [n_paths, length, N] f64 on ``device``, idx int64)."""
     import torch
     dev = torch.device(device)
     hist = torch.as_tensor(hist_log_returns).to(dev, dtype=torch.float64)
-    g = torch.Generator(device=dev)
-    g.manual_seed(int(seed))
-    # one draw per path keeps path p identical whatever the shard boundaries are
-    idx = torch.empty((n_paths, length), dtype=torch.int64, device=dev)
-    for p in range(n_paths):
-        g.manual_seed(int(seed) * 1_000_003 + offset + p)
-        idx[p] = torch.randint(0, hist.shape[0], (length,), generator=g, device=dev)
+    idx = bootstrap_indices(n_paths, length, hist.shape[0], seed, offset, dev)
     return hist[idx], idx
 
 

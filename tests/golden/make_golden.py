@@ -167,6 +167,49 @@ def gen_forecasts():
     np.savez(os.path.join(HERE, "forecast_lista_mlp_meta.npz"), L=50.0, alpha=0.5, loops=cfg.MODEL.ENCODER.LISTA.NUM_LOOPS)
 
 
+def gen_forecast_cfg2():
+    """BASELINE config 2 at its FULL architecture (finance_sparse code defaults: 1000 -> 1024 -> 1024 -> 1024, linear
+    decoder, the weights bench.py uses) through the reference model.py (torch CPU fp32), the forecast loop of
+    KoopmanMPCStrategy.rebalance (backtest.py:85-121) on 2 scenario paths x 246 rows of the bench inputs
+    (bench.make_inputs(cfg2, 2, 10_000): GBM paths 10 000 and 10 001).  Also the same forecasts from the model in
+    float64 (model.double()) to bound the reference's own fp32 rounding."""
+    import bench
+    w = bench.WORKLOADS["cfg2"]
+    N, d, H, Z, rows = w["N"], w["d"], w["H"], w["Z"], w["rows"]
+    ns = rows - 1 - H
+    cfg = ref_config.get_config("finance_sparse")
+    assert cfg.MODEL.TARGET_SIZE == Z and list(cfg.MODEL.ENCODER.LAYERS) == w["enc"]
+    sd = synthetic.generic_km_weights(0, N * d, w["enc"], Z)
+    model = ref_model.make_model(cfg, N * d)
+    model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    lr, mean, std, T = bench.make_inputs(w, 2, 10_000)
+    yh32, yh64 = [], []
+    torch.set_num_threads(8)
+    for b in range(2):
+        frame = pd.DataFrame(lr[b])
+        z = ((frame - mean[b]) / std[b]).values.astype(np.float32)       # standardize_returns + the f32 cast (data_finance.py:243-259, :331)
+        emb = ref_data.time_delay_embedding(z, d)
+        env = EnvLike(N, mean[b], std[b])
+        yh32.append(ref_forecast(model, env, emb[:ns], H))
+        m64 = ref_model.make_model(cfg, N * d).double()
+        m64.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)).double() for k, v in sd.items()}, strict=True)
+        out = []
+        with torch.no_grad():
+            m64.eval()
+            zz = m64.encode(torch.from_numpy(emb[:ns]).double())
+            for _ in range(H):
+                zz = m64.step_latent(zz)
+                x = m64.decode(zz)[..., :N]
+                out.append((x * torch.from_numpy(std[b]) + torch.from_numpy(mean[b])).numpy())
+        yh64.append(np.stack(out, axis=1))
+    torch.set_num_threads(1)
+    yh32 = np.stack(yh32).astype(np.float32); yh64 = np.stack(yh64)
+    rel = np.abs(yh32 - yh64).reshape(2 * ns, -1).max(1) / np.abs(yh64).reshape(2 * ns, -1).max(1)
+    print("cfg2 forecast golden: reference fp32 vs its own fp64 model, worst row-wise rel", rel.max())
+    np.savez_compressed(os.path.join(HERE, "forecast_cfg2.npz"), yhat=yh32, yhat_f64model=yh64.astype(np.float32),
+                        seed=10_000, paths=2, ns=ns)
+
+
 def cfg1_model():
     cfg = ref_config.get_config("finance_sparse")
     cfg.MODEL.TARGET_SIZE = 128
@@ -394,6 +437,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "data":
         gen_data_small()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "forecast_cfg2":
+        gen_forecast_cfg2()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoints":
         gen_checkpoints()
         sys.exit(0)
@@ -408,6 +454,7 @@ if __name__ == "__main__":
         sys.exit(0)
     gen_data_small()
     gen_forecasts()
+    gen_forecast_cfg2()
     gen_cfg1()
     gen_dmd()
     gen_rollouts()

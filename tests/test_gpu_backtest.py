@@ -6,16 +6,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["lane", "cta", "warp"], autouse=True)
-def mpc_kernel_layout(request):
-    """every test runs against the three kernel layouts: thread = asset (default), thread = (stage, asset), and
-    one warp per problem"""
-    from koopman_mpc_portfolio_rebalancing_b200 import _capi
-    _capi.lib().kmpc_set_mpc_kernel({"lane": 2, "cta": 1, "warp": 0}[request.param])
-    yield request.param
-    _capi.lib().kmpc_set_mpc_kernel(2)
-
-
 def _mods():
     import torch
     from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt
@@ -99,10 +89,8 @@ def test_rebalance_freq_and_short_horizon():
     assert np.allclose(hist[:, 0], rh[:, 0], rtol=1e-6)
 
 
-def test_config3_shape_backtest_vs_oracle_loop(mpc_kernel_layout):
+def test_config3_shape_backtest_vs_oracle_loop():
     """500 assets, H = 10 (BASELINE config 3 shape): persistent backtest kernel vs the oracle loop on a few steps."""
-    if mpc_kernel_layout != "lane":
-        pytest.skip("shape is compiled for the lane layout only")
     torch, bt, bo, do = _mods()
     rng = np.random.default_rng(33)
     B, N, H, rows = 2, 500, 10, 17

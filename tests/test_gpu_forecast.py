@@ -82,6 +82,45 @@ def test_cfg1_vs_reference_and_strict_keys(golden):
     check_model(m, g)
 
 
+def test_config2_full_architecture_vs_reference_golden(golden):
+    """BASELINE config 2 at its full architecture (1000 -> 1024 -> 1024 -> 1024 + linear decoder, the bench weights and
+    the first two bench paths) against the reference model.py run on CPU in fp32 (tests/golden/forecast_cfg2.npz, made
+    by make_golden.py::gen_forecast_cfg2): the default chain (fp16-pair tcgen05 GEMMs + folded [1024 x 250] multi-horizon
+    read-out), the 3xTF32 chain with the folded read-out, and the unfolded step-by-step 3xTF32 chain all sit within
+    1e-5 row-wise of the reference — and of the reference's own float64 model, which bounds the reference's rounding."""
+    import torch
+    import bench
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, data_finance as df, model as km, synthetic
+    g = golden("forecast_cfg2.npz")
+    w = bench.WORKLOADS["cfg2"]
+    N, d, H, Z, rows = w["N"], w["d"], w["H"], w["Z"], w["rows"]
+    ns = int(g["ns"])
+    lr, mean, std, T = bench.make_inputs(w, int(g["paths"]), int(g["seed"]))
+    # 128 more paths behind the two golden ones: full 128-row tiles and several of them, like the bench
+    lr2, mean2, std2, _ = bench.make_inputs(w, 64, 777)
+    lr_all = np.concatenate([lr, lr2]); mean_all = np.concatenate([mean, mean2]); std_all = np.concatenate([std, std2])
+    m = km.make_model(km.model_config("GenericKM", Z, w["enc"], enc_bias=True), N * d)
+    m.load_state_dict(synthetic.generic_km_weights(0, N * d, w["enc"], Z))
+    z = df.standardize_device(lr_all, mean_all, std_all)
+    mean_d, std_d = torch.from_numpy(mean_all).cuda(), torch.from_numpy(std_all).cuda()
+    L = _capi.lib()
+    got = {}
+    got["fp16 pairs, folded"] = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, ns, H)[:2].cpu().numpy()
+    try:
+        L.kmpc_set_gemm_fp16_pairs(0)
+        got["3xTF32, folded"] = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, ns, H)[:2].cpu().numpy()
+        L.kmpc_set_forecast_fold(0)
+        got["3xTF32, step by step"] = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, ns, H)[:2].cpu().numpy()
+    finally:
+        L.kmpc_set_gemm_fp16_pairs(1); L.kmpc_set_forecast_fold(1)
+    for name, y in got.items():
+        assert y.shape == g["yhat"].shape
+        r32 = max(rowwise_rel(y[b], g["yhat"][b]) for b in range(2))
+        r64 = max(rowwise_rel(y[b], g["yhat_f64model"][b]) for b in range(2))
+        print(f"{name}: vs reference fp32 {r32:.2e}, vs reference model in fp64 {r64:.2e}")
+        assert r32 < FORECAST_RTOL and r64 < FORECAST_RTOL, (name, r32, r64)
+
+
 def test_window_forecast_equals_explicit_embedding(golden):
     """forecast_series reads the delay window in place (permuted first-layer weights): must equal the forecast of
     the materialised embedding, for per-path statistics and a ragged N (padding columns)."""

@@ -170,3 +170,48 @@ def test_mean_variance_oracle_known_answers():
         assert r.status == 0 and abs(r.value + sol.fun) < 1e-9
         assert np.abs(r.w - sol.x[:H * N].reshape(H, N)).max() < 1e-6
         assert abs(mo.mv_objective(r.w, w0, mu, S, g, lam) - r.value) < 1e-15
+
+
+# ---- solver-independent optimality certificate (oracle/mpc_certificate.py) ------------------------------------------
+
+def test_certificate_on_reference_known_answers():
+    """T2 / T3 of the reference's tests/test_mpc.py at their exact optima: zero certified gap; a perturbed plan: a
+    positive gap of the size of its objective loss."""
+    from oracle import mpc_certificate as mc
+    R = np.exp(np.array([[0.1, 0.0]]))
+    c = mc.certify(np.array([[0.6, 0.4]]), np.array([0.5, 0.5]), R, 0.0, 0.2)
+    assert abs(c["value"] - 0.06119156775022542) < 1e-12 and abs(c["gap"]) < 1e-9 and max(c["feas"]) < 1e-12
+    c2 = mc.certify(np.array([[0.55, 0.45]]), np.array([0.5, 0.5]), R, 0.0, 0.2)
+    assert c2["gap"] > 0.9 * (c["value"] - c2["value"]) > 0
+    R3 = np.exp(np.array([[0.0, 0.01]]))
+    c3 = mc.certify(np.array([[1.0, 0.0]]), np.array([1.0, 0.0]), R3, 10.0, 0.2)
+    assert abs(c3["value"]) < 1e-12 and abs(c3["gap"]) < 1e-9
+
+
+@pytest.mark.parametrize("N,H", [(3, 2), (10, 5), (50, 5)])
+def test_certificate_bounds_both_oracles(N, H):
+    """value <= optimum <= upper for the plans of BOTH oracle solvers, within the parity bar (1e-6 relative), over mixed
+    lambda / tau including the uncapped and the cost-free cases; and the certificate rejects a plan that solves a
+    DIFFERENT program (cap ignored / cost ignored), which a twin-vs-twin comparison would not."""
+    from oracle import mpc_certificate as mc
+    rng = np.random.default_rng(31 * N + H)
+    for p in range(6):
+        w0 = rng.dirichlet(np.ones(N) * rng.choice([0.3, 1.0, 5.0]))
+        y = (3e-4 + rng.standard_normal((H, N)) * rng.choice([0.003, 0.01, 0.03])).astype(np.float32)
+        lam = float(rng.choice([1e-3, 0.0, 1e-4, 1e-2])); tau = float(rng.choice([0.2, 0.05, 1.0, 0.0]))
+        R = mo.gross_returns_f32(y)
+        for fn in (mo.solve_structured, mo.solve_dense):
+            r = fn(w0, y, lam, tau)
+            assert r.status == mo.STATUS_OPTIMAL
+            c = mc.certify(r.w, w0, R, lam, tau)
+            assert abs(c["value"] - r.value) < 1e-12
+            assert -1e-9 < c["gap"] < 1e-6 * max(abs(c["value"]), 1e-3), (fn.__name__, p, c)
+            assert c["feas"][0] < 1e-9 and c["feas"][1] < 1e-10 and c["feas"][2] < 1e-9
+    # a plan optimal for a different program is NOT certified for this one
+    w0 = rng.dirichlet(np.ones(N)); y = (rng.standard_normal((H, N)) * 0.02).astype(np.float32)
+    R = mo.gross_returns_f32(y)
+    no_cost = mo.solve_structured(w0, y, 0.0, 1.0)
+    c = mc.certify(no_cost.w, w0, R, 2e-2, 1.0)                   # judged with a cost it ignored
+    assert c["gap"] > 1e-4
+    uncapped = mo.solve_structured(w0, y, 1e-4, 0.0)
+    assert mc.feasibility(uncapped.w, w0, 0.05)[2] > 1e-3         # judged against a cap it ignored
