@@ -214,7 +214,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------------------
 
 def _stats_dict(stats, n_dec):
-    st = stats.sum(dim=0).cpu().numpy() if hasattr(stats, "sum") and stats.dim() == 2 else np.asarray(stats)
+    st = np.asarray(stats, dtype=np.float64)
     return {"iterations_per_decision": float(st[3]) / max(1, n_dec), "optimal": int(st[0]), "inaccurate": int(st[1]),
             "fallback": int(st[2])}
 

@@ -64,9 +64,18 @@ int64_t kmpc_launch_count(const kmpc_handle* h);
 int kmpc_mpc_supported(int H, int N);
 /* Solver options of this handle (defaults: csrc/mpc_common.cuh default_ipm_options).  Tuning / diagnostics only:
  * the parity tests run with the defaults.  KMPC_PARAM_DUAL_INIT = 0 selects the mu0-based starting point. */
-enum { KMPC_PARAM_RESET = 0, KMPC_PARAM_STEP_FRAC = 1, KMPC_PARAM_DUAL_INIT = 2, KMPC_PARAM_MAX_ITER = 3,
-       KMPC_PARAM_CLIP_FIRST_TRADE = 4 /* 1 [default]: an optimal_inaccurate plan whose first trade sits outside the
-                                          turnover cap (by <= 2e-5, a few decisions per million) is scaled back onto it */ };
+enum {
+  KMPC_PARAM_RESET = 0,
+  KMPC_PARAM_STEP_FRAC = 1,
+  KMPC_PARAM_DUAL_INIT = 2,
+  KMPC_PARAM_MAX_ITER = 3,
+  /* 1 [default]: an optimal_inaccurate plan whose first trade sits outside the turnover cap (by <= 2e-5) is scaled back
+   * onto it */
+  KMPC_PARAM_CLIP_FIRST_TRADE = 4,
+  /* 1 [default]: a solve whose first attempt does not end "optimal" is repeated from the cold start with robust
+   * parameters (csrc/mpc_common.cuh kRobust*) */
+  KMPC_PARAM_SECOND_ATTEMPT = 5
+};
 int kmpc_set_solver_param(kmpc_handle* h, int which, double value);
 
 /* ---------------------------------------------------------------------------------------------

@@ -82,6 +82,8 @@ int kmpc_set_solver_param(kmpc_handle* h, int which, double value) {
     case KMPC_PARAM_MAX_ITER:
       if (value < 1.0 || value > 1000.0) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: max_iter must be in [1,1000]");
       h->ipm.max_iter = (int)value; break;
+    case KMPC_PARAM_SECOND_ATTEMPT:
+      h->ipm.second_attempt = (value != 0.0) ? 1 : 0; break;
     case KMPC_PARAM_CLIP_FIRST_TRADE:
       h->ipm.clip_first_trade = (value != 0.0) ? 1 : 0; break;
     case KMPC_PARAM_RESET:

@@ -93,7 +93,7 @@ __global__ void dict_normalize_transpose_kernel(const float* __restrict__ dict, 
 }
 
 // z <- z / ||z||_2 per row (GenericKM 'ball' norm, model.py:751-752; no epsilon, like the reference)
-__device__ __forceinline__ float lo_of(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ float lo_of(float v) { return tf32_residual(v); }
 
 __global__ void row_normalize_kernel(float* __restrict__ z, float* __restrict__ zlo, int M, int Z) {
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

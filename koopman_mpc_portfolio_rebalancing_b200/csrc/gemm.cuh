@@ -80,6 +80,17 @@ void set_gemm_tc_mode(int on);
 int launch_split_lo(const float* x, float* lo, long long n, cudaStream_t st, const int* gate = nullptr);
 int launch_gemm(const GemmArgs& g, cudaStream_t st, long long* launches);
 
+// 3xTF32 operand split: kind::tf32 reads the top 19 bits of an fp32 container, x_hi = trunc19(x), and the residual twin
+// carries x - x_hi (exact in fp32, <= 13 significant bits).  The MMA would TRUNCATE that residual to TF32 as well — a
+// one-sided error of up to 2^-21 |x| that adds up over K (the step-by-step 3xTF32 chain sat at 1.0e-5 of the reference
+// on the config-2 golden); rounding the residual to nearest here halves the bound and removes the bias.
+__device__ __forceinline__ float tf32_residual(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
+  return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float epilogue_apply(float x, int act, float thr) {
   switch (act) {
     case EPI_RELU: return (x < 0.0f) ? 0.0f : x;               // NaN propagates like torch.relu

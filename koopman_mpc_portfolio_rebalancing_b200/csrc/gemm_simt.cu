@@ -123,10 +123,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
         x = __fadd_rn(__fmul_rn(x, g.std32[(long long)sg * g.stat_ld + sn]), g.mean32[(long long)sg * g.stat_ld + sn]);
       }
       g.C[(long long)m * g.ldc + n] = x;
-      if (g.C_lo) {
-        const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-        g.C_lo[(long long)m * g.ldc + n] = x - hi;
-      }
+      if (g.C_lo) g.C_lo[(long long)m * g.ldc + n] = tf32_residual(x);
     }
   }
 }

@@ -177,7 +177,7 @@ __device__ __forceinline__ void store_block_fast(const Params& p, const float (&
     for (int j4 = 0; j4 < 4; ++j4) {
       float lo[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const float t = x[j4 * 4 + j]; lo[j] = t - __uint_as_float(__float_as_uint(t) & 0xffffe000u); }
+      for (int j = 0; j < 4; ++j) { const float t = x[j4 * 4 + j]; lo[j] = tf32_residual(t); }
       lrow[j4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
@@ -334,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + sn]), p.mean32[sg * p.stat_ld + sn]);
               }
               x[j] = t;
-              lo[j] = t - __uint_as_float(__float_as_uint(t) & 0xffffe000u);
+              lo[j] = tf32_residual(t);
             }
             if (full) {
               *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(x[0], x[1], x[2], x[3]);
@@ -457,7 +457,7 @@ __global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__
   if (gate && *gate == 0) return;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
-    lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    lo[i] = tf32_residual(v);
   }
 }
 int launch_split_lo(const float* x, float* lo, long long n, cudaStream_t st, const int* gate) {

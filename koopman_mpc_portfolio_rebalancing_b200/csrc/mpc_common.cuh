@@ -31,6 +31,7 @@ struct IpmOptions {
   double mu0;
   double dual_init;
   int max_iter;
+  int second_attempt;     // 1: a solve that does not end "optimal" is repeated with the robust parameters (kRobust*)
   int clip_first_trade;   // 1: pull the executed trade of an optimal_inaccurate plan back onto the turnover cap
 };
 
@@ -41,6 +42,7 @@ __host__ __device__ inline IpmOptions default_ipm_options() {
   // failure rate (3 fallbacks per million), 9.8 -> 8.9 on the mix with zero failures
   o.tol = 1e-10; o.tol_dual = 1e-8; o.delta = 1e-5; o.step_frac = 0.9999; o.mu0 = 1e-3; o.dual_init = 1e-3;
   o.max_iter = 100;
+  o.second_attempt = 1;
   o.clip_first_trade = 1;
   return o;
 }
@@ -52,6 +54,14 @@ __host__ __device__ inline IpmOptions default_ipm_options() {
 // the optimal objective and 4e-4 of the optimal first-stage weights, whereas holding the weights (the fallback) is
 // 0.1 away.
 constexpr double kLoosePres = 1e-8, kLooseDres = 1e-4, kLooseGap = 1e-7;
+// Second attempt of a solve whose first (aggressive) attempt did not end "optimal": restart from the cold starting point
+// with textbook-robust parameters — one common primal/dual step length, a shorter fraction to the boundary, a centring
+// floor and a weaker proximal term (oracle/mpc_oracle.py ROBUST_*; the parameterisation of the dense oracle).  On the
+// ~50 decisions per million of a config-2 step that the first attempt leaves "optimal_inaccurate" (near-degenerate
+// optima: the dual residual stalls at 1e-7..1e-5 while the gap collapses; a few of them 2-5e-6 off the optimal
+// objective) the second attempt reaches "optimal" on every one.
+constexpr double kRobustStepFrac = 0.995, kRobustSigmaMin = 0.05, kRobustDelta = 1e-7;
+constexpr int ST_RESTART = -2;          // LaneIpm::check(): call begin() again for the second attempt
 // Mehrotra's second-order term is scaled by min(1, affine step / kCorrFull): see oracle/mpc_oracle.py (CORRECTOR_FULL_STEP)
 constexpr double kCorrFull = 0.3;
 // lane kernel: factorisation breakdowns answered by a stronger proximal term before the decision falls back

@@ -77,6 +77,64 @@ struct KMap {
 template <int H>
 __device__ __constant__ KMap<H> g_kmap{};
 
+// Tensor-core assembly of the border matrix (H <= 5, non-LOC kernels).  Per asset the Green's functions of the path
+// network are semi-separable: with T_k = tR_1 ... tR_k,  G[l][j] = T_l * (gjj_j / T_j) for l >= j, and the edge drops
+// D, DD factor the same way (all products / quotients of positive numbers: componentwise accurate).  Every entry of K is
+// therefore ONE inner product over the assets of a left column X[.][m] with a right column Y[.][n]:
+//   X = [ P_R(H) | P_1(H) | Pe2(H) ],   P_R[k] = R_k T_k,  P_1[k] = T_k,  Pe2[k] = ph_k qR_k T_{k-1}  (0 for k = 0)
+//   Y = [ Q_R(H) | Q_1(H) | Qe1(H) | Qe3(H-1) | d(H) ],  Q_R[k] = R_k gjj_k / T_k,  Q_1[k] = gjj_k / T_k,
+//       Qe1[k] = -ph_k qL_k gjj_k / T_k,  Qe3[k] = -ph_k vd_k fL_k / T_k,  d[k] = ph_k^2 vd_k + ie_k (diagonal of the
+//       cap block; summed against the constant column P_1[0] = 1).
+// K = X' Y is a [3H x 5H-1] product with the asset axis as the contraction: fp64 mma.sync.m8n8k4 (DMMA), 2 x 3 tiles of
+// 8 x 8 at H = 5, each warp contracting over its own 32 assets.  KDst maps a position of that product to its entry of
+// the lower triangle of K (or -1: the 60 % of the products that the triangle structure does not need).
+template <int H>
+struct KDst {
+  static constexpr int NB = 3 * H;
+  static constexpr int MT = (3 * H + 7) / 8;            // 8-row tiles of X' (M side)
+  static constexpr int NTL = (5 * H - 1 + 7) / 8;       // 8-column tiles of Y (N side)
+  short dst[MT * NTL * 2][32];                          // [tile * 2 + element][lane]
+  static constexpr int of(int m, int n) {
+    if (m >= 3 * H || n >= 5 * H - 1) return -1;
+    const int a = m / H, l = m % H;                     // a: 0 P_R, 1 P_1, 2 Pe2
+    if (n >= 4 * H - 1) {                               // diagonal slots, summed against the ones column P_1[0]
+      const int k = n - (4 * H - 1);
+      return (a == 1 && l == 0) ? (2 * H + k) * NB + 2 * H + k : -1;
+    }
+    const int b = n / H, j = n % H;                     // b: 0 Q_R, 1 Q_1, 2 Qe1, 3 Qe3
+    if (a <= 1 && b <= 1) {
+      if (l < j) return -1;
+      if (a == 0 && b == 0) return l * NB + j;                          // (Rt_l, Rt_j)
+      if (a == 1 && b == 0) return (H + l) * NB + j;                    // (1t_l, Rt_j)
+      if (a == 0 && b == 1) return (l > j) ? (H + j) * NB + l : -1;     // (1t_j, Rt_l)
+      return (H + l) * NB + H + j;                                      // (1t_l, 1t_j)
+    }
+    if (a == 2) {                                       // edge l, source node / edge j strictly to its left
+      if (!(l > j)) return -1;
+      if (b == 0) return (2 * H + l) * NB + j;                          // (et_l, Rt_j)
+      if (b == 1) return (2 * H + l) * NB + H + j;                      // (et_l, 1t_j)
+      if (b == 3) return (2 * H + l) * NB + 2 * H + j;                  // (et_l, et_j)
+      return -1;
+    }
+    if (b == 2) return (j <= l) ? (2 * H + j) * NB + (a == 0 ? l : H + l) : -1;   // edge j at or left of node l
+    return -1;
+  }
+  constexpr KDst() : dst() {
+    for (int mt = 0; mt < MT; ++mt)
+      for (int nt = 0; nt < NTL; ++nt)
+        for (int e = 0; e < 2; ++e)
+          for (int lane = 0; lane < 32; ++lane)
+            dst[(mt * NTL + nt) * 2 + e][lane] = (short)of(8 * mt + lane / 4, 8 * nt + 2 * (lane % 4) + e);
+  }
+};
+template <int H>
+__device__ const KDst<H> g_kdst{};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // LOC = true ("large" problems, e.g. 500 assets x 10 stages): the per-asset sweep factors and corrector targets are
 // thread-private arrays instead of shared-memory columns (a problem's 100+ rows x 512 assets do not fit an SM's
 // shared memory); together with the iterate they exceed the register file and ptxas keeps the excess in local
@@ -100,7 +158,13 @@ struct LaneIpm {
   static constexpr int OFF_FAC = 0;
   static constexpr int OFF_TILE = OFF_FAC + (LOC ? 0 : FAC_ROWS * NT);      // reduction tile, rows of LD doubles
   static constexpr int SMALL_ROWS = NB + 1;                                 // rows usable while the targets are live
-  static constexpr int TILE_A = KB * LD;
+  // border assembly on the fp64 tensor cores (see KDst) where the border fits one 16 x 24 product; else the tile path
+  static constexpr bool DMMA = !LOC && H <= 5;
+  static constexpr int MT = KDst<(H <= 5 ? H : 1)>::MT, NTL = KDst<(H <= 5 ? H : 1)>::NTL;
+  static constexpr int LDX = NT + 4;                  // row stride of the X|Y columns: LDX mod 16 = 4, conflict-free LDS.64
+  static constexpr int XY_DOUBLES = 8 * (MT + NTL) * LDX;
+  static constexpr int PART_DOUBLES = (G - 1) * MT * NTL * 2 * 32;   // partial products of warps 1..G-1
+  static constexpr int TILE_A = DMMA ? XY_DOUBLES + PART_DOUBLES : KB * LD;
   static constexpr int TGT_DOUBLES = LOC ? 0 : NTGT * H * NT;
   static constexpr int TILE_B = SMALL_ROWS * LD + TGT_DOUBLES;
   static constexpr int TILE_DOUBLES = ((TILE_A > TILE_B ? TILE_A : TILE_B) + 1) & ~1;
@@ -122,7 +186,8 @@ struct LaneIpm {
   double lam, tau, delta;
   // state of the solve in progress (begin / check / factor_a / factor_b / newton_phase)
   double w0_, mu_, gap_, mcount_, kkt_[3];
-  int it_, nretry_;
+  int it_, it0_, nretry_;
+  bool robust_;                       // second attempt (see kRobust* in mpc_common.cuh)
 
   // `slot`: which of the problems that share this thread block (its threads are [slot*NT, (slot+1)*NT), its
   // named barrier is 1 + slot; barrier 0 stays free for block-wide lockstep points of the caller).
@@ -137,7 +202,7 @@ struct LaneIpm {
     sm = smem_slice; tid = (int)threadIdx.x - slot * NT; lane = tid & 31; psel = 0; bar_id = 1 + slot;
     warp = __shfl_sync(kFull, tid >> 5, 0);        // provably warp-uniform: branches on it need no reconvergence code
     valid = tid < n_assets;
-    fact_ok_ = true; it_ = 0;
+    fact_ok_ = true; it_ = 0; it0_ = 0; robust_ = false;
   }
   __device__ __forceinline__ double& FAC(int arr, int k) const {      // arr >= F_QL requires k >= 1
     const int row = (arr < F_QL) ? arr * H + k : 2 * H + (arr - F_QL) * (H - 1) + (k - 1);
@@ -356,7 +421,10 @@ struct LaneIpm {
       }
     }
     KMPC_PROF(*this, 2)
-    // ---- border matrix: emit the entries in KMap order, KB at a time --------------------------------------------
+    if constexpr (DMMA) {
+      assemble_K_dmma(gjj, vd, fL, qL, qR, tR);
+    } else {
+    // ---- border matrix: emit the entries in KMap order, KB at a time (H = 10 / thread-private factors) ----------
     if (warp == 0) {                                 // clear K (rows >= 2H stay identity when there is no cap)
       for (int q = lane; q < NB * NB; q += 32) sm[OFF_K + q] = (q / NB == q % NB) ? 1.0 : 0.0;
     }
@@ -412,6 +480,74 @@ struct LaneIpm {
       if (en % KB != 0) flush_batch(en - en % KB, en % KB);
     }
 #undef KMPC_FLUSH_IF_FULL
+    }
+  }
+
+  // ---- border matrix on the fp64 tensor cores (see KDst): my asset's X | Y columns, X' Y over my warp's 32 assets,
+  // warp 0 adds up the warps and scatters the needed products into the lower triangle of K -------------------------
+  __device__ __forceinline__ void assemble_K_dmma(const double (&gjj)[H], const double (&vd)[H], const double (&fL)[H],
+                                                  const double (&qL)[H], const double (&qR)[H], const double (&tR)[H]) {
+    constexpr int HH = (H <= 5 ? H : 1);
+    double* col = sm + OFF_TILE + tid;                       // column `tid` of the X | Y rows
+    {
+      double T = 1.0, Tprev = 1.0, iT = 1.0;
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        // no u variables (lam = 0 and tau <= 0): the stages are decoupled, tR = 0 exactly and T_l / T_j has no meaning;
+        // a decay of 2^-200 per stage puts the off-diagonal blocks 60 decades below the diagonal ones instead of at 0
+        if (k > 0) { Tprev = T; T *= hu() ? tR[k] : 0x1p-200; iT = rcp_fast(T); }
+        const double gq = gjj[k] * iT;                       // padding lanes: gjj = vd = ie = 0 -> zero Y columns
+        const double phk = hc() ? ph[k] : 0.0;
+        col[k * LDX] = R[k] * T;                                            // P_R
+        col[(H + k) * LDX] = T;                                             // P_1  (k = 0: the ones column)
+        col[(2 * H + k) * LDX] = (k > 0) ? phk * qR[k] * Tprev : 0.0;       // Pe2
+        double* y = col + 8 * MT * LDX;
+        y[k * LDX] = R[k] * gq;                                             // Q_R
+        y[(H + k) * LDX] = gq;                                              // Q_1
+        y[(2 * H + k) * LDX] = -phk * qL[k] * gq;                           // Qe1
+        if (k < H - 1) y[(3 * H + k) * LDX] = -phk * vd[k] * fL[k] * iT;    // Qe3
+        // diagonal of the cap block; without a cap the rows stay decoupled with a positive diagonal (= N)
+        y[(4 * H - 1 + k) * LDX] = hc() ? fma(phk * phk, vd[k], ie[k]) : (valid ? 1.0 : 0.0);
+      }
+    }
+    __syncwarp();                                            // a warp contracts over its OWN 32 columns only
+    double acc[MT][NTL][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    const double* frag = sm + OFF_TILE + (lane >> 2) * LDX + 32 * warp + (lane & 3);
+#pragma unroll
+    for (int st = 0; st < 8; ++st) {                         // 4 assets per step
+      double av[MT], bv[NTL];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) av[mt] = frag[(8 * mt) * LDX + 4 * st];
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) bv[nt] = frag[(8 * (MT + nt)) * LDX + 4 * st];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
+    }
+    if (G > 1) {
+      double* part = sm + OFF_TILE + XY_DOUBLES;
+      if (warp > 0) {
+#pragma unroll
+        for (int q = 0; q < MT * NTL * 2; ++q) part[((warp - 1) * MT * NTL * 2 + q) * 32 + lane] = acc[q / (2 * NTL)][(q / 2) % NTL][q & 1];
+      }
+      sync();
+    }
+    if (warp == 0) {
+      const double* part = sm + OFF_TILE + XY_DOUBLES;
+#pragma unroll
+      for (int q = 0; q < MT * NTL * 2; ++q) {
+        double v = acc[q / (2 * NTL)][(q / 2) % NTL][q & 1];
+#pragma unroll
+        for (int g = 1; g < G; ++g) v += part[((g - 1) * MT * NTL * 2 + q) * 32 + lane];
+        const int dst = g_kdst<HH>.dst[q][lane];
+        if (dst >= 0) sm[OFF_K + dst] = v;
+      }
+    }
   }
 
   // L D L' factorisation of K by warp 0: lane = row, row in registers, columns exchanged by shuffles.  False on a
@@ -600,13 +736,17 @@ struct LaneIpm {
   //   factor_a/b()   factorisation at the current iterate
   //   newton_phase() predictor (0) and corrector + step (1)
   // R[] (gross returns of my asset, all stages) must be set before begin(); w0 = my current weight.
+  // restart = true: the second attempt of the same problem (check() returned ST_RESTART): same R, same w0, the
+  // iteration count carries on.
   __device__ __forceinline__ int begin(double w0, int N, double lam_, double tau_, bool allow_short,
-                                       const IpmOptions& opt) {
-    lam = lam_; tau = tau_; delta = opt.delta;
+                                       const IpmOptions& opt, bool restart = false) {
+    robust_ = uni(restart);
+    lam = lam_; tau = tau_; delta = robust_ ? kRobustDelta : opt.delta;
     has_u_ = uni((lam > 0.0) || (tau > 0.0));
     has_c_ = has_u_ && uni(tau > 0.0);
     has_w_ = !allow_short; allow_short_ = allow_short;
-    it_ = 0; fact_ok_ = true; nretry_ = 0;
+    if (!robust_) it_ = 0;
+    it0_ = it_; fact_ok_ = true; nretry_ = 0;
     kkt_[0] = kkt_[1] = kkt_[2] = CUDART_NAN;
     if (!valid) {
       w0 = 0.0;
@@ -695,6 +835,12 @@ struct LaneIpm {
     return -1;
   }
 
+  // An attempt ends without "optimal": the first attempt hands over to the second one (the caller runs begin() again
+  // with restart = true), the second one ends the solve.
+  __device__ __forceinline__ int end_attempt(int status, const IpmOptions& opt) {
+    if (!robust_ && opt.second_attempt && status != ST_NONFINITE) return ST_RESTART;
+    return finish(status);
+  }
   // final status of a solve that left the iteration without meeting the tolerances (or never started)
   __device__ __forceinline__ int finish(int status) {
     if (status == ST_FAILED && isfinite(kkt_[1] + kkt_[2]) && kkt_[0] < kLoosePres && kkt_[1] < kLooseDres && kkt_[2] < kLooseGap)
@@ -714,9 +860,9 @@ struct LaneIpm {
       // The first breakdown is always retried (most such iterates then reach the tolerances); from the second one on
       // an iterate that meets the loose bar is accepted as it is (finish() applies the loose acceptance).
       const bool loose = isfinite(kkt_[1] + kkt_[2]) && kkt_[0] < kLoosePres && kkt_[1] < kLooseDres && kkt_[2] < kLooseGap;
-      if (nretry_ >= kMaxFactorRetries || (nretry_ > 0 && loose)) return finish(ST_FAILED);
+      if (nretry_ >= kMaxFactorRetries || (nretry_ > 0 && loose)) return end_attempt(ST_FAILED, opt);
       ++nretry_;
-      delta = fmin(fmax(delta, opt.delta) * 30.0, 1e-2);
+      delta = fmin(fmax(delta, robust_ ? kRobustDelta : opt.delta) * 30.0, 1e-2);
       fact_ok_ = true;
     }
     ++it_;
@@ -749,7 +895,8 @@ struct LaneIpm {
     sync();
     // The dual residual only decides anything once the gap is small (every acceptance test below, and the loose one
     // in finish(), asks for gap < max(tol, kLooseGap)) or at the iteration cap: it is not evaluated before that (NaN).
-    const bool near = uni(gap < fmax(opt.tol, kLooseGap)) || (it_ == opt.max_iter + 1);
+    const bool last_it = (it_ - it0_ == opt.max_iter + 1);
+    const bool near = uni(gap < fmax(opt.tol, kLooseGap)) || last_it;
     double dres = CUDART_NAN;
     if (near) {
       int dres_h = 0;
@@ -769,12 +916,15 @@ struct LaneIpm {
     }
     kkt_[0] = pres; kkt_[1] = dres; kkt_[2] = gap;
     gap_ = gap;
-    if (uni(!isfinite(gap) || (near && !isfinite(dres)))) return finish(ST_FAILED);
+    if (uni(!isfinite(gap) || (near && !isfinite(dres)))) return end_attempt(ST_FAILED, opt);
     if (uni(pres < opt.tol && dres < opt.tol_dual && gap < opt.tol)) return ST_OPTIMAL;
     // flat directions (curvature << delta): the dual residual crawls at ~delta*|dx| while the gap has long
     // collapsed; the objective is converged -> "optimal_inaccurate" instead of iterating into round-off
-    if (uni(pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6)) return ST_INACCURATE;
-    if (it_ == opt.max_iter + 1) return finish(ST_FAILED);
+    if (uni(pres < opt.tol && gap < 1e-6 * opt.tol && dres < 1e-6)) {
+      if (!robust_ && opt.second_attempt) return ST_RESTART;
+      return ST_INACCURATE;
+    }
+    if (last_it) return end_attempt(ST_FAILED, opt);
     mu_ = div_fast(gap, fmax(mcount_, 1.0));
     if (uni(pres < opt.tol && gap < opt.tol)) delta = fmax(0.3 * delta, 1e-9);   // endgame: shrink the proximal term
     return -1;
@@ -815,7 +965,7 @@ struct LaneIpm {
       if (hc() && tid < H) g2 = fma(fma(aa, dsc, U(U_SC, tid)), fma(ab, dzc, U(U_ZC, tid)), g2);
       g2 = block_sum1(g2);
       const double ratio = (gap_ > 0.0) ? fmin(1.0, fmax(div_fast(g2, gap_), 0.0)) : 0.0;
-      const double smu = ratio * ratio * ratio * mu_;
+      const double smu = fmax(ratio * ratio * ratio, robust_ ? kRobustSigmaMin : 0.0) * mu_;
       const double dmp = fmin(1.0, fmin(aa, ab) * (1.0 / kCorrFull));   // short affine step: damp the corrector
 #pragma unroll
       for (int k = 0; k < H; ++k) {      // complementarity targets of the corrector
@@ -826,8 +976,9 @@ struct LaneIpm {
       if (tid < H) U(U_CC, tid) = hc() ? fma(-dmp * dsc, dzc, smu) : 0.0;
       sync();
     } else {
-      const double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;
-      const double pb = stepped ? fmin(1.0, opt.step_frac * ab) : 1.0;
+      double pa = stepped ? fmin(1.0, opt.step_frac * aa) : 1.0;
+      double pb = stepped ? fmin(1.0, opt.step_frac * ab) : 1.0;
+      if (robust_) { pa = stepped ? fmin(1.0, kRobustStepFrac * fmin(aa, ab)) : 1.0; pb = pa; }
       if (valid) {
 #pragma unroll
         for (int k = 0; k < H; ++k) {
@@ -854,8 +1005,13 @@ struct LaneIpm {
                                        const IpmOptions& opt, int& iters, double (&kkt)[3]) {
     int status = begin(w0, N, lam_, tau_, allow_short, opt);
     while (status < 0) {
+      if (status == ST_RESTART) {                      // second attempt: same R, same w0
+        sync();
+        status = begin(w0, N, lam_, tau_, allow_short, opt, true);
+        continue;
+      }
       status = check(opt);
-      if (status >= 0) break;
+      if (status >= 0 || status == ST_RESTART) continue;
       factor_a();
       if (!factor_b()) continue;
 #pragma unroll 1

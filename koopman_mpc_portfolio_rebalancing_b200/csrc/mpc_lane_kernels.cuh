@@ -142,15 +142,21 @@ backtest_lane_kernel(BacktestArgs A, int want) {
     if (uni(active)) {
 #pragma unroll 1
       for (;;) {
-        if (uni(need_start)) {
-          const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
-          const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
-          const float y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + s.tid] : 0.0f;
-          e_next = s.load_returns(A.yhat + yb + (size_t)t * H * N, (size_t)N, y_next);      // mpc.py:55
-          st = s.begin(wc, N, A.lam ? A.lam[b] : A.lam0, A.tau ? A.tau[b] : A.tau0, A.allow_short != 0, opt);
+        if (uni(need_start) || uni(st == ST_RESTART)) {
+          const bool restart = !need_start;                          // second attempt: same returns, same weights
+          if (!restart) {
+            const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
+            const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
+            const float y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + s.tid] : 0.0f;
+            e_next = s.load_returns(A.yhat + yb + (size_t)t * H * N, (size_t)N, y_next);    // mpc.py:55
+          } else {
+            s.sync();
+          }
+          st = s.begin(wc, N, A.lam ? A.lam[b] : A.lam0, A.tau ? A.tau[b] : A.tau0, A.allow_short != 0, opt, restart);
           need_start = false;
         }
-        if (uni(st < 0)) st = s.check(opt);
+        if (uni(st == -1)) st = s.check(opt);
+        if (uni(st == ST_RESTART)) continue;                       // the first attempt did not end "optimal"
         if (uni(st < 0)) break;                                    // take a Newton step
         // ---- the decision is made: portfolio step (backtest.py:175-217) ---------------------------------------
         const bool market = (t + 1 < A.rows);

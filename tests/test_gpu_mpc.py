@@ -266,6 +266,34 @@ def test_hard_instances_no_fallback(golden):
         assert _certified_gap(W[p], g["w"][p], g["y"][p], 1e-3, 0.2) < OBJ_RTOL, p
 
 
+def test_second_attempt_solves_the_stalling_decisions(golden):
+    """tests/golden/stall_instances.npz: the 52 decisions of a config-2 step that the aggressive first attempt of the
+    solver leaves `optimal_inaccurate` (a few of them 2-5e-6 off the optimal objective).  With the second attempt
+    (default) every one must end `optimal`, within the objective bar of the dense oracle and certified by the LP
+    certificate; with it switched off the first attempt's behaviour is still there (the fixture exercises the path)."""
+    torch, mpc, mo = _mods()
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    g = golden("stall_instances.npz")
+    w0 = torch.from_numpy(g["w"]).cuda(); y = torch.from_numpy(g["y"]).cuda()
+    out = mpc.solve_mpc_batch(w0, y)
+    st = out["status"].cpu().numpy(); val = out["value"].cpu().numpy(); W = out["w"].cpu().numpy()
+    its = out["iterations"].cpu().numpy()
+    assert (st == 0).all(), (st, its)
+    rel = np.abs(val - g["value"]) / np.maximum(np.abs(g["value"]), OBJ_FLOOR)
+    assert rel.max() < OBJ_RTOL, rel.max()
+    for p in range(len(st)):
+        assert _certified_gap(W[p], g["w"][p], g["y"][p], 1e-3, 0.2) < OBJ_RTOL, p
+    h = _capi.Handle.get(0)
+    _capi.check(_capi.lib().kmpc_set_solver_param(h.ptr, 5, 0.0))
+    try:
+        st1 = mpc.solve_mpc_batch(w0, y)["status"].cpu().numpy()
+    finally:
+        _capi.check(_capi.lib().kmpc_set_solver_param(h.ptr, 0, 0.0))
+    print(f"first attempt only: {(st1 != 0).sum()} of {len(st1)} not optimal; with the second attempt: 0; "
+          f"iterations {its.mean():.1f} on average, worst objective gap {rel.max():.1e}")
+    assert (st1 != 0).sum() >= 10 and (st1 <= 1).all()
+
+
 def test_inaccurate_decisions_of_a_full_config2_step():
     """Every decision of a full config-2 step (4096 backtests x 246 decisions, replayed day by day through the batch
     solver) that ends `optimal_inaccurate`: the plan must meet the 1e-6 objective bar against the independent dense
@@ -300,7 +328,7 @@ def test_inaccurate_decisions_of_a_full_config2_step():
         wc = wn * (1.0 + rr).double() / (1.0 + pr)
     print(f"{B * ns} decisions: {len(bad_w)} optimal_inaccurate, {n_fail} fallbacks")
     assert n_fail == 0
-    assert len(bad_w) <= 200                                  # ~50 per million; a regression of the acceptance rule shows here
+    assert len(bad_w) <= 20                                   # ~50 per million before the second attempt, ~0 with it
     if not bad_w:
         return
     bw, by, bp = np.array(bad_w), np.array(bad_y), np.array(bad_plan)
