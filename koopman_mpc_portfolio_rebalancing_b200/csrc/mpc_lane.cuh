@@ -32,6 +32,14 @@
 #pragma once
 #include "mpc_common.cuh"
 
+// tuning switches (scripts/ab_bench.py builds variants with -D flags; the defaults are the product)
+#ifndef KMPC_BW_SPREAD
+#define KMPC_BW_SPREAD 1        // border warp chosen per slot so that the four chains of an SM use four sub-partitions
+#endif
+#ifndef KMPC_RCP_QUADRATIC
+#define KMPC_RCP_QUADRATIC 0    // experiment: one quadratic Newton step after MUFU.RCP64H (~1e-12 relative) instead of the cubic one
+#endif
+
 namespace kmpc {
 
 // Block-uniform conditions are evaluated from shared-memory values; the vote makes them provably warp-uniform so
@@ -42,7 +50,11 @@ __device__ __forceinline__ double rcp_fast(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // ~20 correct bits
   const double e = fma(-x, y, 1.0);
+#if KMPC_RCP_QUADRATIC
+  return fma(y, e, y);
+#else
   return fma(y, fma(e, e, e), y);                            // relative error ~e^3
+#endif
 }
 // a / b to within ~1.5 ulp in 7 instructions.  Used where a decision is STARTED or BOOKED: that code runs once per
 // decision, each problem of a block at its own time, so it is always fetched cold (the Newton loop has evicted it)
@@ -182,6 +194,7 @@ struct LaneIpm {
   mutable double fac_[LOC ? FAC_ROWS : 1], tgt_[LOC ? NTGT * H : 1];   // LOC only: thread-private factors / targets
   double* sm;
   int tid, lane, warp, psel, bar_id;
+  int bw;                             // the warp of this problem that factorises and solves the border system
   bool valid, has_w_, has_u_, has_c_, allow_short_, fact_ok_;
   double lam, tau, delta;
   // state of the solve in progress (begin / check / factor_a / factor_b / newton_phase)
@@ -201,6 +214,10 @@ struct LaneIpm {
   __device__ __forceinline__ void bind(double* smem_slice, int n_assets, int slot) {
     sm = smem_slice; tid = (int)threadIdx.x - slot * NT; lane = tid & 31; psel = 0; bar_id = 1 + slot;
     warp = __shfl_sync(kFull, tid >> 5, 0);        // provably warp-uniform: branches on it need no reconvergence code
+    // The border work (L D L', triangular solves) is one warp's dependent chain.  Warp w of the block issues on SM
+    // sub-partition w % 4: with "warp 0 of every slot" the chains of the four slots of an SM share two sub-partitions;
+    // picking the border warp by slot gives every chain a sub-partition of its own.
+    bw = (KMPC_BW_SPREAD && DMMA && G > 1 && G <= 4) ? __shfl_sync(kFull, (slot / (4 / (G <= 4 ? G : 4))) % G, 0) : 0;
     valid = tid < n_assets;
     fact_ok_ = true; it_ = 0; it0_ = 0; robust_ = false;
   }
@@ -531,13 +548,14 @@ struct LaneIpm {
     }
     if (G > 1) {
       double* part = sm + OFF_TILE + XY_DOUBLES;
-      if (warp > 0) {
+      if (warp != bw) {
+        const int pw = warp - (warp > bw ? 1 : 0);           // my slot among the G - 1 partial products
 #pragma unroll
-        for (int q = 0; q < MT * NTL * 2; ++q) part[((warp - 1) * MT * NTL * 2 + q) * 32 + lane] = acc[q / (2 * NTL)][(q / 2) % NTL][q & 1];
+        for (int q = 0; q < MT * NTL * 2; ++q) part[(pw * MT * NTL * 2 + q) * 32 + lane] = acc[q / (2 * NTL)][(q / 2) % NTL][q & 1];
       }
       sync();
     }
-    if (warp == 0) {
+    if (warp == bw) {
       const double* part = sm + OFF_TILE + XY_DOUBLES;
 #pragma unroll
       for (int q = 0; q < MT * NTL * 2; ++q) {
@@ -553,7 +571,7 @@ struct LaneIpm {
   // L D L' factorisation of K by warp 0: lane = row, row in registers, columns exchanged by shuffles.  False on a
   // non-positive pivot.
   __device__ __forceinline__ bool factor_b() {
-    if (warp == 0) {
+    if (warp == bw) {
       __syncwarp();                  // K was scattered by lanes of this warp (flush_batch); nobody else touches it
       const int nb = hc() ? 3 * H : 2 * H;
       const int r = (lane < NB) ? lane : NB - 1;
@@ -592,9 +610,16 @@ struct LaneIpm {
     return fact_ok_;
   }
 
-  // OFF_T <- K^{-1} t by warp 0; lane r < NB passes entry r of the right-hand side in t_in
+  // OFF_T <- K^{-1} t by the border warp; lane r < NB passes entry r of the right-hand side in t_in.
+  // The substitutions run in blocks of H unknowns: the block's right-hand sides are broadcast with H independent
+  // shuffles, every lane solves the H x H unit-triangular diagonal block for itself (its entries are warp-uniform
+  // loads) and then updates its own entry with the H solved values.  Same arithmetic as the plain substitution — one
+  // shuffle round trip per BLOCK on the critical path instead of one per unknown (42 cycles each: 30 of them per solve).
+#ifndef KMPC_KSOLVE_BLOCKED
+#define KMPC_KSOLVE_BLOCKED 1
+#endif
   __device__ __forceinline__ void k_solve_shared(double t_in) {
-    if (warp == 0) {
+    if (warp == bw) {
       const int r = (lane < NB) ? lane : NB - 1;
       double Lr[NB], Lc[NB];
 #pragma unroll
@@ -604,11 +629,40 @@ struct LaneIpm {
       }
       const double myinv = (lane < NB) ? sm[OFF_K + NB * NB + r] : 0.0;
       double t = (lane < NB) ? t_in : 0.0;
+#if KMPC_KSOLVE_BLOCKED
+      constexpr int BS = H;
+#pragma unroll
+      for (int b0 = 0; b0 < NB; b0 += BS) {                                      // L y = t
+        double y[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) y[i] = shfl_d(t, b0 + i);
+#pragma unroll
+        for (int i = 1; i < BS; ++i)
+#pragma unroll
+          for (int k = 0; k < i; ++k) y[i] = fma(-sm[OFF_K + (b0 + i) * NB + b0 + k], y[k], y[i]);
+#pragma unroll
+        for (int i = 0; i < BS; ++i) t = fma(-Lr[b0 + i], y[i], t);              // Lr[j] = 0 for j >= lane
+      }
+      t *= myinv;                                                                // D z = y
+#pragma unroll
+      for (int b0 = NB - BS; b0 >= 0; b0 -= BS) {                                // L' x = z
+        double x[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) x[i] = shfl_d(t, b0 + i);
+#pragma unroll
+        for (int i = BS - 2; i >= 0; --i)
+#pragma unroll
+          for (int k = BS - 1; k > i; --k) x[i] = fma(-sm[OFF_K + (b0 + k) * NB + b0 + i], x[k], x[i]);
+#pragma unroll
+        for (int i = BS - 1; i >= 0; --i) t = fma(-Lc[b0 + i], x[i], t);         // Lc[j] = 0 for j <= lane
+      }
+#else
 #pragma unroll
       for (int j = 0; j < NB; ++j) t = fma(-Lr[j], shfl_d(t, j), t);        // L y = t   (Lr[j] = 0 for j >= lane)
       t *= myinv;                                                              // D z = y
 #pragma unroll
       for (int j = NB - 1; j >= 0; --j) t = fma(-Lc[j], shfl_d(t, j), t);   // L' x = z  (Lc[j] = 0 for j <= lane)
+#endif
       if (lane < NB) sm[OFF_T + lane] = t;
     }
   }
@@ -652,9 +706,9 @@ struct LaneIpm {
       }
       tile_reduce<NB>(v);
       double t = 0.0;
-      if (tid < NB) {
-        t = ptotal(tid);
-        if (tid >= H && tid < 2 * H) t += U(U_RP, tid - H);  // t[H+k] = sum dw0 - q, q = -rp
+      if (warp == bw && lane < NB) {
+        t = ptotal(lane);
+        if (lane >= H && lane < 2 * H) t += U(U_RP, lane - H);  // t[H+k] = sum dw0 - q, q = -rp
       }
       KMPC_PROF(*this, 7)
       k_solve_shared(t);
