@@ -7,7 +7,7 @@ batch-resident on the GPU.
                              backtest.py:133-219
 * ``calculate_metrics(df)``  backtest.py:221-249
 * ``run_backtest_batched``   the data-parallel form: B independent backtests (scenario paths, lambda/tau sweeps,
-                             weight sets) in one launch of the persistent backtest kernel (csrc/mpc_kernels.cuh).
+                             weight sets) in one launch of the persistent backtest kernel (csrc/mpc_lane_kernels.cuh).
 
 For a ``KoopmanMPCStrategy`` the forecast never depends on the weights (backtest.py:85-121 reads only
 ``data[t]``), so ``run_backtest`` computes the forecasts of all steps in one batched pass and runs the
@@ -61,12 +61,13 @@ class BuyAndHoldStrategy(Strategy):
 
 class KoopmanMPCStrategy(Strategy):
     """Koopman forecast + MPC (backtest.py:67-131).  ``model`` is a KoopmanMachine of this package
-    (model.GenericKM / model.LISTAKM); ``device`` is accepted for signature parity and must be a CUDA device."""
+    (model.GenericKM / model.LISTAKM).  ``device`` keeps the reference's signature and default (backtest.py:66,
+    ``device='cpu'``): this library has no CPU path, so ``'cpu'`` means "wherever the model lives" (a CUDA device)."""
 
-    def __init__(self, model, mpc_config: MPCConfig, device: str = "cuda"):
+    def __init__(self, model, mpc_config: MPCConfig, device: str = "cpu"):
         self.model = model
         self.mpc_config = mpc_config
-        self.device = device
+        self.device = str(getattr(model, "device", "cuda")) if str(device) == "cpu" else device
 
     def forecast(self, env, t0: int, t1: int):
         """yhat [t1-t0, H, N] float32 CUDA tensor for test rows t0..t1-1 (backtest.py:85-121 for all t at once)."""
@@ -138,7 +139,10 @@ def run_backtest(strategy: Strategy, env, config: BacktestConfig, verbose: bool 
     n_steps = len(env.test_dataset) - config.horizon
     n_assets = env.n_assets
     dates = env.test_dataset.dates
-    if isinstance(strategy, KoopmanMPCStrategy) and hasattr(env, "realized_test_returns_device"):
+    # The fused path evaluates the stock KoopmanMPCStrategy.rebalance for every step at once; a subclass that overrides
+    # rebalance() (DMDStrategy does not) decides step by step through the generic loop below.
+    fused = isinstance(strategy, KoopmanMPCStrategy) and type(strategy).rebalance is KoopmanMPCStrategy.rebalance
+    if fused and hasattr(env, "realized_test_returns_device"):
         if n_steps <= 0:
             return pd.DataFrame([])
         mc = strategy.mpc_config

@@ -169,6 +169,9 @@ def run_grid(models, n_assets: int, delay: int, log_returns, mean, std, lam_grid
     import torch
     dev = torch.device(device)
     bt = bt_config or BacktestConfig(horizon=horizon)
+    if bt.horizon != horizon:
+        raise ValueError(f"run_grid: bt_config.horizon ({bt.horizon}) and horizon ({horizon}) must agree "
+                         "(the number of steps and the forecasts are both derived from it)")
     lr = torch.as_tensor(log_returns).to(dev, dtype=torch.float64).reshape(1, -1, n_assets).contiguous()
     mean_d = torch.as_tensor(mean).to(dev, dtype=torch.float64).reshape(-1).contiguous()
     std_d = torch.as_tensor(std).to(dev, dtype=torch.float64).reshape(-1).contiguous()

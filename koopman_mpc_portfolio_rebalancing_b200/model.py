@@ -378,16 +378,32 @@ def _observation_size_of(sd):
     raise ValueError("cannot infer observation_size: state_dict has no encoder / dictionary weight")
 
 
-def read_checkpoint(path):
+def read_checkpoint(path, trust: bool = False):
     """Host part of the checkpoint loader: the file train.py:475-487 writes (``checkpoint.pt`` / ``last.pt``:
     step, epoch, model_state_dict, optimizer_state_dict, config, metrics, finance_metadata).  Returns
     ``(cfg, state_dict, info)`` with ``info = {step, epoch, metrics, finance_metadata, observation_size}``; a bare
-    state_dict file is accepted too (cfg None)."""
+    state_dict file is accepted too (cfg None).
+
+    The file is read with ``weights_only=True`` (tensors, containers and the numpy scalar / array types that
+    ``finance_metadata`` holds are allow-listed); a checkpoint that needs anything else is refused unless the caller
+    passes ``trust=True``, which unpickles arbitrary objects and must only be used on files of known origin."""
+    import pickle
     import torch
+    safe = []
     try:
-        ck = torch.load(path, map_location="cpu", weights_only=True)
+        import numpy as _np
+        safe = [_np.dtype, _np.ndarray, type(_np.dtype("float64")), type(_np.dtype("float32")), type(_np.dtype("int64"))]
+        core = getattr(_np, "_core", None) or getattr(_np, "core")
+        safe += [core.multiarray.scalar, core.multiarray._reconstruct]
     except Exception:
-        # finance_metadata may hold tuples/np scalars older torch versions pickled as globals
+        pass
+    try:
+        with torch.serialization.safe_globals(safe):
+            ck = torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError as e:
+        if not trust:
+            raise ValueError(f"{path}: cannot be read with weights_only=True ({e}); pass trust=True only for a file "
+                             "of known origin") from e
         ck = torch.load(path, map_location="cpu", weights_only=False)
     if not isinstance(ck, dict):
         raise ValueError(f"{path}: not a checkpoint dictionary")
@@ -406,11 +422,11 @@ def read_checkpoint(path):
     return cfg, sd, info
 
 
-def load_checkpoint(path, cfg=None, device="cuda"):
+def load_checkpoint(path, cfg=None, device="cuda", trust: bool = False):
     """``torch.load`` + ``Config.from_dict`` + ``make_model`` + ``load_state_dict`` + ``eval`` exactly as
     run_experiment.py:67-79 / evaluate_checkpoints.py:121-151 do, for a model of this package.  ``cfg`` overrides
     the stored config (needed for bare state_dict files).  Returns ``(model, info)``."""
-    ck_cfg, sd, info = read_checkpoint(path)
+    ck_cfg, sd, info = read_checkpoint(path, trust=trust)
     cfg = cfg if cfg is not None else ck_cfg
     if cfg is None:
         raise ValueError(f"{path}: holds no config; pass cfg=")

@@ -2,8 +2,9 @@
 
 ``MPCConfig`` mirrors mpc.py:17-25 field for field; ``solve_mpc_log_utility`` mirrors mpc.py:27-117: it never
 raises on solver failure, it falls back to ``np.tile(current_weights, (H, 1))`` with ``value=None`` and a
-non-"optimal" status string.  The solve itself is the warp-per-problem fp64 interior-point kernel of
-csrc/mpc_ipm.cuh, reached through the C ABI (kmpc_mpc_solve_host / kmpc_mpc_solve).  No CPU fallback.
+non-"optimal" status string.  The solve itself is the lane-per-asset fp64 interior-point kernel of
+csrc/mpc_lane.cuh, reached through the C ABI (kmpc_mpc_solve_host / kmpc_mpc_solve).  No CPU fallback: a shape without a
+compiled kernel variant raises ``KmpcError`` (it is a deployment error, not a solver failure).
 """
 from __future__ import annotations
 

@@ -106,3 +106,46 @@ def test_config3_shape_backtest_vs_oracle_loop():
         assert hist[b].shape == ref.shape
         assert np.allclose(hist[b][:, 0], ref[:, 0], rtol=1e-7)           # portfolio value
         assert np.allclose(hist[b][:, 1:], ref[:, 1:], atol=2e-7)         # return, turnover, cost
+
+
+@pytest.mark.parametrize("N,H,mixed", [(10, 5, False), (50, 5, False), (50, 5, True), (100, 3, True), (40, 10, False)])
+def test_persistent_kernel_is_schedule_independent(N, H, mixed):
+    """Race hunting without a sanitizer (compute-sanitizer is closed on this GPU pool): the persistent kernel runs
+    several backtests per block in lockstep with named barriers, a barrier-as-exit-vote every 4th trip, shared-memory
+    tiles reused between phases and a DMMA contraction whose partial products cross warps.  A race or a missed barrier
+    shows as a dependence on WHO shares the block: every backtest's full history must be bit-identical whether it runs
+    alone, with 2, 5, 9 or 37 neighbours (more backtests than slots of a block, so slots re-fetch work), in any position
+    of the batch, and from run to run.  G = 1, 2, 4 kernels and the H = 10 (thread-private factors) variant; `mixed`:
+    per-backtest lambda / tau with zeros (the generic instantiation; backtest 0 carries a zero so that every subset
+    takes that instantiation), else the reference defaults (the FIX instantiation)."""
+    torch, bt, bo, do = _mods()
+    rng = np.random.default_rng(500 + N)
+    Bmax, rows = 37, 12 + H
+    ns = rows - 1 - H
+    yhat = (3e-4 + rng.standard_normal((Bmax, ns, H, N)) * 0.01).astype(np.float32)
+    realized = (3e-4 + rng.standard_normal((Bmax, rows, N)) * 0.012).astype(np.float32)
+    lam = np.where(rng.random(Bmax) < 0.7, 1e-3, rng.choice([0.0, 1e-2], Bmax)) if mixed else np.full(Bmax, 1e-3)
+    tau = np.where(rng.random(Bmax) < 0.7, 0.2, rng.choice([0.0, 0.05], Bmax)) if mixed else np.full(Bmax, 0.2)
+    if mixed:
+        lam[0] = 0.0
+    yd, rd = torch.from_numpy(yhat).cuda(), torch.from_numpy(realized).cuda()
+
+    def run(idx):
+        idx = np.asarray(idx)
+        out = bt.run_backtest_batched(yd, rd, n_steps=ns, horizon=H, lam=lam[idx], tau=tau[idx],
+                                      yhat_index=idx.astype(np.int32), realized_index=idx.astype(np.int32), B=len(idx),
+                                      want_history=True)
+        return out["history"].cpu().numpy(), out["metrics"].cpu().numpy()
+
+    full_h, full_m = run(np.arange(Bmax))
+    assert np.isfinite(full_h).all()
+    for rep in range(3):                                       # run to run
+        h2, m2 = run(np.arange(Bmax))
+        assert np.array_equal(h2, full_h) and np.array_equal(m2, full_m)
+    for k in (1, 2, 5, 9):                                     # alone / few neighbours
+        h, m = run(np.arange(k))
+        assert np.array_equal(h, full_h[:k]) and np.array_equal(m, full_m[:k]), k
+    perm = np.concatenate([[0], 1 + rng.permutation(Bmax - 1)])   # any position in the batch (0 stays: see `mixed`)
+    perm[[0, 17]] = perm[[17, 0]]
+    h, m = run(perm)
+    assert np.array_equal(h, full_h[perm]) and np.array_equal(m, full_m[perm])
