@@ -206,7 +206,9 @@ int kmpc_mpc_solve_host(kmpc_handle* h, const void* yhat_host, int yhat_is_f64, 
 /* P independent problems:  max sum_t [ w_t.mu_t - gamma w_t' Sigma w_t ] - lam sum_t ||w_t - w_{t-1}||_1,
  * sum(w_t) = 1, w_t >= 0 unless allow_short, no turnover cap.  mu [P,H,N] fp64, sigma [N,N] shared or [P,N,N]
  * (sigma_per_problem != 0), w_cur [P,N].  Outputs as kmpc_mpc_solve; on failure w_out = tile(w_cur), obj = NaN
- * (mpc.py:179-180).  The dense Newton block must fit one SM: H * N <= 160, else KMPC_E_UNSUPPORTED. */
+ * (mpc.py:179-180).  H * N <= 160 runs one warp per problem with the dense Newton matrix in shared memory; up to
+ * H * N = 1280 (H <= 8) one block per problem with the matrix in a handle-owned global workspace; beyond that
+ * KMPC_E_UNSUPPORTED. */
 int kmpc_mv_supported(int H, int N);
 int kmpc_mpc_mean_variance(kmpc_handle* h, const double* mu, const double* sigma, int sigma_per_problem, const double* w_cur,
                            double gamma, double lam, int allow_short, int P, int H, int N, double* w_out, double* obj,

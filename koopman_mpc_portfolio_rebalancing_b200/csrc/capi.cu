@@ -50,6 +50,8 @@ int kmpc_create(int device, kmpc_handle** out) {
   h->scratch_bytes = 0;
   h->stats32 = nullptr;
   h->stats32_cap = 0;
+  h->mv_work = nullptr;
+  h->mv_work_doubles = 0;
   h->ipm = kmpc::default_ipm_options();
   e = cudaMalloc(&h->work_counter, 4 * sizeof(int));      // [0] backtest work counter, [2] structure-flag scratch
   if (e != cudaSuccess) { delete h; return kmpc_fail_cuda(e, "cudaMalloc(work_counter)"); }
@@ -63,6 +65,7 @@ int kmpc_destroy(kmpc_handle* h) {
   cudaFree(h->work_counter);
   if (h->scratch) cudaFree(h->scratch);
   if (h->stats32) cudaFree(h->stats32);
+  if (h->mv_work) cudaFree(h->mv_work);
   delete h;
   return KMPC_OK;
 }
@@ -207,10 +210,16 @@ int kmpc_mpc_mean_variance(kmpc_handle* h, const double* mu, const double* sigma
   if (!h || !mu || !sigma || !w_cur || !w_out) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance: NULL argument");
   if (P <= 0 || H <= 0 || N <= 0 || !(gamma >= 0.0) || !(lam >= 0.0)) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance: bad argument");
   if (!kmpc::mv_supported(H, N))
-    return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_mean_variance: H*N = %d exceeds 160 (the dense Newton block must fit one SM)", H * N);
+    return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_mean_variance: H = %d, H*N = %d outside the compiled range (H <= 8, H*N <= 1280)", H, H * N);
   CK(cudaSetDevice(h->device));
+  const size_t need = (size_t)kmpc::mv_work_doubles(H, N) * (size_t)kmpc::mv_blocks(P, H, N, h->sm_count);
+  if (need > h->mv_work_doubles) {                // large problems: global workspace for the dense Newton matrix
+    if (h->mv_work) { CK(cudaStreamSynchronize((cudaStream_t)stream)); cudaFree(h->mv_work); h->mv_work = nullptr; h->mv_work_doubles = 0; }
+    CK(cudaMalloc(&h->mv_work, need * sizeof(double)));
+    h->mv_work_doubles = need;
+  }
   int rc = kmpc::launch_mpc_mv(mu, sigma, sigma_per_problem ? (long long)N * N : 0, w_cur, gamma, lam, allow_short, P, H, N, w_out,
-                               obj, kkt, status, iters, h->sm_count, (cudaStream_t)stream);
+                               obj, kkt, status, iters, h->mv_work, h->sm_count, (cudaStream_t)stream);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_mean_variance: unsupported shape");
   if (rc) return kmpc_fail_cuda((cudaError_t)rc, "mpc_mv_kernel");

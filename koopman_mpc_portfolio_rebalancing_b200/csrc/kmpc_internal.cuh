@@ -51,9 +51,11 @@ int dispatch_backtest(const BacktestArgs& A, int H, int sm_count, cudaStream_t s
 namespace kmpc {
 int mpc_variant_supported(int H, int N);
 int mv_supported(int H, int N);
+long long mv_work_doubles(int H, int N);
+int mv_blocks(int P, int H, int N, int sm_count);
 int launch_mpc_mv(const double* mu, const double* sigma, long long sigma_stride, const double* w_cur, double gamma, double lam,
                   int allow_short, int P, int H, int N, double* w_out, double* obj, double* kkt, int* status, int* iters,
-                  int sm_count, cudaStream_t st);
+                  double* work, int sm_count, cudaStream_t st);
 int launch_standardize(const double* y, const double* mean, const double* sd, int spp, int B, int T, int N, float* out,
                        int ld, int sm_count, cudaStream_t st);
 int launch_embed_gather(const float* data, int ld, int B, int T, int N, int d, float* out, int sm_count, cudaStream_t st);
@@ -68,6 +70,8 @@ struct kmpc_handle {
   int* work_counter;      // device int for the persistent backtest kernel
   void* scratch;          // device workspace (forecast activations), grown on demand
   size_t scratch_bytes;
+  double* mv_work;        // device workspace of the block-wide mean-variance kernel, grown on demand
+  size_t mv_work_doubles;
   float* stats32;         // device [stats32_cap] fp32 copies of (std, mean) for the forecast epilogue
   int stats32_cap;
   kmpc::IpmOptions ipm;   // solver options of this handle (kmpc_set_solver_param)

@@ -205,6 +205,68 @@ def run_grid(models, n_assets: int, delay: int, log_returns, mean, std, lam_grid
     return out
 
 
+def run_markowitz_batched(realized, risk_aversion: float = 1.0, cost_coeff: float = 1e-3, bt_config: Optional[BacktestConfig] = None,
+                          allow_short: bool = False, lookback_window: int = 60, want_history: bool = False):
+    """B Markowitz backtests advanced together: ``MarkowitzStrategy.rebalance`` (baselines.py:55-106) + the step loop of
+    ``run_backtest`` (backtest.py:161-217) for every path at once.
+
+    ``realized`` [B, rows, N] float32 CUDA: de-standardised log-returns of every test row (``kmpc_current_returns``).
+    Per step t: rolling window ``realized[:, max(0, t+1-lookback):t+1]``, ``mu`` = its float32 mean, ``Sigma`` = its float64
+    sample covariance + 1e-6 I (``np.cov`` semantics: float64 arithmetic on the float32 data, ddof = 1), one batched
+    mean-variance solve (``kmpc_mpc_mean_variance`` with a covariance per problem, H = 1), then the portfolio step in
+    float64.  The first four steps hold the weights (fewer than 5 observations, baselines.py:72-74).  The rolling
+    statistics are plain batched reductions / one DGEMM per step (library calls); the solve is this library's kernel.
+    Returns dict(metrics [B,5] f64 CUDA, history [B, n_hist, 4] or None, status_counts [3])."""
+    import torch
+    from .mpc import solve_mean_variance_batch
+    bt = bt_config or BacktestConfig(horizon=1)
+    assert realized.is_cuda and realized.dtype == torch.float32 and realized.dim() == 3
+    B, rows, N = realized.shape
+    dev = realized.device
+    n_steps = (rows - 1) - bt.horizon                                    # len(test_dataset) - horizon, backtest.py:150
+    steps = list(range(0, max(n_steps, 0), bt.rebalance_freq))
+    w = torch.full((B, N), 1.0 / N, dtype=torch.float64, device=dev)     # backtest.py:161
+    V = torch.full((B,), float(bt.initial_capital), dtype=torch.float64, device=dev)
+    simple = (torch.exp(realized.double()).float() - 1.0)               # float32 simple returns, backtest.py:193
+    hist = torch.empty((B, len(steps), 4), dtype=torch.float64, device=dev)
+    eye = torch.eye(N, dtype=torch.float64, device=dev) * 1e-6
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    for k, t in enumerate(steps):
+        target = w
+        if t + 1 >= 5:
+            win = realized[:, max(0, t + 1 - lookback_window):t + 1]     # [B, W, N] float32
+            mu = win.double().mean(dim=1).float().double()              # the float32 mean, carried in float64
+            X = win.double()
+            Xc = X - X.mean(dim=1, keepdim=True)
+            sigma = torch.bmm(Xc.transpose(1, 2), Xc) / float(win.shape[1] - 1) + eye
+            out = solve_mean_variance_batch(w, mu.unsqueeze(1), sigma, risk_aversion, cost_coeff=cost_coeff, allow_short=allow_short)
+            target = out["w"][:, 0]                                      # tile(w_cur) on a failed solve (mpc.py:179-180)
+            st = out["status"]
+            counts += torch.stack([(st == 0).sum(), (st == 1).sum(), (st >= 2).sum()])
+        traded = (target - w).abs().sum(dim=1)
+        fee = bt.cost_coeff * traded * V
+        V = V - fee
+        gain = torch.zeros_like(V)
+        w = target
+        if t + 1 < rows:
+            r = simple[:, t + 1].double()
+            gain = (target * r).sum(dim=1)
+            V = V * (1.0 + gain)
+            scale = 1.0 + gain
+            scale = torch.where(scale.abs() < 1e-8, torch.full_like(scale, 1e-8), scale)
+            w = target * (1.0 + simple[:, t + 1]).double() / scale.unsqueeze(1)
+        hist[:, k, 0] = V; hist[:, k, 1] = gain; hist[:, k, 2] = traded; hist[:, k, 3] = fee
+    ret = hist[:, :, 1]
+    n = max(len(steps), 1)
+    mean = ret.mean(dim=1)
+    std = ((ret - mean.unsqueeze(1)) ** 2).mean(dim=1).sqrt()
+    cum = torch.cumprod(1.0 + ret, dim=1)
+    peak = torch.cummax(cum, dim=1).values
+    metrics = torch.stack([np.sqrt(252.0) * mean / (std + 1e-8), ((cum - peak) / peak).min(dim=1).values,
+                           hist[:, :, 2].mean(dim=1), hist[:, -1, 0], hist[:, -1, 0] / hist[:, 0, 0] - 1.0], dim=1)
+    return {"metrics": metrics, "history": hist if want_history else None, "status_counts": counts}
+
+
 def bootstrap_indices(n_paths: int, length: int, n_hist: int, seed: int, offset: int = 0, device="cpu"):
     """Row indices of the iid bootstrap: idx[p, t] = mix64(seed, offset + p, t) mod n_hist, a counter-based generator
     (the splitmix64 finaliser on a per-(path, day) counter) evaluated for all paths at once.  Path `offset + p` gets the

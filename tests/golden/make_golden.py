@@ -256,12 +256,13 @@ def gen_cfg1():
     print("buy&hold    ", bh_metrics)
 
 
-def gen_markowitz():
+def gen_markowitz(N=6, name="markowitz_small.npz", keep_every=1):
     """UNMODIFIED reference MarkowitzStrategy (baselines.py:24-106) + run_backtest on the small env of gen_dmd: the
     (mu, Sigma) it estimates at every step, the weights the (substitute, fp64 oracle) mean-variance solve returns,
-    history and metrics."""
+    history and metrics.  N = 50 (markowitz_n50.npz): the 50-asset case of VERDICT item 9; only every 8th solver call
+    is stored (Sigma is 50 x 50)."""
     import baselines as ref_baselines
-    N, d, H = 6, 4, 1
+    d, H = 4, 1
     T = 700
     frame = make_frame(21, T, N)
     val_end = str(frame.index[T - 61].date())
@@ -272,9 +273,9 @@ def gen_markowitz():
     shim_mpc.MV_CALLS.clear()
     df = ref_backtest.run_backtest(strat, env, bt_cfg, verbose=False)
     metrics = ref_backtest.calculate_metrics(df)
-    calls = shim_mpc.MV_CALLS
-    np.savez(
-        os.path.join(HERE, "markowitz_small.npz"),
+    calls = shim_mpc.MV_CALLS[::keep_every]
+    np.savez_compressed(
+        os.path.join(HERE, name), call_stride=keep_every,
         T=T, N=N, d=d, log_returns_seed=21, n_train_days=T - 61 - 100 + 1, n_val_days=100, gamma=2.0,
         mean=stats.mean, std=stats.std,
         mu=np.stack([c[1] for c in calls]), sigma=np.stack([c[2] for c in calls]),
@@ -448,6 +449,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "markowitz":
         gen_markowitz()
+        gen_markowitz(50, "markowitz_n50.npz", 8)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rollouts":
         gen_rollouts()
@@ -459,6 +461,7 @@ if __name__ == "__main__":
     gen_dmd()
     gen_rollouts()
     gen_markowitz()
+    gen_markowitz(50, "markowitz_n50.npz", 8)
     gen_checkpoints()
     gen_sequences()
     gen_prices()
