@@ -36,7 +36,8 @@ int kmpc_create(int device, kmpc_handle** out) {
     return fail(KMPC_E_CUDA, "kmpc_create: no CUDA device (%s); libkmpc has no CPU fallback",
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   if (device < 0 || device >= n) return fail(KMPC_E_INVALID, "kmpc_create: device %d out of range [0,%d)", device, n);
-  CK(cudaSetDevice(device));
+  kmpc_device_guard dev_guard_(device);
+  CK(dev_guard_.err);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -61,7 +62,7 @@ int kmpc_create(int device, kmpc_handle** out) {
 
 int kmpc_destroy(kmpc_handle* h) {
   if (!h) return KMPC_OK;
-  cudaSetDevice(h->device);
+  kmpc_device_guard dev_guard_(h->device);
   cudaFree(h->work_counter);
   if (h->scratch) cudaFree(h->scratch);
   if (h->stats32) cudaFree(h->stats32);
@@ -101,7 +102,8 @@ int kmpc_standardize(kmpc_handle* h, const double* logret, const double* mean, c
                      int B, int T, int N, float* out, int ld_out, void* stream) {
   if (!h || !logret || !mean || !std || !out) return fail(KMPC_E_INVALID, "kmpc_standardize: NULL argument");
   if (B <= 0 || T <= 0 || N <= 0 || ld_out < N) return fail(KMPC_E_INVALID, "kmpc_standardize: bad shape");
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   int rc = kmpc::launch_standardize(logret, mean, std, stats_per_path, B, T, N, out, ld_out, h->sm_count, (cudaStream_t)stream);
   h->launches++;
   if (rc) return kmpc_fail_cuda((cudaError_t)rc, "standardize_kernel");
@@ -112,7 +114,8 @@ int kmpc_embed_gather(kmpc_handle* h, const float* data, int ld_in, int B, int T
   if (!h || !data || !out) return fail(KMPC_E_INVALID, "kmpc_embed_gather: NULL argument");
   if (T < d) return fail(KMPC_E_INVALID, "Time series length %d < embedding_dim %d", T, d);
   if (B <= 0 || N <= 0 || d <= 0 || ld_in < N) return fail(KMPC_E_INVALID, "kmpc_embed_gather: bad shape");
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   int rc = kmpc::launch_embed_gather(data, ld_in, B, T, N, d, out, h->sm_count, (cudaStream_t)stream);
   h->launches++;
   if (rc) return kmpc_fail_cuda((cudaError_t)rc, "embed_gather_kernel");
@@ -134,7 +137,8 @@ int kmpc_current_returns(kmpc_handle* h, const float* z, int ld_z, const double*
   if (!h || !z || !mean || !std || !out) return fail(KMPC_E_INVALID, "kmpc_current_returns: NULL argument");
   if (B <= 0 || rows <= 0 || N <= 0 || d <= 0 || row0 < 0 || row0 + rows + d - 1 > T || ld_z < N)
     return fail(KMPC_E_INVALID, "kmpc_current_returns: bad shape (row0=%d rows=%d d=%d T=%d)", row0, rows, d, T);
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   int rc = kmpc::launch_current_returns(z, ld_z, mean, std, stats_per_path, B, T, N, d, row0, rows, out, h->sm_count,
                                         (cudaStream_t)stream);
   h->launches++;
@@ -150,7 +154,8 @@ int kmpc_mpc_solve(kmpc_handle* h, const float* yhat, const double* yhat64, cons
   if (P == 0) return KMPC_OK;
   if (!kmpc::mpc_variant_supported(H, N))
     return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_solve: no compiled kernel variant for H=%d N=%d", H, N);
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   kmpc::MpcSolveArgs A;
   A.yhat = yhat; A.yhat64 = yhat64; A.w_cur = w_cur; A.lam = lam; A.tau = tau; A.lam0 = lam0; A.tau0 = tau0;
   A.allow_short = allow_short; A.P = P; A.N = N; A.w_out = w_out; A.obj = obj; A.kkt = kkt; A.status = status;
@@ -167,7 +172,8 @@ int kmpc_mpc_solve_host(kmpc_handle* h, const void* yhat_host, int yhat_is_f64, 
                         double* kkt_host, int32_t* status_host, int32_t* iters_host) {
   if (!h || !yhat_host || !w_cur_host || !w_out_host) return fail(KMPC_E_INVALID, "kmpc_mpc_solve_host: NULL argument");
   if (P <= 0 || H <= 0 || N <= 0) return fail(KMPC_E_INVALID, "kmpc_mpc_solve_host: bad shape");
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   const size_t nw = (size_t)P * H * N;
   const size_t ybytes = nw * (yhat_is_f64 ? sizeof(double) : sizeof(float));
   const size_t bytes = nw * sizeof(double) + (size_t)P * N * sizeof(double) + nw * sizeof(double) +
@@ -211,7 +217,8 @@ int kmpc_mpc_mean_variance(kmpc_handle* h, const double* mu, const double* sigma
   if (P <= 0 || H <= 0 || N <= 0 || !(gamma >= 0.0) || !(lam >= 0.0)) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance: bad argument");
   if (!kmpc::mv_supported(H, N))
     return fail(KMPC_E_UNSUPPORTED, "kmpc_mpc_mean_variance: H = %d, H*N = %d outside the compiled range (H <= 8, H*N <= 1280)", H, H * N);
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   const size_t need = (size_t)kmpc::mv_work_doubles(H, N) * (size_t)kmpc::mv_blocks(P, H, N, h->sm_count);
   if (need > h->mv_work_doubles) {                // large problems: global workspace for the dense Newton matrix
     if (h->mv_work) { CK(cudaStreamSynchronize((cudaStream_t)stream)); cudaFree(h->mv_work); h->mv_work = nullptr; h->mv_work_doubles = 0; }
@@ -231,7 +238,8 @@ int kmpc_mpc_mean_variance_host(kmpc_handle* h, const double* mu_host, const dou
                                 double* kkt_host, int32_t* status_host, int32_t* iters_host) {
   if (!h || !mu_host || !sigma_host || !w_cur_host || !w_out_host) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance_host: NULL argument");
   if (H <= 0 || N <= 0) return fail(KMPC_E_INVALID, "kmpc_mpc_mean_variance_host: bad shape");
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   const size_t nw = (size_t)H * N;
   const size_t doubles = nw + (size_t)N * N + N + nw + 1 + 3;
   char* buf = nullptr;
@@ -265,7 +273,8 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
     return fail(KMPC_E_INVALID, "kmpc_backtest_run: bad shape");
   if (!kmpc::mpc_variant_supported(D->H, D->N))
     return fail(KMPC_E_UNSUPPORTED, "kmpc_backtest_run: no compiled kernel variant for H=%d N=%d", D->H, D->N);
-  CK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  CK(dev_guard_.err);
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
   kmpc::BacktestArgs A;

@@ -529,7 +529,7 @@ extern "C" {
 
 int kmpc_model_free(kmpc_model* m) {
   if (!m) return KMPC_OK;
-  cudaSetDevice(m->h->device);
+  kmpc_device_guard dev_guard_(m->h->device);
   for (void* p : m->owned) cudaFree(p);
   if (m->z_lo) cudaFree(m->z_lo);
   if (m->fold_w) { cudaFree(m->fold_w); cudaFree(m->fold_w_lo); }
@@ -548,7 +548,8 @@ int kmpc_model_load(kmpc_handle* h, const kmpc_model_desc* D, kmpc_model** out) 
   if (!h || !D || !out) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: NULL argument");
   if (D->obs != D->n_assets * D->delay || D->latent <= 0 || D->n_assets <= 0)
     return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_model_load: obs must equal n_assets*delay");
-  FCK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  FCK(dev_guard_.err);
   kmpc_model* m = new kmpc_model();
   m->h = h; m->kind = D->kind; m->obs = D->obs; m->N = D->n_assets; m->d = D->delay; m->Z = D->latent;
   m->ld = ((D->n_assets + 3) / 4) * 4; m->norm_fn = D->norm_fn;
@@ -653,7 +654,8 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
   if (ld_z != m->ld) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_forecast: ld_z must be n_assets rounded up to a multiple of 4");
   if (B <= 0 || H <= 0 || t1 <= t0 || row0 < 0 || t0 < 0 || row0 + t1 + m->d - 1 > T)
     return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_forecast: bad row range");
-  FCK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  FCK(dev_guard_.err);
   cudaStream_t st = (cudaStream_t)stream;
   float *std32, *mean32;
   int rc = stats_to_f32(h, mean, std, (stats_per_path ? B : 1) * m->N, &std32, &mean32, st);
@@ -690,7 +692,8 @@ int kmpc_forecast(kmpc_handle* h, const kmpc_model* m, const float* z, int ld_z,
 
 int kmpc_encode(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, float* latent, void* stream) {
   if (!h || !m || !obs || !latent || M <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_encode: bad argument");
-  FCK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  FCK(dev_guard_.err);
   kmpc::AView av; av.A = obs; av.A_lo = nullptr; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
   return kmpc::run_chain(h, m, av, M, 0, 0, 0, nullptr, nullptr, 0, latent, (cudaStream_t)stream);
 }
@@ -698,7 +701,8 @@ int kmpc_encode(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, fl
 int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, int H, int obs_cols, float* pred, void* stream) {
   if (!h || !m || !obs || !pred || M <= 0 || H <= 0 || obs_cols <= 0 || obs_cols > m->obs)
     return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_rollout: bad argument");
-  FCK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  FCK(dev_guard_.err);
   kmpc::AView av; av.A = obs; av.A_lo = nullptr; av.group_stride = 0; av.rows_per_group = M; av.lda = m->obs; av.K = m->obs; av.window = false;
   return kmpc::run_chain(h, m, av, M, H, 2, obs_cols, nullptr, nullptr, 0, pred, (cudaStream_t)stream);
 }
@@ -706,7 +710,8 @@ int kmpc_rollout(kmpc_handle* h, const kmpc_model* m, const float* obs, int M, i
 // KoopmanMachine.step_latent (model.py:311-321, 787-797): out = norm(z @ kmat)
 int kmpc_step_latent(kmpc_handle* h, const kmpc_model* m, const float* z, int M, float* out, void* stream) {
   if (!h || !m || !z || !out || M <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_step_latent: bad argument");
-  FCK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  FCK(dev_guard_.err);
   cudaStream_t st = (cudaStream_t)stream;
   kmpc::GemmArgs g = kmpc::base_args();
   g.A = z; g.a_rows_per_group = M; g.lda = m->Z; g.K = m->Z; g.W = m->kmatT; g.ldw = m->Z;
@@ -722,7 +727,8 @@ int kmpc_step_latent(kmpc_handle* h, const kmpc_model* m, const float* z, int M,
 // KoopmanMachine.decode (model.py:768-777, 839-850): out [M, obs]
 int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, float* out, void* stream) {
   if (!h || !m || !z || !out || M <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_decode: bad argument");
-  FCK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  FCK(dev_guard_.err);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (m->kind == KMPC_MODEL_LISTA) {
@@ -765,7 +771,8 @@ int kmpc_set_gemm_fp16_pairs(int on) { kmpc::set_gemm_tc16_mode(on); return KMPC
 // KMPC_E_UNSUPPORTED if the shape is not eligible).  Allocates the residual twins internally; synchronous.
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode) {
   if (!h || !A || !W || !C || M <= 0 || Nout <= 0 || K <= 0) return kmpc_fail_cuda(cudaErrorInvalidValue, "kmpc_debug_gemm: bad argument");
-  FCK(cudaSetDevice(h->device));
+  kmpc_device_guard dev_guard_(h->device);
+  FCK(dev_guard_.err);
   if (mode == 2) {           // fp16-pair tensor-core kernel
     __half *Ah = nullptr, *Al = nullptr, *Wh = nullptr, *Wl = nullptr;
     FCK(cudaMalloc(&Ah, (size_t)M * K * sizeof(__half))); FCK(cudaMalloc(&Al, (size_t)M * K * sizeof(__half)));

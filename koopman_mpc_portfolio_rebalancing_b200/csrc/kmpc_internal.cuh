@@ -63,6 +63,19 @@ int launch_current_returns(const float* z, int ld, const double* mean, const dou
                            int d, int row0, int rows, float* out, int sm_count, cudaStream_t st);
 }  // namespace kmpc
 
+// Entry points run on the handle's device and leave the caller's current device as they found it (a process that
+// drives several GPUs — one handle each — shares the CUDA current-device state with its tensor library).
+struct kmpc_device_guard {
+  int prev = -1;
+  cudaError_t err;
+  explicit kmpc_device_guard(int dev) {
+    cudaGetDevice(&prev);
+    err = (prev == dev) ? cudaSuccess : cudaSetDevice(dev);
+    if (prev == dev) prev = -1;
+  }
+  ~kmpc_device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct kmpc_handle {
   int device;
   int sm_count;

@@ -303,3 +303,30 @@ def test_compare_strategies_table(golden, tmp_path):
     assert np.allclose(back.values, table.values.astype(float), rtol=1e-12)
     with pytest.raises(ValueError):
         engine.compare_strategies(m, env, strategies=("nope",))
+
+
+def test_two_devices_from_one_process():
+    """One process driving two GPUs through one handle each (kmpc.h: "one handle per device"): the once-only kernel setup
+    (dynamic shared-memory attribute, occupancy, SM count) and the handle's scratch buffers are per DEVICE, so the same
+    small batch gives bit-identical metrics on cuda:0 and cuda:1.  Needs two visible GPUs (skipped otherwise; run with
+    `gpurun --gpus 2`)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    from koopman_mpc_portfolio_rebalancing_b200 import engine, model as km, synthetic, backtest as bt
+    B, N, d, H, rows, Z = 6, 50, 8, 5, 40, 128
+    T = rows + d - 1
+    lr = synthetic.gbm_log_returns_batch(3, B, T, N)
+    mean, std = lr.mean(axis=1), lr.std(axis=1, ddof=1)
+    sd = synthetic.generic_km_weights(5, N * d, [128, 128], Z)
+    res = []
+    for dev in ("cuda:1", "cuda:0", "cuda:1"):                       # device 1 FIRST: nothing may be cached for device 0 only
+        m = km.make_model(km.model_config("GenericKM", Z, [128, 128], enc_bias=True), N * d, device=dev)
+        m.load_state_dict(sd)
+        eng = engine.BatchedBacktester(m, N, d, bt.MPCConfig(horizon=H), bt.BacktestConfig(horizon=H), device=dev)
+        with torch.cuda.device(dev):
+            out = eng.run(engine.PathBatch(lr, mean, std, 0, rows), want_history=True)
+        res.append(out)
+    for r in res[1:]:
+        assert np.array_equal(r["metrics"], res[0]["metrics"]) and np.array_equal(r["history"], res[0]["history"])
+    assert res[0]["stats"][:, 2].sum() == 0
