@@ -74,7 +74,9 @@ enum {
   KMPC_PARAM_CLIP_FIRST_TRADE = 4,
   /* 1 [default]: a solve whose first attempt does not end "optimal" is repeated from the cold start with robust
    * parameters (csrc/mpc_common.cuh kRobust*) */
-  KMPC_PARAM_SECOND_ATTEMPT = 5
+  KMPC_PARAM_SECOND_ATTEMPT = 5,
+  /* tolerance on the complementarity gap and the primal residual (default: default_ipm_options().tol) */
+  KMPC_PARAM_TOL = 6
 };
 int kmpc_set_solver_param(kmpc_handle* h, int which, double value);
 

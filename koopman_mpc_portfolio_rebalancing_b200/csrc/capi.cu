@@ -86,6 +86,9 @@ int kmpc_set_solver_param(kmpc_handle* h, int which, double value) {
     case KMPC_PARAM_MAX_ITER:
       if (value < 1.0 || value > 1000.0) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: max_iter must be in [1,1000]");
       h->ipm.max_iter = (int)value; break;
+    case KMPC_PARAM_TOL:
+      if (!(value >= 1e-13 && value <= 1e-6)) return fail(KMPC_E_INVALID, "kmpc_set_solver_param: tol must be in [1e-13, 1e-6]");
+      h->ipm.tol = value; break;
     case KMPC_PARAM_SECOND_ATTEMPT:
       h->ipm.second_attempt = (value != 0.0) ? 1 : 0; break;
     case KMPC_PARAM_CLIP_FIRST_TRADE:

@@ -17,11 +17,14 @@ sys.path.insert(0, ROOT)
 AB = os.path.join(ROOT, "build_ab")
 
 
-def one(lib, steps):
+def one(lib, steps, params=()):
     import numpy as np
     import torch
     from koopman_mpc_portfolio_rebalancing_b200 import _capi
     _capi.LIB_PATH = lib
+    for kv in params:                                # e.g. 6=3e-10  (KMPC_PARAM_TOL)
+        k, v = kv.split("=")
+        _capi.check(_capi.lib().kmpc_set_solver_param(_capi.Handle.get(0).ptr, int(k), float(v)))
     from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt, engine, model as km, synthetic
     import bench
     w = bench.WORKLOADS["cfg2"]
@@ -43,7 +46,7 @@ def one(lib, steps):
         ms.append(ev[2].elapsed_time(ev[3]))
     st = out["stats"].sum(dim=0).cpu().numpy()
     met = out["metrics"].cpu().numpy()
-    print(json.dumps({"lib": os.path.basename(lib), "mpc_ms": float(np.median(ms)), "mpc_ms_all": [round(x, 2) for x in ms],
+    print(json.dumps({"lib": os.path.basename(lib), "params": list(params), "mpc_ms": float(np.median(ms)), "mpc_ms_all": [round(x, 2) for x in ms],
                       "iters": float(st[3]) / (B * (rows - 1 - H)), "optimal": int(st[0]), "inaccurate": int(st[1]),
                       "fallback": int(st[2]), "mean_final_value": float(met[:, 3].mean())}))
 
@@ -66,7 +69,7 @@ def main():
             line = [l for l in p.stdout.splitlines() if l.startswith("{")]
             print(line[-1] if line else f"{os.path.basename(lib)} FAILED: {p.stderr[-400:]}")
     elif mode == "one":
-        one(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 3)
+        one(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 3, sys.argv[4:])
 
 
 if __name__ == "__main__":
