@@ -387,7 +387,7 @@ def run_gpu_arm(args):
     lr_h = torch.from_numpy(lr).pin_memory(); mean_h = torch.from_numpy(mean).pin_memory(); std_h = torch.from_numpy(std).pin_memory()
     lr_d, mean_d, std_d = lr_h.to(dev), mean_h.to(dev), std_h.to(dev)
     handle = _capi.Handle.get(local)
-    _capi.lib().kmpc_set_gemm_fp16_pairs(1 if args.gemm == "fp16" else 0)
+    _capi.lib().kmpc_set_gemm_fp16_pairs({"fp16": 1, "fp16x2": 2, "tf32": 0}[args.gemm])
     B_total = B * world
 
     def step_device(timings=None):
@@ -470,7 +470,7 @@ def run_gpu_arm(args):
         fc_tflops = fpd * decisions_per_step_rank / (st_fc * 1e-3) / 1e12
         # fp32-accurate tensor rate of the fp16-pair kernel: three kind::f16 MMAs (hi.hi, lo.hi, hi.lo) per product,
         # fp16 dense rate = the measured bf16 rate
-        tensor_peak = bf16 / 3.0 if args.gemm == "fp16" else bf16 / 2.0 / 3.0
+        tensor_peak = bf16 / 3.0 if args.gemm.startswith("fp16") else bf16 / 2.0 / 3.0
         hbm_bytes_bt = (8 * N + 8 * H * N + 32) * decisions_per_step_rank
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roof_fc = {"kernel": "forecast GEMM chain (gemm_tc16_kernel, tcgen05 fp16 pairs: encoder 3 GEMMs + folded multi-horizon read-out)", "bound": "tensor", "achieved": fc_tflops,
@@ -545,7 +545,8 @@ def main():
     ap.add_argument("--cpu-scenarios", type=int, default=10, help="scenarios in the rank-0 cpu_baseline sample (~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short passes of BASELINE configs 3-5")
-    ap.add_argument("--gemm", default="fp16", choices=["fp16", "tf32"], help="forecast tensor-core kernel (diagnostics)")
+    ap.add_argument("--gemm", default="fp16", choices=["fp16", "fp16x2", "tf32"],
+                    help="forecast tensor-core kernel (diagnostics): fp16 pairs on one CTA per tile, on CTA pairs, or 3xTF32")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -177,7 +177,8 @@ int kmpc_set_forecast_fold(int on);
  * (an fp32 value travels as fp16(x) and fp16((x - hi) * 2^11): 22 significant bits like the 3xTF32 pair at half the
  * operand bytes and twice the MMA rate).  Its epilogues raise a device flag when a value leaves the fp16 range
  * (|x| > 65504); the 3xTF32 chain is queued behind it gated on that flag (its kernels exit at once otherwise), so the
- * call stays asynchronous on `stream`.  0: always the 3xTF32 chain. */
+ * call stays asynchronous on `stream`.  0: always the 3xTF32 chain.  2: as 1, on the CTA-pair instantiation of the kernel
+ * (tcgen05 cta_group::2, 256 x 128 tiles: each CTA stages half of the weight tile). */
 int kmpc_set_gemm_fp16_pairs(int on);
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode);
 

@@ -370,7 +370,7 @@ static int ensure_fold(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st) {
 
 namespace kmpc {
 static int g_tc16 = 1;
-void set_gemm_tc16_mode(int on) { g_tc16 = on ? 1 : 0; }
+void set_gemm_tc16_mode(int on) { g_tc16 = on ? 1 : 0; set_gemm_tc16_pair(on == 2); }
 
 static bool tc16_eligible(const kmpc_model* m) {
   if (!g_tc16 || !g_fold) return false;

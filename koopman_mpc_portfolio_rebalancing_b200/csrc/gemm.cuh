@@ -69,6 +69,7 @@ struct Gemm16Args {
 };
 // returns -100 when the launch is not eligible (shape, alignment)
 int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st);
+void set_gemm_tc16_pair(int on);
 int launch_split16(const float* x, long long rows, int cols, int ld_in, __half* hi, __half* lo, int ld_out, int* overflow,
                    cudaStream_t st);
 

@@ -188,6 +188,95 @@ __device__ __forceinline__ void store_pair_block(const Params& p, const float (&
   lrow[0] = reinterpret_cast<const uint4*>(ll)[0]; lrow[1] = reinterpret_cast<const uint4*>(ll)[1];
 }
 
+// Epilogue of one 128 x 128 accumulator set for one warp: TMEM lane quarter q (rows q*32 + lane of the CTA's tile),
+// column blocks [cb0, cb0 + CB_PER_WARP) of 16.  m = global output row of this lane, tn = column tile.
+constexpr int CB_PER_WARP = (BN / 16) / (EPI_WARPS / 4);       // column blocks of 16 per warp
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_base, int q, int cb0, int tn, long long m,
+                                              bool row_ok, int nhi) {
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+  const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (long long)((int)(m + p.row0) / p.stat_rows_per_group) : 0;
+#pragma unroll 1
+  for (int cb = cb0; cb < cb0 + CB_PER_WARP; ++cb) {
+    uint32_t v[16], u0[16], u1[16], u2[16];
+    float acc[16];
+    tmem_ld16_nowait(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);    // lo products, scaled by 2^11
+    tmem_ld16_nowait(lane_addr + (uint32_t)(0 * BN + cb * 16), u0);
+    if (nhi > 1) tmem_ld16_nowait(lane_addr + (uint32_t)(1 * BN + cb * 16), u1);
+    if (nhi > 2) tmem_ld16_nowait(lane_addr + (uint32_t)(2 * BN + cb * 16), u2);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = __fadd_rn(__uint_as_float(v[j]) * (1.0f / 2048.0f), __uint_as_float(u0[j]));
+      if (nhi > 1) a = __fadd_rn(a, __uint_as_float(u1[j]));
+      if (nhi > 2) a = __fadd_rn(a, __uint_as_float(u2[j]));
+      acc[j] = a;
+    }
+    const int n0 = tn * BN + cb * 16;
+    if (row_ok && p.C16_hi && !p.C && n0 + 16 <= p.n_store) {       // interior block of an fp16-pair layer
+      switch (p.act) {
+        case EPI_RELU: store_pair_block<EPI_RELU>(p, acc, m, n0); break;
+        case EPI_TANH: store_pair_block<EPI_TANH>(p, acc, m, n0); break;
+        case EPI_GELU: store_pair_block<EPI_GELU>(p, acc, m, n0); break;
+        default: store_pair_block<EPI_NONE>(p, acc, m, n0); break;
+      }
+    } else if (row_ok && n0 < p.n_store) {
+      float x[16];
+      const int smod = p.stat_mod ? p.stat_mod : 0x7fffffff;
+      int sn = p.stat_mod ? n0 % p.stat_mod : n0;                    // statistics column of output column n
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + j;
+        float t = acc[j];
+        if (n < p.n_store) {
+          if (p.bias) t += p.bias[n];
+          t = epilogue_apply(t, p.act, 0.0f);
+          if (p.std32) {
+            t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + sn]), p.mean32[sg * p.stat_ld + sn]);
+            if (++sn == smod) sn = 0;
+          }
+        }
+        x[j] = t;
+      }
+      if (p.C16_hi) {                       // next layer's operand: fp16 pair, lo scaled by 2^11
+        __align__(16) __half hh[16];
+        __align__(16) __half ll[16];
+        bool ovf = false;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const __half h = __float2half_rn(x[j]);
+          hh[j] = h;
+          ll[j] = __float2half_rn((x[j] - __half2float(h)) * 2048.0f);
+          ovf = ovf || !(fabsf(x[j]) <= 65504.0f);
+        }
+        if (ovf && p.overflow) *p.overflow = 1;
+        __half* hrow = p.C16_hi + m * p.ldc16 + n0;
+        __half* lrow = p.C16_lo + m * p.ldc16 + n0;
+        if (n0 + 16 <= p.n_store) {
+          reinterpret_cast<uint4*>(hrow)[0] = reinterpret_cast<const uint4*>(hh)[0];
+          reinterpret_cast<uint4*>(hrow)[1] = reinterpret_cast<const uint4*>(hh)[1];
+          reinterpret_cast<uint4*>(lrow)[0] = reinterpret_cast<const uint4*>(ll)[0];
+          reinterpret_cast<uint4*>(lrow)[1] = reinterpret_cast<const uint4*>(ll)[1];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) { hrow[j] = hh[j]; lrow[j] = ll[j]; }
+        }
+      }
+      if (p.C) {
+        float* crow = p.C + m * p.ldc + n0;
+        const bool full = (n0 + 16 <= p.n_store) && ((((uintptr_t)crow) & 15) == 0);
+        if (full) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) crow[j] = x[j];
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo, Params p) {
@@ -274,7 +363,6 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
     const int q = warp & 3;                                        // TMEM lane quarter this warp may access
-    constexpr int CB_PER_WARP = (BN / 16) / (EPI_WARPS / 4);       // column blocks of 16 per warp
     const int cb0 = ((warp - EPI_WARP0) >> 2) * CB_PER_WARP;
     uint32_t acc_phase = 0;
     const int nhi = p.k_blocks < NUM_HI ? p.k_blocks : NUM_HI;
@@ -286,88 +374,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const long long m = (long long)g * p.rows_per_group + r_in_group;
       mbar_wait(&tfull_bar[0], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (long long)((int)(m + p.row0) / p.stat_rows_per_group) : 0;
-#pragma unroll 1
-      for (int cb = cb0; cb < cb0 + CB_PER_WARP; ++cb) {
-        uint32_t v[16], u0[16], u1[16], u2[16];
-        float acc[16];
-        tmem_ld16_nowait(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);    // lo products, scaled by 2^11
-        tmem_ld16_nowait(lane_addr + (uint32_t)(0 * BN + cb * 16), u0);
-        if (nhi > 1) tmem_ld16_nowait(lane_addr + (uint32_t)(1 * BN + cb * 16), u1);
-        if (nhi > 2) tmem_ld16_nowait(lane_addr + (uint32_t)(2 * BN + cb * 16), u2);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = __fadd_rn(__uint_as_float(v[j]) * (1.0f / 2048.0f), __uint_as_float(u0[j]));
-          if (nhi > 1) a = __fadd_rn(a, __uint_as_float(u1[j]));
-          if (nhi > 2) a = __fadd_rn(a, __uint_as_float(u2[j]));
-          acc[j] = a;
-        }
-        const int n0 = tn * BN + cb * 16;
-        if (row_ok && p.C16_hi && !p.C && n0 + 16 <= p.n_store) {       // interior block of an fp16-pair layer
-          switch (p.act) {
-            case EPI_RELU: store_pair_block<EPI_RELU>(p, acc, m, n0); break;
-            case EPI_TANH: store_pair_block<EPI_TANH>(p, acc, m, n0); break;
-            case EPI_GELU: store_pair_block<EPI_GELU>(p, acc, m, n0); break;
-            default: store_pair_block<EPI_NONE>(p, acc, m, n0); break;
-          }
-        } else if (row_ok && n0 < p.n_store) {
-          float x[16];
-          const int smod = p.stat_mod ? p.stat_mod : 0x7fffffff;
-          int sn = p.stat_mod ? n0 % p.stat_mod : n0;                    // statistics column of output column n
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + j;
-            float t = acc[j];
-            if (n < p.n_store) {
-              if (p.bias) t += p.bias[n];
-              t = epilogue_apply(t, p.act, 0.0f);
-              if (p.std32) {
-                t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + sn]), p.mean32[sg * p.stat_ld + sn]);
-                if (++sn == smod) sn = 0;
-              }
-            }
-            x[j] = t;
-          }
-          if (p.C16_hi) {                       // next layer's operand: fp16 pair, lo scaled by 2^11
-            __align__(16) __half hh[16];
-            __align__(16) __half ll[16];
-            bool ovf = false;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const __half h = __float2half_rn(x[j]);
-              hh[j] = h;
-              ll[j] = __float2half_rn((x[j] - __half2float(h)) * 2048.0f);
-              ovf = ovf || !(fabsf(x[j]) <= 65504.0f);
-            }
-            if (ovf && p.overflow) *p.overflow = 1;
-            __half* hrow = p.C16_hi + m * p.ldc16 + n0;
-            __half* lrow = p.C16_lo + m * p.ldc16 + n0;
-            if (n0 + 16 <= p.n_store) {
-              reinterpret_cast<uint4*>(hrow)[0] = reinterpret_cast<const uint4*>(hh)[0];
-              reinterpret_cast<uint4*>(hrow)[1] = reinterpret_cast<const uint4*>(hh)[1];
-              reinterpret_cast<uint4*>(lrow)[0] = reinterpret_cast<const uint4*>(ll)[0];
-              reinterpret_cast<uint4*>(lrow)[1] = reinterpret_cast<const uint4*>(ll)[1];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) { hrow[j] = hh[j]; lrow[j] = ll[j]; }
-            }
-          }
-          if (p.C) {
-            float* crow = p.C + m * p.ldc + n0;
-            const bool full = (n0 + 16 <= p.n_store) && ((((uintptr_t)crow) & 15) == 0);
-            if (full) {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4)
-                *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) crow[j] = x[j];
-            }
-          }
-        }
-      }
+      epilogue_tile(p, tmem_base, q, cb0, tn, m, row_ok, nhi);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[0]);
@@ -381,6 +388,181 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
+
+// --------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes a 256 x 128 output tile.  CTA r stages its own
+// 128 rows of A (hi, lo: 2 x 16 KB) and HALF of the W tile (rows 64 r .. 64 r + 63 of the 128: 2 x 8 KB) per k-block;
+// the leader CTA's MMA issuer runs tcgen05.mma.cta_group::2 with M = 256, N = 128: each SM's tensor core reads its
+// own A tile and both halves of W, accumulators land in each CTA's own TMEM.  Shared-memory traffic per k-block and
+// CTA drops from 160 KB (64 written by TMA + 96 read by the 12 MMAs) to 120 KB (48 + 72): the main loop of the
+// single-CTA kernel is bound by exactly that traffic (128 B/clk per SM against 768 MMA cycles per k-block).
+// Barriers: the leader's full barrier counts the bytes of both CTAs' TMA loads; MMA completion is committed by
+// multicast to both CTAs' empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's
+// accumulator-empty barrier.
+constexpr int STAGES2 = 4;
+constexpr int TILE_W2_BYTES = (BN / 2) * BK * 2;                 // 8 KB
+constexpr int STAGE2_BYTES = 2 * TILE_BYTES + 2 * TILE_W2_BYTES;  // 48 KB
+constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc2), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc16x2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo, Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(base + STAGES2 * STAGE2_BYTES);   // the leader's are the ones in use
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tfull_bar = empty_bar + STAGES2;
+  uint64_t* tempty_bar = tfull_bar + 1;                               // the leader's is the one in use
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pairs_per_group = (p.tiles_per_group + 1) / 2;
+  const int num_pairs = p.tiles_n * pairs_per_group * p.n_groups;
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapWlo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tempty_bar[0], 2 * EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = cluster_id; t < num_pairs; t += n_clusters) {
+        const int tn = t % p.tiles_n, tm = t / p.tiles_n;
+        const int g = tm / pairs_per_group, pb = tm - g * pairs_per_group;
+        const int tb = 2 * pb + (int)rank;                         // my 128-row tile inside the group
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = base + stage * STAGE2_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
+          tma2_load_3d(&mapA, fb, st, kb * BK, tb * BM, g);
+          tma2_load_3d(&mapAlo, fb, st + TILE_BYTES, kb * BK, tb * BM, g);
+          tma2_load_2d(&mapW, fb, st + 2 * TILE_BYTES, kb * BK, tn * BN + (int)rank * (BN / 2));
+          tma2_load_2d(&mapWlo, fb, st + 2 * TILE_BYTES + TILE_W2_BYTES, kb * BK, tn * BN + (int)rank * (BN / 2));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t acc_phase = 0;
+      for (int t = cluster_id; t < num_pairs; t += n_clusters) {
+        mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_lo = tmem_base + NUM_HI * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(base + stage * STAGE2_BYTES);
+          const uint64_t dA = make_desc(sa), dAlo = make_desc(sa + TILE_BYTES);
+          const uint64_t dW = make_desc(sa + 2 * TILE_BYTES), dWlo = make_desc(sa + 2 * TILE_BYTES + TILE_W2_BYTES);
+          const uint32_t d_hi = tmem_base + (uint32_t)(kb % NUM_HI) * BN;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+            mma2_f16(d_lo, dAlo + adv, dW + adv, (kb == 0 && kk == 0) ? 0u : 1u);
+            mma2_f16(d_lo, dA + adv, dWlo + adv, 1u);
+            mma2_f16(d_hi, dA + adv, dW + adv, (kb < NUM_HI && kk == 0) ? 0u : 1u);
+          }
+          umma2_commit_mc(&empty_bar[stage]);                      // frees the stage in BOTH CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_mc(&tfull_bar[0]);                            // accumulators complete, both CTAs
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (both CTAs, each its own 128 rows) =====================
+    const int q = warp & 3;
+    const int cb0 = ((warp - EPI_WARP0) >> 2) * CB_PER_WARP;
+    uint32_t acc_phase = 0;
+    const int nhi = p.k_blocks < NUM_HI ? p.k_blocks : NUM_HI;
+    const uint32_t tempty0 = mapa_rank(smem_u32(&tempty_bar[0]), 0);
+    for (int t = cluster_id; t < num_pairs; t += n_clusters) {
+      const int tn = t % p.tiles_n, tm = t / p.tiles_n;
+      const int g = tm / pairs_per_group, pb = tm - g * pairs_per_group;
+      const int tb = 2 * pb + (int)rank;
+      const int r_in_group = tb * BM + q * 32 + lane;
+      const bool row_ok = r_in_group < p.rows_per_group;
+      const long long m = (long long)g * p.rows_per_group + r_in_group;
+      mbar_wait(&tfull_bar[0], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      epilogue_tile(p, tmem_base, q, cb0, tn, m, row_ok, nhi);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0);
+      acc_phase ^= 1;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                                              // nobody leaves while the peer may still signal it
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
 
 // --------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -413,6 +595,9 @@ static bool encode(CUtensorMap* map, const __half* ptr, int rank, const cuuint64
 }
 
 }  // namespace tc16
+
+static int g_tc16_pair = 0;       // 1: CTA-pair kernel (cta_group::2) where the launch has at least two 256-row tiles
+void set_gemm_tc16_pair(int on) { g_tc16_pair = on ? 1 : 0; }
 
 int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st) {
   using namespace tc16;
@@ -455,9 +640,25 @@ int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.Nout};
     cuuint64_t strides[1] = {(cuuint64_t)g.ldw * 2};
-    cuuint32_t box[2] = {BK, BN};
+    const int pairs = p.tiles_n * ((p.tiles_per_group + 1) / 2) * p.n_groups;
+    const bool use_pair = g_tc16_pair && pairs >= 2;
+    cuuint32_t box[2] = {BK, (cuuint32_t)(use_pair ? BN / 2 : BN)};          // CTA pair: each CTA stages half of the W tile
     if (!encode(&mW, g.W_hi, 2, dims, strides, box)) return -100;
     if (!encode(&mWlo, g.W_lo, 2, dims, strides, box)) return -100;
+    if (use_pair) {
+      const size_t smem2 = (size_t)STAGES2 * STAGE2_BYTES + 1024 + 256;
+      static PerDeviceInt sm_table2;
+      const int sm2 = sm_table2.get([&] {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gemm_tc16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        return n;
+      });
+      int clusters = pairs < sm2 / 2 ? pairs : sm2 / 2;
+      gemm_tc16x2_kernel<<<2 * clusters, NUM_THREADS, smem2, st>>>(mA, mAlo, mW, mWlo, p);
+      return (int)cudaGetLastError();
+    }
   }
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
   static PerDeviceInt sm_table;           // SM count; the shared-memory attribute is set on the same first use

@@ -48,3 +48,24 @@ def test_small_shapes_are_not_eligible_for_tcgen05():
         run(A, W, 1)
     out = run(A, W, 0)
     assert torch.allclose(out, A @ W.T, atol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 256, 256), (640, 250, 1024), (1000, 1024, 1040), (4096, 1024, 1024), (777, 320, 200)])
+def test_cta_pair_variant_is_bit_identical(M, N, K):
+    """kmpc_set_gemm_fp16_pairs(2): the same fp16-pair GEMM on CTA pairs (tcgen05 cta_group::2, 256 x 128 tiles, each CTA
+    staging half of the weight tile, barriers across the pair).  Same MMA sequence per output row, so the result must be
+    bit-identical to the single-CTA kernel — including ragged M (rows beyond the matrix in the second CTA of a pair) and a
+    ragged N tile."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K), generator=g, device="cuda", dtype=torch.float32)
+    W = torch.randn((N, K), generator=g, device="cuda", dtype=torch.float32) / K ** 0.5
+    single = run(A, W, 2)
+    try:
+        _capi.lib().kmpc_set_gemm_fp16_pairs(2)
+        pair = run(A, W, 2)
+        pair2 = run(A, W, 2)
+    finally:
+        _capi.lib().kmpc_set_gemm_fp16_pairs(1)
+    assert torch.equal(single, pair) and torch.equal(pair, pair2)
