@@ -349,7 +349,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t adv = (uint64_t)((kk * 32) >> 4);       // 16 halves = 32 bytes inside the swizzle atom
-            mma_f16(d_lo, dAlo + adv, dW + adv, (kb == 0 && kk == 0) ? 0u : 1u);
+mma_f16(d_lo, dAlo + adv, dW + adv, (kb == 0 && kk == 0) ? 0u : 1u);
             mma_f16(d_lo, dA + adv, dWlo + adv, 1u);
             mma_f16(d_hi, dA + adv, dW + adv, (kb < NUM_HI && kk == 0) ? 0u : 1u);
           }

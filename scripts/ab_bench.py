@@ -37,16 +37,16 @@ def one(lib, steps, params=()):
     for _ in range(2):
         out = eng.run_device(lr_d, mean_d, std_d, 0, rows)
     torch.cuda.synchronize()
-    ms = []
+    ms = []; fc = []
     for _ in range(steps):
         tm = {}
         out = eng.run_device(lr_d, mean_d, std_d, 0, rows, timings=tm)
         torch.cuda.synchronize()
         ev = tm["_events"]
-        ms.append(ev[2].elapsed_time(ev[3]))
+        ms.append(ev[2].elapsed_time(ev[3])); fc.append(ev[1].elapsed_time(ev[2]))
     st = out["stats"].sum(dim=0).cpu().numpy()
     met = out["metrics"].cpu().numpy()
-    print(json.dumps({"lib": os.path.basename(lib), "params": list(params), "mpc_ms": float(np.median(ms)), "mpc_ms_all": [round(x, 2) for x in ms],
+    print(json.dumps({"lib": os.path.basename(lib), "params": list(params), "forecast_ms": float(np.median(fc)), "mpc_ms": float(np.median(ms)), "mpc_ms_all": [round(x, 2) for x in ms],
                       "iters": float(st[3]) / (B * (rows - 1 - H)), "optimal": int(st[0]), "inaccurate": int(st[1]),
                       "fallback": int(st[2]), "mean_final_value": float(met[:, 3].mean())}))
 
@@ -57,7 +57,8 @@ def main():
         from koopman_mpc_portfolio_rebalancing_b200 import build as kb
         os.makedirs(AB, exist_ok=True)
         name, defs = sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
-        kb.build(verbose=False, lib=os.path.join(AB, f"libkmpc_{name}.so"), lane_variants=[(5, 2)], lane_defs=defs)
+        gdefs = sys.argv[4] if len(sys.argv) > 4 else ""          # -D flags for the tcgen05 GEMM units
+        kb.build(verbose=False, lib=os.path.join(AB, f"libkmpc_{name}.so"), lane_variants=[(5, 2)], lane_defs=defs, gemm_defs=gdefs)
         kb.build(verbose=False)                     # restore the generated variant list of the product build
         print("built", name, defs)
     elif mode == "run":
