@@ -180,6 +180,9 @@ int kmpc_set_forecast_fold(int on);
  * call stays asynchronous on `stream`.  0: always the 3xTF32 chain.  2: as 1, on the CTA-pair instantiation of the kernel
  * (tcgen05 cta_group::2, 256 x 128 tiles: each CTA stages half of the weight tile). */
 int kmpc_set_gemm_fp16_pairs(int on);
+/* diagnostics / tuning: rows per pass of the fp16-pair forecast chain (rounded down to whole paths; default: see
+ * forecast.cu).  Smaller passes keep the layer activations L2-resident between the GEMMs of the chain. */
+int kmpc_set_forecast_chunk_rows(int rows);
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode);
 
 /* ---------------------------------------------------------------------------------------------

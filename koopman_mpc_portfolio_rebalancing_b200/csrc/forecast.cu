@@ -370,6 +370,10 @@ static int ensure_fold(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st) {
 
 namespace kmpc {
 static int g_tc16 = 1;
+// Rows per pass of the fp16-pair chain (whole paths).  The activations of a pass ping-pong between two fp16-pair buffers
+// of CH x width x 4 bytes.
+static long long g_chunk_rows = 32768;
+void set_forecast_chunk_rows(long long rows) { g_chunk_rows = rows < 128 ? 128 : rows; }
 void set_gemm_tc16_mode(int on) { g_tc16 = on ? 1 : 0; set_gemm_tc16_pair(on == 2); }
 
 static bool tc16_eligible(const kmpc_model* m) {
@@ -445,7 +449,7 @@ static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int
   h->launches++;
   int maxw = Z;
   for (int v : m->enc_dims) if (v > maxw) maxw = v;
-  long long ch = 32768;
+  long long ch = g_chunk_rows;
   if (rpp < M) { ch = (ch / rpp) * rpp; if (ch < rpp) ch = rpp; }
   if (ch > M) ch = M;
   const int CH = (int)ch;
@@ -766,6 +770,7 @@ int kmpc_decode(kmpc_handle* h, const kmpc_model* m, const float* z, int M, floa
 int kmpc_set_gemm_mode(int use_tensor_cores) { kmpc::set_gemm_tc_mode(use_tensor_cores); return KMPC_OK; }
 int kmpc_set_forecast_fold(int on) { kmpc::set_forecast_fold(on); return KMPC_OK; }
 int kmpc_set_gemm_fp16_pairs(int on) { kmpc::set_gemm_tc16_mode(on); return KMPC_OK; }
+int kmpc_set_forecast_chunk_rows(int rows) { kmpc::set_forecast_chunk_rows(rows); return KMPC_OK; }
 
 // C[M,Nout] = A[M,K] . W[Nout,K]^T through one chosen kernel: mode 0 = SIMT fp32, 1 = tcgen05 3xTF32 (returns
 // KMPC_E_UNSUPPORTED if the shape is not eligible).  Allocates the residual twins internally; synchronous.

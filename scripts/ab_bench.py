@@ -22,8 +22,12 @@ def one(lib, steps, params=()):
     import torch
     from koopman_mpc_portfolio_rebalancing_b200 import _capi
     _capi.LIB_PATH = lib
-    for kv in params:                                # e.g. 6=3e-10  (KMPC_PARAM_TOL)
+    for kv in params:                                # e.g. 6=3e-10  (KMPC_PARAM_TOL), chunk=9102, gemm=2
         k, v = kv.split("=")
+        if k == "chunk":
+            _capi.lib().kmpc_set_forecast_chunk_rows(int(v)); continue
+        if k == "gemm":
+            _capi.lib().kmpc_set_gemm_fp16_pairs(int(v)); continue
         _capi.check(_capi.lib().kmpc_set_solver_param(_capi.Handle.get(0).ptr, int(k), float(v)))
     from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt, engine, model as km, synthetic
     import bench
