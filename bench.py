@@ -476,7 +476,10 @@ def run_gpu_arm(args):
         roof_fc = {"kernel": "forecast GEMM chain (gemm_tc16_kernel, tcgen05 fp16 pairs: encoder 3 GEMMs + folded multi-horizon read-out)", "bound": "tensor", "achieved": fc_tflops,
                    "peak": tensor_peak, "unit": "TFLOP/s", "frac": fc_tflops / tensor_peak, "traffic": None,
                    "peak_source": f"{peak_src} bf16 sustained / 3 (three fp16 MMAs per fp32-accurate product)",
-                   "flops_per_decision": fpd, "flops_per_decision_unfolded": flops_per_decision(w), "ms": st_fc}
+                   "flops_per_decision": fpd, "flops_per_decision_unfolded": flops_per_decision(w), "ms": st_fc,
+                   "note": "the tensor roofline is the stated bound of a dense contraction; timing experiments (DESIGN.md section 8) "
+                           "show this chain limited by operand delivery into the SMs (1 MB of fp16-pair operands per 128 x 128 "
+                           "tile), not by the tensor pipe: a third of the MMAs still takes 89 % of the time"}
         # The solver's bound is SM instruction issue: 4 warp instructions per clock and SM.
         cnt = solver_counters() if args.workload == "cfg2" else None
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count

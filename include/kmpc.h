@@ -12,7 +12,10 @@
  *     on that stream unless stated otherwise;
  *   - return value: 0 = success, negative = KMPC_E_*; kmpc_last_error() gives a message
  *     (thread-local);
- *   - a handle is bound to one device; not thread-safe per handle, re-entrant across handles.
+ *   - a handle is bound to one device; not thread-safe per handle, re-entrant across handles.  A handle owns a work
+ *     counter, device flags and scratch buffers: issue its calls on ONE stream at a time (calls on one stream are
+ *     ordered and safe back to back); concurrent streams or threads need a handle each.  Entry points leave the
+ *     caller's current CUDA device unchanged.
  *   - there is NO CPU fallback: every entry point fails with KMPC_E_CUDA / KMPC_E_UNSUPPORTED if the
  *     device or a compiled kernel variant is missing.
  */

@@ -98,7 +98,7 @@ def test_random_instances_vs_oracle(N, H):
 
 
 def test_wide_parity_sweep_dense_and_certificate():
-    """The wide mix of scripts/parity_sweep.py as a test: shapes N 2..64, H 1..5, lambda in {0, 1e-5..1e-1}, tau in
+    """The wide random mix (round 1 ran it as a script, now a test): shapes N 2..64, H 1..5, lambda in {0, 1e-5..1e-1}, tau in
     {0, 0.01..1}, concentrated and diffuse current weights, calm and wild forecasts; 24 instances per shape.  Every
     accepted plan is certified against the optimum of mpc.py's program (certificate) and every fourth one is compared
     with the independent dense oracle; no instance may fall back."""
