@@ -190,96 +190,151 @@ __device__ __forceinline__ void store_pair_block(const Params& p, const float (&
 
 // Epilogue of one 128 x 128 accumulator set for one warp: TMEM lane quarter q (rows q*32 + lane of the CTA's tile),
 // column blocks [cb0, cb0 + CB_PER_WARP) of 16.  m = global output row of this lane, tn = column tile.
+// Two phases.  DRAIN: the warp's share of the four accumulators is read out of TMEM and combined into 16 x CB_PER_WARP
+// fp32 registers per thread, then `release()` hands the accumulators back to the MMA issuer.  STORE: bias /
+// activation / fp16 split / global stores run from registers while the next tile's MMAs are already accumulating —
+// the four accumulators fill TMEM, so they cannot be double-buffered; the registers of the epilogue warps are the
+// second buffer.  (Before: the accumulators were held through the stores, 6.5 of a tile's 16.9 us.)
+#ifndef KMPC_TC16_EARLY_RELEASE
+#define KMPC_TC16_EARLY_RELEASE 1
+#endif
 constexpr int CB_PER_WARP = (BN / 16) / (EPI_WARPS / 4);       // column blocks of 16 per warp
+__device__ __forceinline__ void drain_block(uint32_t lane_addr, int cb, int nhi, float (&acc)[16]) {
+  uint32_t v[16], u0[16], u1[16], u2[16];
+  tmem_ld16_nowait(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);    // lo products, scaled by 2^11
+  tmem_ld16_nowait(lane_addr + (uint32_t)(0 * BN + cb * 16), u0);
+  if (nhi > 1) tmem_ld16_nowait(lane_addr + (uint32_t)(1 * BN + cb * 16), u1);
+  if (nhi > 2) tmem_ld16_nowait(lane_addr + (uint32_t)(2 * BN + cb * 16), u2);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float a = __fadd_rn(__uint_as_float(v[j]) * (1.0f / 2048.0f), __uint_as_float(u0[j]));
+    if (nhi > 1) a = __fadd_rn(a, __uint_as_float(u1[j]));
+    if (nhi > 2) a = __fadd_rn(a, __uint_as_float(u2[j]));
+    acc[j] = a;
+  }
+}
+
+// Every block that is not an interior fp16-pair block with a cheap activation (fp32 output: read-out, encode / decode
+// hooks; tanh / gelu layers; ragged column edges) goes through a per-warp staging tile ([32][17] floats, conflict-free
+// both ways) and a ROLLED loop over its rows (one copy of the element code per block).  Two reasons, both measured
+// (profiles/README.md):
+//  * code size.  With bias / activation switch (inlined tanhf, erff) / de-standardisation unrolled over the 16 elements
+//    of a block the kernel was 27 800 SASS instructions (445 KB): every tile's epilogue streamed its code from L2, and
+//    the read-out ran at 28-52 us per tile against a 12 us main loop (tensor pipe 10 %);
+//  * store pattern.  A thread owns one ROW of the accumulator, so a store from the accumulator registers puts every lane
+//    on a different 128-byte line (rows are 1000 bytes apart in the config-2 read-out).  From the tile the block is stored
+//    TRANSPOSED: lane = (row parity, column), 16 instructions of two contiguous row segments each.
+// The per-column operands (bias, statistics column) are loaded once per block; the statistics row changes at most once
+// inside a warp's 32 rows when a group has >= 32 rows (else it is looked up per row).
+constexpr int STAGE_LD = 17;
+constexpr int STAGE_FLOATS_PER_WARP = 32 * STAGE_LD;
+constexpr int BAR_BYTES = 256;                       // mbarriers + TMEM slot, after the operand stages
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * STAGE_LD * 4;
+// tanh / gelu / shrink: one out-of-line copy (inlined per element they were most of the kernel's code)
+__device__ __noinline__ float act_slow(float x, int act) { return epilogue_apply(x, act, 0.0f); }
+
+__device__ __forceinline__ void store_rows_staged(const Params& p, const float* stage, int n0, long long m0, int rows_ok, int lane) {
+  const int col = lane & 15, half = lane >> 4;
+  const int n = n0 + col;
+  if (n >= p.n_store) return;
+  // every field used inside the row loop is copied to a local first: the loop stores through pointers, so the compiler
+  // would otherwise re-load the fields from the parameter block in every iteration (measured: six dependent generic
+  // loads per element, 23 us of epilogue per tile)
+  float* const C = p.C; __half* const C16_hi = p.C16_hi; __half* const C16_lo = p.C16_lo;
+  const long long ldc = p.ldc, ldc16 = p.ldc16;
+  const int act = p.act;
+  const bool has_bias = p.bias != nullptr;
+  const float b = has_bias ? p.bias[n] : 0.0f;
+  const float* const std32 = p.std32; const float* const mean32 = p.mean32;
+  const bool stats = std32 != nullptr;
+  const int stat_ld = p.stat_ld;
+  const long long row0 = p.row0;
+  const int sn = p.stat_mod ? n % p.stat_mod : n;
+  const int srpg = p.stat_rows_per_group;
+  long long sg0 = 0; int rem0 = 0;
+  float s0 = 1.0f, mu0 = 0.0f, s1 = 1.0f, mu1 = 0.0f;
+  const bool two = stats && srpg >= 32;               // at most two statistics rows in this warp's 32 rows
+  if (stats && srpg > 0) { sg0 = (m0 + row0) / srpg; rem0 = (int)((m0 + row0) - sg0 * srpg); }
+  if (stats && (two || srpg <= 0)) {
+    s0 = std32[sg0 * stat_ld + sn]; mu0 = mean32[sg0 * stat_ld + sn];
+    if (two && rem0 + rows_ok > srpg) { s1 = std32[(sg0 + 1) * stat_ld + sn]; mu1 = mean32[(sg0 + 1) * stat_ld + sn]; }
+  }
+  bool ovf = false;
+#pragma unroll 4
+  for (int r = half; r < rows_ok; r += 2) {
+    float t = stage[r * STAGE_LD + col];
+    if (has_bias) t += b;
+    if (act == EPI_RELU) t = (t < 0.0f) ? 0.0f : t;              // NaN propagates like torch.relu
+    else if (act != EPI_NONE) t = act_slow(t, act);
+    if (stats) {
+      float sd = s0, mn = mu0;
+      if (two) { if (rem0 + r >= srpg) { sd = s1; mn = mu1; } }
+      else if (srpg > 0) {
+        const long long sg = (m0 + r + row0) / srpg;
+        sd = std32[sg * stat_ld + sn]; mn = mean32[sg * stat_ld + sn];
+      }
+      t = __fadd_rn(__fmul_rn(t, sd), mn);
+    }
+    const long long m = m0 + r;
+    if (C16_hi) {                       // next layer's operand: fp16 pair, lo scaled by 2^11
+      const __half h = __float2half_rn(t);
+      C16_hi[m * ldc16 + n] = h;
+      C16_lo[m * ldc16 + n] = __float2half_rn((t - __half2float(h)) * 2048.0f);
+      ovf = ovf || !(fabsf(t) <= 65504.0f);
+    }
+    if (C) C[m * ldc + n] = t;
+  }
+  if (ovf && p.overflow) *p.overflow = 1;
+}
+
+// `release()` is called exactly once, by all lanes of the warp, when the warp no longer needs the accumulators.
+// `stage`: this warp's STAGE_FLOATS_PER_WARP floats of shared memory.
+template <typename Release>
 __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_base, int q, int cb0, int tn, long long m,
-                                              bool row_ok, int nhi) {
+                                              bool row_ok, int nhi, float* stage, Release release) {
   const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-  const long long sg = (p.std32 && p.stat_rows_per_group > 0) ? (long long)((int)(m + p.row0) / p.stat_rows_per_group) : 0;
+  const int lane = threadIdx.x & 31;
+  const int rows_ok = __popc(__ballot_sync(0xffffffffu, row_ok));  // valid rows are a prefix of the warp's 32
+  const long long m0 = m - lane;
+  const bool pair_fast = p.C16_hi && !p.C && (p.act == EPI_RELU || p.act == EPI_NONE);     // warp-uniform
+  auto store = [&](const float (&a)[16], int cb) {
+    const int n0 = tn * BN + cb * 16;
+    if (pair_fast && n0 + 16 <= p.n_store) {                     // interior block of an fp16-pair layer
+      if (row_ok) {
+        if (p.act == EPI_RELU) store_pair_block<EPI_RELU>(p, a, m, n0);
+        else store_pair_block<EPI_NONE>(p, a, m, n0);
+      }
+    } else if (n0 < p.n_store) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) stage[lane * STAGE_LD + j] = a[j];
+      __syncwarp();
+      store_rows_staged(p, stage, n0, m0, rows_ok, lane);
+      __syncwarp();                                              // the staging tile is reused by the next block
+    }
+  };
+#if KMPC_TC16_EARLY_RELEASE
+  float acc[CB_PER_WARP][16];
+#pragma unroll
+  for (int c = 0; c < CB_PER_WARP; ++c) drain_block(lane_addr, cb0 + c, nhi, acc[c]);
+  release();
+#pragma unroll
+  for (int c = 0; c < CB_PER_WARP; ++c) store(acc[c], cb0 + c);
+#else
 #pragma unroll 1
   for (int cb = cb0; cb < cb0 + CB_PER_WARP; ++cb) {
-    uint32_t v[16], u0[16], u1[16], u2[16];
     float acc[16];
-    tmem_ld16_nowait(lane_addr + (uint32_t)(NUM_HI * BN + cb * 16), v);    // lo products, scaled by 2^11
-    tmem_ld16_nowait(lane_addr + (uint32_t)(0 * BN + cb * 16), u0);
-    if (nhi > 1) tmem_ld16_nowait(lane_addr + (uint32_t)(1 * BN + cb * 16), u1);
-    if (nhi > 2) tmem_ld16_nowait(lane_addr + (uint32_t)(2 * BN + cb * 16), u2);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float a = __fadd_rn(__uint_as_float(v[j]) * (1.0f / 2048.0f), __uint_as_float(u0[j]));
-      if (nhi > 1) a = __fadd_rn(a, __uint_as_float(u1[j]));
-      if (nhi > 2) a = __fadd_rn(a, __uint_as_float(u2[j]));
-      acc[j] = a;
-    }
-    const int n0 = tn * BN + cb * 16;
-    if (row_ok && p.C16_hi && !p.C && n0 + 16 <= p.n_store) {       // interior block of an fp16-pair layer
-      switch (p.act) {
-        case EPI_RELU: store_pair_block<EPI_RELU>(p, acc, m, n0); break;
-        case EPI_TANH: store_pair_block<EPI_TANH>(p, acc, m, n0); break;
-        case EPI_GELU: store_pair_block<EPI_GELU>(p, acc, m, n0); break;
-        default: store_pair_block<EPI_NONE>(p, acc, m, n0); break;
-      }
-    } else if (row_ok && n0 < p.n_store) {
-      float x[16];
-      const int smod = p.stat_mod ? p.stat_mod : 0x7fffffff;
-      int sn = p.stat_mod ? n0 % p.stat_mod : n0;                    // statistics column of output column n
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + j;
-        float t = acc[j];
-        if (n < p.n_store) {
-          if (p.bias) t += p.bias[n];
-          t = epilogue_apply(t, p.act, 0.0f);
-          if (p.std32) {
-            t = __fadd_rn(__fmul_rn(t, p.std32[sg * p.stat_ld + sn]), p.mean32[sg * p.stat_ld + sn]);
-            if (++sn == smod) sn = 0;
-          }
-        }
-        x[j] = t;
-      }
-      if (p.C16_hi) {                       // next layer's operand: fp16 pair, lo scaled by 2^11
-        __align__(16) __half hh[16];
-        __align__(16) __half ll[16];
-        bool ovf = false;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const __half h = __float2half_rn(x[j]);
-          hh[j] = h;
-          ll[j] = __float2half_rn((x[j] - __half2float(h)) * 2048.0f);
-          ovf = ovf || !(fabsf(x[j]) <= 65504.0f);
-        }
-        if (ovf && p.overflow) *p.overflow = 1;
-        __half* hrow = p.C16_hi + m * p.ldc16 + n0;
-        __half* lrow = p.C16_lo + m * p.ldc16 + n0;
-        if (n0 + 16 <= p.n_store) {
-          reinterpret_cast<uint4*>(hrow)[0] = reinterpret_cast<const uint4*>(hh)[0];
-          reinterpret_cast<uint4*>(hrow)[1] = reinterpret_cast<const uint4*>(hh)[1];
-          reinterpret_cast<uint4*>(lrow)[0] = reinterpret_cast<const uint4*>(ll)[0];
-          reinterpret_cast<uint4*>(lrow)[1] = reinterpret_cast<const uint4*>(ll)[1];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) { hrow[j] = hh[j]; lrow[j] = ll[j]; }
-        }
-      }
-      if (p.C) {
-        float* crow = p.C + m * p.ldc + n0;
-        const bool full = (n0 + 16 <= p.n_store) && ((((uintptr_t)crow) & 15) == 0);
-        if (full) {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + j < p.n_store) crow[j] = x[j];
-        }
-      }
-    }
+    drain_block(lane_addr, cb, nhi, acc);
+    store(acc, cb);
   }
+  release();
+#endif
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
-               const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo, Params p) {
+               const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo,
+                 const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: stages first (1024-aligned), then barriers
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -290,6 +345,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stage = (float*)(base + STAGES * STAGE_BYTES + BAR_BYTES) + (warp >= EPI_WARP0 ? warp - EPI_WARP0 : 0) * STAGE_FLOATS_PER_WARP;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -374,10 +430,11 @@ mma_f16(d_lo, dAlo + adv, dW + adv, (kb == 0 && kk == 0) ? 0u : 1u);
       const long long m = (long long)g * p.rows_per_group + r_in_group;
       mbar_wait(&tfull_bar[0], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      epilogue_tile(p, tmem_base, q, cb0, tn, m, row_ok, nhi);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[0]);
+      epilogue_tile(p, tmem_base, q, cb0, tn, m, row_ok, nhi, stage, [&] {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[0]);
+      });
       acc_phase ^= 1;
     }
   }
@@ -448,7 +505,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc16x2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
-                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo, Params p) {
+                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWlo,
+                 const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(base + STAGES2 * STAGE2_BYTES);   // the leader's are the ones in use
@@ -458,6 +516,7 @@ gemm_tc16x2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stage = (float*)(base + STAGES2 * STAGE2_BYTES + BAR_BYTES) + (warp >= EPI_WARP0 ? warp - EPI_WARP0 : 0) * STAGE_FLOATS_PER_WARP;
   const uint32_t rank = cluster_ctarank();
   const int pairs_per_group = (p.tiles_per_group + 1) / 2;
   const int num_pairs = p.tiles_n * pairs_per_group * p.n_groups;
@@ -550,10 +609,11 @@ gemm_tc16x2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const long long m = (long long)g * p.rows_per_group + r_in_group;
       mbar_wait(&tfull_bar[0], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      epilogue_tile(p, tmem_base, q, cb0, tn, m, row_ok, nhi);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty0);
+      epilogue_tile(p, tmem_base, q, cb0, tn, m, row_ok, nhi, stage, [&] {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty0);
+      });
       acc_phase ^= 1;
     }
   }
@@ -646,7 +706,7 @@ int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st) {
     if (!encode(&mW, g.W_hi, 2, dims, strides, box)) return -100;
     if (!encode(&mWlo, g.W_lo, 2, dims, strides, box)) return -100;
     if (use_pair) {
-      const size_t smem2 = (size_t)STAGES2 * STAGE2_BYTES + 1024 + 256;
+      const size_t smem2 = (size_t)STAGES2 * STAGE2_BYTES + 1024 + BAR_BYTES + EPI_STAGE_BYTES;
       static PerDeviceInt sm_table2;
       const int sm2 = sm_table2.get([&] {
         int dev = 0, n = 0;
@@ -660,7 +720,7 @@ int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st) {
       return (int)cudaGetLastError();
     }
   }
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + BAR_BYTES + EPI_STAGE_BYTES;
   static PerDeviceInt sm_table;           // SM count; the shared-memory attribute is set on the same first use
   const int sm_count = sm_table.get([&] {
     int dev = 0, n = 0;
