@@ -288,6 +288,59 @@ __device__ __forceinline__ void store_rows_staged(const Params& p, const float* 
   if (ovf && p.overflow) *p.overflow = 1;
 }
 
+// Interior block of an fp32 output (read-out, encode / decode hooks): 16 full columns straight from the accumulator
+// registers.  The staging tile above costs shared-memory bandwidth that the tensor core and TMA are already using (the
+// kernel's busiest unit, ~85 % in the main loop): measured 15 us of epilogue per tile through the tile against a 12 us
+// main loop.  Here every lane stores its own row's 64 bytes with the widest vectors the WARP's rows all allow (rows of
+// the config-2 read-out are 1000 bytes apart: 8-byte aligned) — scattered over 32 lines, but fire-and-forget.
+__device__ __forceinline__ void store_c_block(const Params& p, const float (&acc)[16], long long m, int n0, bool row_ok,
+                                              long long sg) {
+  float x[16];
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);          // warp-uniform address: broadcast loads
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 b = b4[j4];
+      x[j4 * 4] = acc[j4 * 4] + b.x; x[j4 * 4 + 1] = acc[j4 * 4 + 1] + b.y;
+      x[j4 * 4 + 2] = acc[j4 * 4 + 2] + b.z; x[j4 * 4 + 3] = acc[j4 * 4 + 3] + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = acc[j];
+  }
+  if (p.act == EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = (x[j] < 0.0f) ? 0.0f : x[j];
+  }
+  if (p.std32) {
+    const float* sd = p.std32 + sg * p.stat_ld;
+    const float* mn = p.mean32 + sg * p.stat_ld;
+    const int smod = p.stat_mod ? p.stat_mod : 0x7fffffff;
+    int sn = p.stat_mod ? n0 % p.stat_mod : n0;                    // statistics column of output column n
+    if (!row_ok) sn = 0;                                           // rows beyond the group read (and discard) row sg's first entries
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      x[j] = __fadd_rn(__fmul_rn(x[j], sd[sn]), mn[sn]);
+      if (++sn == smod) sn = 0;
+    }
+  }
+  float* crow = p.C + m * p.ldc + n0;
+  const unsigned a16 = __all_sync(0xffffffffu, !row_ok || (((uintptr_t)crow) & 15) == 0);
+  const unsigned a8 = __all_sync(0xffffffffu, !row_ok || (((uintptr_t)crow) & 7) == 0);
+  if (!row_ok) return;
+  if (a16) {
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4)
+      *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+  } else if (a8) {
+#pragma unroll
+    for (int j2 = 0; j2 < 8; ++j2) *reinterpret_cast<float2*>(crow + j2 * 2) = make_float2(x[j2 * 2], x[j2 * 2 + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) crow[j] = x[j];
+  }
+}
+
 // `release()` is called exactly once, by all lanes of the warp, when the warp no longer needs the accumulators.
 // `stage`: this warp's STAGE_FLOATS_PER_WARP floats of shared memory.
 template <typename Release>
@@ -297,7 +350,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_bas
   const int lane = threadIdx.x & 31;
   const int rows_ok = __popc(__ballot_sync(0xffffffffu, row_ok));  // valid rows are a prefix of the warp's 32
   const long long m0 = m - lane;
-  const bool pair_fast = p.C16_hi && !p.C && (p.act == EPI_RELU || p.act == EPI_NONE);     // warp-uniform
+  const bool cheap_act = (p.act == EPI_RELU || p.act == EPI_NONE);
+  const bool pair_fast = p.C16_hi && !p.C && cheap_act;           // warp-uniform
+  const bool c_fast = p.C && !p.C16_hi && cheap_act;
+  const int srpg = p.stat_rows_per_group;
+  const long long sg = (c_fast && p.std32 && srpg > 0 && row_ok) ? (m + p.row0) / srpg : 0;   // my row's statistics row
   auto store = [&](const float (&a)[16], int cb) {
     const int n0 = tn * BN + cb * 16;
     if (pair_fast && n0 + 16 <= p.n_store) {                     // interior block of an fp16-pair layer
@@ -305,6 +362,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_bas
         if (p.act == EPI_RELU) store_pair_block<EPI_RELU>(p, a, m, n0);
         else store_pair_block<EPI_NONE>(p, a, m, n0);
       }
+    } else if (c_fast && n0 + 16 <= p.n_store) {                 // interior block of an fp32 output
+      store_c_block(p, a, m, n0, row_ok, sg);
     } else if (n0 < p.n_store) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) stage[lane * STAGE_LD + j] = a[j];

@@ -1,2 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python scripts/cfg3_run.py build_ab/libkmpc_prof10cl.so 7=1 > gpurun_out/r2v_cfg3_cluster_prof.log 2>&1; echo "cluster rc=$?"; grep -v -i warn gpurun_out/r2v_cfg3_cluster_prof.log | grep "block 0" | tail -2 | cut -c1-700
+python scripts/gemm_shapes.py 9102,250,1024 32718,250,1024 32718,1024,1024 2>&1 | grep -v -i Warn
+python scripts/kernel_timeline.py > gpurun_out/r2w_timeline.log 2>&1; echo rc=$?
+sed -n 3,5p gpurun_out/r2w_timeline.log | cut -c1-150; sed -n 13,18p gpurun_out/r2w_timeline.log | cut -c1-150
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_forecast.py tests/test_gpu_pipeline.py -m gpu -x -q > gpurun_out/r2w_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2w_pytest.log

@@ -261,6 +261,46 @@ def test_fp16_pair_chain_matches_tf32_chain_and_oracle():
         assert rowwise_rel(y32[b], want) < FORECAST_RTOL
 
 
+@pytest.mark.parametrize("B,T,d,enc,act,last_relu", [
+    (40, 18, 12, [256, 128], "relu", False),       # 7 rows per path: the read-out looks its statistics row up per output row
+    (5, 61, 12, [256, 128], "relu", True),         # 50 rows per path: two statistics rows inside one warp's 32 rows
+    (6, 150, 12, [264, 136], "relu", False),       # widths 8-aligned but not 16-aligned: ragged last column block of a pair layer
+    (6, 150, 12, [256, 128], "tanh", False),       # tanh / gelu layers: staged fp16-pair output, out-of-line activation
+    (6, 150, 12, [256, 128], "gelu", False),
+])
+def test_fp16_pair_chain_epilogue_paths(B, T, d, enc, act, last_relu):
+    """Every store path of the fp16-pair GEMM epilogue (csrc/gemm_tc16.cu: branch-free interior blocks, the staged /
+    transposed path for fp32 output, slow activations and ragged column blocks, both statistics look-ups of the
+    de-standardising read-out) against the oracle and against the 3xTF32 chain."""
+    import torch
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, data_finance as df, model as km, synthetic
+    from oracle import forecast_oracle as fo, data_oracle as do
+    rng = np.random.default_rng([41, B, T])
+    N, H, Z = 10, 5, 128
+    lr = rng.standard_normal((B, T, N)) * 0.012
+    mean = rng.normal(3e-4, 1e-4, (B, N)); std = rng.uniform(0.008, 0.02, (B, N))
+    sd = synthetic.generic_km_weights(13, N * d, enc, Z)
+    m = km.make_model(km.model_config("GenericKM", Z, enc, enc_bias=True, enc_act=act, last_relu=last_relu), N * d)
+    m.load_state_dict(sd)
+    z = df.standardize_device(lr, mean, std)
+    mean_d, std_d = torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda()
+    rows = T - d + 1
+    assert B * rows >= 128                                    # tensor-core eligible
+    y16 = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, rows, H).cpu().numpy()
+    try:
+        _capi.lib().kmpc_set_gemm_fp16_pairs(0)
+        y32 = m.forecast_series(z, mean_d, std_d, N, d, 0, 0, rows, H).cpu().numpy()
+    finally:
+        _capi.lib().kmpc_set_gemm_fp16_pairs(1)
+    assert not np.array_equal(y16, y32)                      # two different kernels really ran
+    spec = fo.ModelSpec(kind="generic", act=act, last_relu=last_relu, norm_fn="id", dec_act="relu")
+    for b in range(B):
+        emb = do.time_delay_embedding(do.standardize(lr[b], mean[b], std[b]), d)
+        want = fo.forecast(emb, sd, spec, H, N, mean[b], std[b])
+        assert rowwise_rel(y16[b], want) < FORECAST_RTOL
+        assert rowwise_rel(y32[b], want) < FORECAST_RTOL
+
+
 def test_fp16_pair_chain_falls_back_when_values_leave_the_fp16_range():
     """an input beyond 65504 standard deviations cannot travel as an fp16 pair: the range flag sends the call to the
     3xTF32 chain, and the result still matches the oracle"""
