@@ -317,8 +317,10 @@ def other_configs(dev, rank, world, barrier, which=("cfg3", "cfg4", "cfg5"), cfg
         hist_d = torch.from_numpy(hist).to(dev)
         ns = eng.n_steps(rows)
         chunk = 32768                                                   # paths per pass: 16 GB of forecasts
-        wp, _ = engine.bootstrap_paths(hist_d, 1184, T, seed=1234, device=dev, offset=lo)
-        eng.run_device(wp, mean_d, std_d, 0, rows)                      # warm-up on a small sample
+        # warm-up at the size of a timed pass: the first pass allocates its buffers (7 GB of paths, 16 GB of forecasts),
+        # which made the timed pass of earlier records vary between 3.8 and 4.6 s
+        wp, _ = engine.bootstrap_paths(hist_d, min(chunk, hi - lo), T, seed=4321, device=dev, offset=lo)
+        eng.run_device(wp, mean_d, std_d, 0, rows)
         del wp
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -477,9 +479,10 @@ def run_gpu_arm(args):
                    "peak": tensor_peak, "unit": "TFLOP/s", "frac": fc_tflops / tensor_peak, "traffic": None,
                    "peak_source": f"{peak_src} bf16 sustained / 3 (three fp16 MMAs per fp32-accurate product)",
                    "flops_per_decision": fpd, "flops_per_decision_unfolded": flops_per_decision(w), "ms": st_fc,
-                   "note": "the tensor roofline is the stated bound of a dense contraction; timing experiments (DESIGN.md section 8) "
-                           "show this chain limited by operand delivery into the SMs (1 MB of fp16-pair operands per 128 x 128 "
-                           "tile), not by the tensor pipe: a third of the MMAs still takes 89 % of the time"}
+                   "note": "peak = the sustained cuBLAS bf16 rate of this part / 3; per-launch timeline (profiles/README.md): encoder "
+                           "layers 2-3 run at 86 % of that rate, L2 operand delivery (1 MB of fp16-pair operands per 128 x 128 "
+                           "tile) sits just under it; the rest of the gap is layer 1's virtual embedding, the narrow read-out "
+                           "and 1.0 ms of gated empty launches"}
         # The solver's bound is SM instruction issue: 4 warp instructions per clock and SM.
         cnt = solver_counters() if args.workload == "cfg2" else None
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
