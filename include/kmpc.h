@@ -186,6 +186,11 @@ int kmpc_set_gemm_fp16_pairs(int on);
 /* diagnostics / tuning: rows per pass of the fp16-pair forecast chain (rounded down to whole paths; default: see
  * forecast.cu).  Smaller passes keep the layer activations L2-resident between the GEMMs of the chain. */
 int kmpc_set_forecast_chunk_rows(int rows);
+/* 1 [default]: the first layer of the fp16-pair chain reads a materialised embedding of each pass (fp16 pair, rows padded
+ * to 128 bytes, written by one gather kernel per pass: the time-delay embedding of data_finance.py:262-300 for the rows
+ * of the pass); 0: it reads the delay windows in place through a 3-D tensor map (no copy, but unaligned operand rows
+ * and K = delay * (n_assets rounded up to 8)).  Same forecasts up to the summation order of the first layer. */
+int kmpc_set_forecast_embedding(int materialise);
 int kmpc_debug_gemm(kmpc_handle* h, const float* A, const float* W, int M, int Nout, int K, float* C, int mode);
 
 /* ---------------------------------------------------------------------------------------------

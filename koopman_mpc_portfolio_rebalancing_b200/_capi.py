@@ -72,6 +72,7 @@ SIGNATURES = {
     "kmpc_set_forecast_fold": (C.c_int, [C.c_int]),
     "kmpc_set_gemm_fp16_pairs": (C.c_int, [C.c_int]),
     "kmpc_set_forecast_chunk_rows": (C.c_int, [C.c_int]),
+    "kmpc_set_forecast_embedding": (C.c_int, [C.c_int]),
     "kmpc_debug_gemm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
     "kmpc_mpc_solve": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                  vp, vp, vp, vp, vp, vp]),

@@ -45,6 +45,7 @@ struct kmpc_model {
   // read with row stride ld16 = N rounded up to 8), the folded read-out, the standardised series of the current call
   int ld16, fold16_H;
   std::vector<__half*> w16_hi, w16_lo;
+  __half *w16e_hi = nullptr, *w16e_lo = nullptr;   // first layer in the reference's column order, rows padded to Kp (embed16_kernel)
   __half *fold16_hi, *fold16_lo;
   __half *z16_hi, *z16_lo;
   size_t z16_cap;
@@ -78,6 +79,56 @@ __global__ void window_permute_kernel(const float* __restrict__ W, int out_f, in
     const int jj = rem / ld, a = rem - jj * ld;
     Wwin[idx] = (a < N) ? W[(size_t)o * d * N + (size_t)(d - 1 - jj) * N + a] : 0.f;
   }
+}
+
+// Embedded rows of one chunk as an fp16 pair, rows padded to Kp = d*N rounded up to 64 halves (128-byte rows):
+//   out[i, j*N + a] = split16(z[b, row_a + t + d-1-j, a]),  global row r0 + i = b * rpp + t,  zero in the padding columns
+// (data_finance.py:290-298: newest day first).  The fp16-pair GEMM can read the delay windows in place through a 3-D
+// tensor map, but then a row of its A operand starts every ld16 * 2 = 112 bytes (50 assets) and K is d * ld16 = 1120:
+// TMA fetches box rows that straddle 128-byte lines (measured on flat GEMMs of this shape: +30 % when the row stride is
+// not a multiple of 128 bytes) over 18 k-blocks and two ragged tiles per 246-row path.  Writing the chunk's rows once
+// (134 MB, ~30 us) makes layer 1 a flat K = 1024 GEMM like layers 2-3.  One thread = 8 consecutive columns.
+__global__ void embed16_kernel(const float* __restrict__ z, int ld, long long T, int rpp, int row_a, int N, int d, int Kp,
+                               int r0, int rows, __half* __restrict__ hi, __half* __restrict__ lo,
+                               int* __restrict__ overflow) {
+  extern __shared__ int col_off[];                   // column -> offset inside the window (or -1: padding)
+  for (int c = threadIdx.x; c < Kp; c += blockDim.x) {
+    const int j = c / N, a = c - j * N;
+    col_off[c] = (j < d) ? (d - 1 - j) * ld + a : -1;
+  }
+  __syncthreads();
+  const int oct = Kp >> 3;                           // 8-column groups per row
+  const int tpr = oct < (int)blockDim.x ? oct : (int)blockDim.x;      // threads per row
+  const int rpi = (int)blockDim.x / tpr;             // rows per block iteration
+  const int sr = (int)threadIdx.x / tpr, lr = (int)threadIdx.x - sr * tpr;
+  bool ovf = false;
+  if (sr < rpi) {
+    for (int i = blockIdx.x * rpi + sr; i < rows; i += gridDim.x * rpi) {
+      const int R = r0 + i, b = R / rpp;
+      const float* zr = z + ((size_t)b * T + row_a + (R - b * rpp)) * ld;
+      for (int o = lr; o < oct; o += tpr) {
+        const int c0 = o * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int off = col_off[c0 + e];
+          v[e] = (off >= 0) ? zr[off] : 0.0f;
+        }
+        __align__(16) __half h8[8];
+        __align__(16) __half l8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const __half h = __float2half_rn(v[e]);
+          h8[e] = h;
+          l8[e] = __float2half_rn((v[e] - __half2float(h)) * 2048.0f);
+          ovf = ovf || !(fabsf(v[e]) <= 65504.0f);
+        }
+        *reinterpret_cast<uint4*>(hi + (size_t)i * Kp + c0) = *reinterpret_cast<const uint4*>(h8);
+        *reinterpret_cast<uint4*>(lo + (size_t)i * Kp + c0) = *reinterpret_cast<const uint4*>(l8);
+      }
+    }
+  }
+  if (ovf && overflow) *overflow = 1;
 }
 
 // wdT[c, z] = dict[z, c] / max(||dict[z,:]||_2, 1e-4)   (model.py:848-850); one warp per dictionary row z
@@ -175,7 +226,10 @@ static int run_chain(kmpc_handle* h, const kmpc_model* m, const AView& av, int M
   // Row chunks: 4 ping-pong activation buffers + their residual twins.  The chain is compute bound (activation
   // traffic is ~16 KB per row and layer against ~2 MFLOP), so the chunk is sized for full waves of 128-row tiles,
   // not for L2 residency; window views are chunked in whole paths so that tiles never straddle two paths.
-  long long ch = gate ? 8192 : 32768;     // a gated (fallback) chain is rare and slow anyway: keep its scratch small
+  // A gated (fallback) chain costs one empty launch per kernel when its gate stays shut (2.1 us each, CUPTI timeline):
+  // few large passes (32 KB of scratch per row: 4 GB at 131 072 rows) instead of the 500 launches per config-2 step
+  // that passes of 8 192 rows made (1.0 ms, 4 % of the forecast stage).
+  long long ch = gate ? 131072 : 32768;
   if (av.window && av.rows_per_group < M) {
     ch = (ch / av.rows_per_group) * av.rows_per_group;
     if (ch < av.rows_per_group) ch = av.rows_per_group;
@@ -374,6 +428,10 @@ static int g_tc16 = 1;
 // of CH x width x 4 bytes.
 static long long g_chunk_rows = 32768;
 void set_forecast_chunk_rows(long long rows) { g_chunk_rows = rows < 128 ? 128 : rows; }
+// 1 [default]: the first layer of the fp16-pair chain reads a materialised, 128-byte-aligned embedding of the chunk
+// (embed16_kernel); 0: it reads the delay windows in place through the 3-D tensor map
+static int g_embed16 = 1;
+void set_forecast_embed16(int on) { g_embed16 = on ? 1 : 0; }
 void set_gemm_tc16_mode(int on) { g_tc16 = on ? 1 : 0; set_gemm_tc16_pair(on == 2); }
 
 static bool tc16_eligible(const kmpc_model* m) {
@@ -412,6 +470,14 @@ static int ensure_tc16(kmpc_handle* h, kmpc_model* m, int H, cudaStream_t st) {
       h->launches += 2;
     }
   }
+  if (!m->w16e_hi) {
+    const int out_f = m->enc_dims[1], Kp = ((m->d * m->N + 63) / 64) * 64;
+    if ((e = cudaMalloc(&m->w16e_hi, (size_t)out_f * Kp * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(w16e)");
+    if ((e = cudaMalloc(&m->w16e_lo, (size_t)out_f * Kp * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(w16e)");
+    int rc = launch_split16(m->enc_w[0], out_f, m->d * m->N, m->d * m->N, m->w16e_hi, m->w16e_lo, Kp, nullptr, st);
+    if (rc) return kmpc_fail_cuda((cudaError_t)rc, "split16(first layer)");
+    h->launches++;
+  }
   if (!m->fold16_hi || m->fold16_H != m->fold_H || m->fold_H < H) {
     if (m->fold16_hi) { cudaFree(m->fold16_hi); cudaFree(m->fold16_lo); m->fold16_hi = m->fold16_lo = nullptr; }
     const size_t rows_pad = (size_t)((m->fold_H * m->N + 127) / 128) * 128;
@@ -435,25 +501,30 @@ static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int
   if ((rc = ensure_tc16(h, m, H, st))) return rc;
   const int Z = m->Z, N = m->N, ld16 = m->ld16, rpp = t1 - t0, M = B * rpp;
   cudaError_t e;
-  // the standardised series as an fp16 pair, row stride ld16
+  const int Kp = ((m->d * N + 63) / 64) * 64;
+  const bool embed = g_embed16 != 0;
+  // (virtual embedding only) the standardised series as an fp16 pair, row stride ld16
   const size_t zn = (size_t)B * T * ld16;
-  if (m->z16_cap < zn) {
+  if (!embed && m->z16_cap < zn) {
     if (m->z16_hi) { cudaFree(m->z16_hi); cudaFree(m->z16_lo); m->z16_hi = m->z16_lo = nullptr; m->z16_cap = 0; }
     if ((e = cudaMalloc(&m->z16_hi, zn * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(z16)");
     if ((e = cudaMalloc(&m->z16_lo, zn * sizeof(__half))) != cudaSuccess) return kmpc_fail_cuda(e, "cudaMalloc(z16)");
     m->z16_cap = zn;
   }
   cudaMemsetAsync(m->ovf_flag, 0, sizeof(int), st);
-  if ((rc = launch_split16(z, (long long)B * T, N, m->ld, m->z16_hi, m->z16_lo, ld16, m->ovf_flag, st)))
-    return kmpc_fail_cuda((cudaError_t)rc, "split16(series)");
-  h->launches++;
+  if (!embed) {
+    if ((rc = launch_split16(z, (long long)B * T, N, m->ld, m->z16_hi, m->z16_lo, ld16, m->ovf_flag, st)))
+      return kmpc_fail_cuda((cudaError_t)rc, "split16(series)");
+    h->launches++;
+  }
   int maxw = Z;
   for (int v : m->enc_dims) if (v > maxw) maxw = v;
   long long ch = g_chunk_rows;
   if (rpp < M) { ch = (ch / rpp) * rpp; if (ch < rpp) ch = rpp; }
   if (ch > M) ch = M;
   const int CH = (int)ch;
-  const size_t need = (size_t)CH * maxw * 4 * sizeof(__half) + 256;
+  const size_t act_halves = (size_t)CH * maxw * 4;
+  const size_t need = (act_halves + (embed ? (size_t)CH * Kp * 2 : 0)) * sizeof(__half) + 256;
   if (h->scratch_bytes < need) {
     if (h->scratch) cudaFree(h->scratch);
     h->scratch = nullptr; h->scratch_bytes = 0;
@@ -465,20 +536,34 @@ static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int
     act_hi[i] = (__half*)h->scratch + (size_t)(2 * i) * CH * maxw;
     act_lo[i] = (__half*)h->scratch + (size_t)(2 * i + 1) * CH * maxw;
   }
+  __half* emb_hi = (__half*)h->scratch + act_halves;
+  __half* emb_lo = emb_hi + (size_t)CH * Kp;
   for (int r0 = 0; r0 < M; r0 += CH) {
     const int rows = (M - r0 < CH) ? (M - r0) : CH;
     int cur = 0;
+    if (embed) {
+      const int oct = Kp / 8, rpi = oct < 256 ? 256 / oct : 1;
+      int blocks = (rows + rpi - 1) / rpi;
+      if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+      embed16_kernel<<<blocks, 256, Kp * sizeof(int), st>>>(z, m->ld, T, rpp, row0 + t0, N, m->d, Kp, r0, rows, emb_hi, emb_lo,
+                                                          m->ovf_flag);
+      if ((e = cudaGetLastError()) != cudaSuccess) return kmpc_fail_cuda(e, "embed16_kernel");
+      h->launches++;
+    }
     for (int li = 0; li < m->n_enc; ++li) {
       Gemm16Args g;
       memset(&g, 0, sizeof(g));
       const bool last = (li == m->n_enc - 1);
-      if (li == 0) {
+      if (li == 0 && embed) {
+        g.A_hi = emb_hi; g.A_lo = emb_lo; g.a_rows_per_group = rows; g.lda = Kp; g.K = Kp;
+      } else if (li == 0) {
         g.A_hi = m->z16_hi + (size_t)(row0 + t0) * ld16; g.A_lo = m->z16_lo + (size_t)(row0 + t0) * ld16;
         g.a_group_stride = (long long)T * ld16; g.a_rows_per_group = rpp; g.lda = ld16; g.row0 = r0; g.K = m->d * ld16;
       } else {
         g.A_hi = act_hi[cur ^ 1]; g.A_lo = act_lo[cur ^ 1]; g.a_rows_per_group = rows; g.lda = m->enc_dims[li]; g.K = m->enc_dims[li];
       }
       g.W_hi = m->w16_hi[li]; g.W_lo = m->w16_lo[li]; g.ldw = g.K;
+      if (li == 0 && embed) { g.W_hi = m->w16e_hi; g.W_lo = m->w16e_lo; }
       g.M = rows; g.Nout = m->enc_dims[li + 1]; g.n_store = g.Nout;
       g.bias = m->enc_b[li];
       g.act = last ? (m->enc_last_relu ? EPI_RELU : EPI_NONE) : act_to_epi(m->enc_act);
@@ -540,6 +625,7 @@ int kmpc_model_free(kmpc_model* m) {
   if (m->fold_b) cudaFree(m->fold_b);
   for (__half* q : m->w16_hi) cudaFree(q);
   for (__half* q : m->w16_lo) cudaFree(q);
+  if (m->w16e_hi) { cudaFree(m->w16e_hi); cudaFree(m->w16e_lo); }
   if (m->fold16_hi) { cudaFree(m->fold16_hi); cudaFree(m->fold16_lo); }
   if (m->z16_hi) { cudaFree(m->z16_hi); cudaFree(m->z16_lo); }
   if (m->ovf_flag) cudaFree(m->ovf_flag);
@@ -771,6 +857,7 @@ int kmpc_set_gemm_mode(int use_tensor_cores) { kmpc::set_gemm_tc_mode(use_tensor
 int kmpc_set_forecast_fold(int on) { kmpc::set_forecast_fold(on); return KMPC_OK; }
 int kmpc_set_gemm_fp16_pairs(int on) { kmpc::set_gemm_tc16_mode(on); return KMPC_OK; }
 int kmpc_set_forecast_chunk_rows(int rows) { kmpc::set_forecast_chunk_rows(rows); return KMPC_OK; }
+int kmpc_set_forecast_embedding(int materialise) { kmpc::set_forecast_embed16(materialise); return KMPC_OK; }
 
 // C[M,Nout] = A[M,K] . W[Nout,K]^T through one chosen kernel: mode 0 = SIMT fp32, 1 = tcgen05 3xTF32 (returns
 // KMPC_E_UNSUPPORTED if the shape is not eligible).  Allocates the residual twins internally; synchronous.

@@ -26,6 +26,8 @@ def main():
             _capi.lib().kmpc_set_forecast_chunk_rows(int(v))
         elif k == "gemm":
             _capi.lib().kmpc_set_gemm_fp16_pairs(int(v))
+        elif k == "embed":
+            _capi.lib().kmpc_set_forecast_embedding(int(v))
     from koopman_mpc_portfolio_rebalancing_b200 import backtest as bt, engine, model as km, synthetic
     import bench
     w = bench.WORKLOADS["cfg2"]
