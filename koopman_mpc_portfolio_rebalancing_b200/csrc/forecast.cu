@@ -431,7 +431,8 @@ void set_forecast_chunk_rows(long long rows) { g_chunk_rows = rows < 128 ? 128 :
 // 1 [default]: the first layer of the fp16-pair chain reads a materialised, 128-byte-aligned embedding of the chunk
 // (embed16_kernel); 0: it reads the delay windows in place through the 3-D tensor map
 static int g_embed16 = 1;
-void set_forecast_embed16(int on) { g_embed16 = on ? 1 : 0; }
+static int g_alternate = 1;       // tile order alternates from kernel to kernel of a pass (mode 2 of the setter turns it off)
+void set_forecast_embed16(int on) { g_embed16 = on ? 1 : 0; g_alternate = (on == 2) ? 0 : 1; }
 void set_gemm_tc16_mode(int on) { g_tc16 = on ? 1 : 0; set_gemm_tc16_pair(on == 2); }
 
 static bool tc16_eligible(const kmpc_model* m) {
@@ -569,6 +570,10 @@ static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int
       g.act = last ? (m->enc_last_relu ? EPI_RELU : EPI_NONE) : act_to_epi(m->enc_act);
       g.C16_hi = act_hi[cur]; g.C16_lo = act_lo[cur]; g.ldc16 = g.Nout;
       g.overflow_flag = m->ovf_flag;
+      // A layer reads what the previous kernel of the pass has just written (134 MB in, 134 MB out, 126 MB of L2): walking
+      // the tiles in the same order as the writer reads the rows that left L2 first.  Every kernel of the pass therefore
+      // runs opposite to its predecessor (the gather writes forward).
+      g.reverse = (g_alternate && embed) ? ((li & 1) == 0) : 0;
       rc = launch_gemm_tc16(g, st);
       h->launches++;
       if (rc == -100) return 1;                         // not eligible after all: let the TF32 chain take over
@@ -583,6 +588,7 @@ static int run_chain16(kmpc_handle* h, kmpc_model* m, const float* z, int B, int
     d.C = out + (size_t)r0 * H * N; d.ldc = (long long)H * N;
     d.std32 = std32; d.mean32 = mean32; d.stat_rows_per_group = stat_rows_per_group; d.stat_ld = N; d.stat_row0 = r0; d.stat_mod = N;
     d.overflow_flag = m->ovf_flag;
+    d.reverse = (g_alternate && embed) ? ((m->n_enc & 1) == 0) : 0;
     rc = launch_gemm_tc16(d, st);
     h->launches++;
     if (rc == -100) return 1;

@@ -66,6 +66,7 @@ struct Gemm16Args {
   const float* std32; const float* mean32;   // de-standardise epilogue on the fp32 output, as in GemmArgs
   int stat_rows_per_group, stat_ld, stat_row0, stat_mod;
   int* overflow_flag;                        // device int, set to 1 when a value outside the fp16 range is written
+  int reverse;                               // 1: walk the output tiles from the last row block to the first (see run_chain16)
 };
 // returns -100 when the launch is not eligible (shape, alignment)
 int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st);

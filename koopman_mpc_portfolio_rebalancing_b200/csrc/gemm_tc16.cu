@@ -41,6 +41,7 @@ struct Params {
   int M, Nout, K;
   int rows_per_group, tiles_per_group, n_groups;     // M = n_groups * rows_per_group
   int tiles_n, num_tiles, k_blocks;
+  int reverse;                                       // tile t stands for tile num_tiles - 1 - t
   const float* bias;
   int act;
   const float* std32; const float* mean32; int stat_rows_per_group; int stat_ld; int row0; int stat_mod;
@@ -432,7 +433,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+        const int te = p.reverse ? p.num_tiles - 1 - tile : tile;
+        const int tn = te % p.tiles_n, tm = te / p.tiles_n;
         const int g = tm / p.tiles_per_group, tb = tm - g * p.tiles_per_group;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -483,7 +485,8 @@ mma_f16(d_lo, dAlo + adv, dW + adv, (kb == 0 && kk == 0) ? 0u : 1u);
     uint32_t acc_phase = 0;
     const int nhi = p.k_blocks < NUM_HI ? p.k_blocks : NUM_HI;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+      const int te = p.reverse ? p.num_tiles - 1 - tile : tile;
+        const int tn = te % p.tiles_n, tm = te / p.tiles_n;
       const int g = tm / p.tiles_per_group, tb = tm - g * p.tiles_per_group;
       const int r_in_group = tb * BM + q * 32 + lane;
       const bool row_ok = r_in_group < p.rows_per_group;
@@ -745,6 +748,7 @@ int launch_gemm_tc16(const Gemm16Args& g, cudaStream_t st) {
   p.std32 = g.std32; p.mean32 = g.mean32; p.stat_rows_per_group = g.stat_rows_per_group; p.stat_ld = g.stat_ld;
   p.row0 = g.stat_row0; p.stat_mod = g.stat_mod;
   p.overflow = g.overflow_flag;
+  p.reverse = g.reverse;
 
   const long long a_off = flat ? (long long)g.row0 * g.lda
                                : (long long)(g.row0 / g.a_rows_per_group) * g.a_group_stride;

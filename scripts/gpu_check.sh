@@ -13,3 +13,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 $PROF > gpurun_out/${TAG}_prof_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:backtest_lane -s 3 -c 1 -o gpurun_out/${TAG}_backtest_lane $PROF > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "ncu done rc=$?"
+# four consecutive launches of the fp16-pair GEMM (layer 2, layer 3, read-out, layer 1 of the next pass)
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc16_kernel -s 61 -c 4 -o gpurun_out/${TAG}_gemm_tc16 $PROF > gpurun_out/${TAG}_ncu3.log 2>&1
+echo "ncu gemm done rc=$?"
