@@ -79,7 +79,13 @@ enum {
    * parameters (csrc/mpc_common.cuh kRobust*) */
   KMPC_PARAM_SECOND_ATTEMPT = 5,
   /* tolerance on the complementarity gap and the primal residual (default: default_ipm_options().tol) */
-  KMPC_PARAM_TOL = 6
+  KMPC_PARAM_TOL = 6,
+  /* 1 [default]: kmpc_backtest_run solves REDUCED problems once a backtest's portfolio has concentrated (32 < N <= 128,
+   * long-only): only the held assets and the best forecasts of each stage enter the interior-point solve (one warp
+   * per problem instead of two or four), and the optimality conditions of every excluded asset are then checked
+   * against the duals of the reduced solution (an asset that fails joins the set and the problem is solved again), so
+   * the plan is an optimum of the FULL program of mpc.py:49-104.  0: every decision solves all N assets. */
+  KMPC_PARAM_ACTIVE_SET = 7
 };
 int kmpc_set_solver_param(kmpc_handle* h, int which, double value);
 

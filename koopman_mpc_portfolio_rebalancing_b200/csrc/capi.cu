@@ -53,8 +53,9 @@ int kmpc_create(int device, kmpc_handle** out) {
   h->stats32_cap = 0;
   h->mv_work = nullptr;
   h->mv_work_doubles = 0;
+  h->bt_state = nullptr; h->bt_state_doubles = 0; h->bt_status = nullptr; h->bt_status_n = 0;
   h->ipm = kmpc::default_ipm_options();
-  e = cudaMalloc(&h->work_counter, 4 * sizeof(int));      // [0] backtest work counter, [2] structure-flag scratch
+  e = cudaMalloc(&h->work_counter, 4 * sizeof(int));      // [0], [1], [3] backtest work counters, [2] structure-flag scratch
   if (e != cudaSuccess) { delete h; return kmpc_fail_cuda(e, "cudaMalloc(work_counter)"); }
   *out = h;
   return KMPC_OK;
@@ -64,6 +65,8 @@ int kmpc_destroy(kmpc_handle* h) {
   if (!h) return KMPC_OK;
   kmpc_device_guard dev_guard_(h->device);
   cudaFree(h->work_counter);
+  if (h->bt_state) cudaFree(h->bt_state);
+  if (h->bt_status) cudaFree(h->bt_status);
   if (h->scratch) cudaFree(h->scratch);
   if (h->stats32) cudaFree(h->stats32);
   if (h->mv_work) cudaFree(h->mv_work);
@@ -93,6 +96,8 @@ int kmpc_set_solver_param(kmpc_handle* h, int which, double value) {
       h->ipm.second_attempt = (value != 0.0) ? 1 : 0; break;
     case KMPC_PARAM_CLIP_FIRST_TRADE:
       h->ipm.clip_first_trade = (value != 0.0) ? 1 : 0; break;
+    case KMPC_PARAM_ACTIVE_SET:
+      h->ipm.active_set = (int)value; break;
     case KMPC_PARAM_RESET:
       h->ipm = kmpc::default_ipm_options(); break;
     default:
@@ -279,7 +284,8 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   kmpc_device_guard dev_guard_(h->device);
   CK(dev_guard_.err);
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(h->work_counter, 0, 2 * sizeof(int), st));
+  CK(cudaMemsetAsync(h->work_counter + 3, 0, sizeof(int), st));
   kmpc::BacktestArgs A;
   A.yhat = D->yhat; A.realized = D->realized; A.yhat_index = D->yhat_index; A.realized_index = D->realized_index;
   A.yhat_stride = (long long)D->n_steps * D->H * D->N;
@@ -291,6 +297,25 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   A.allow_short = D->allow_short; A.B = D->B; A.N = D->N;
   A.history = D->history; A.metrics = D->metrics; A.solve_stats = (long long*)D->solve_stats;
   A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = h->ipm;
+  A.phase = 0; A.state = nullptr; A.bt_status = nullptr; A.state_ld = D->N + 16; A.as_hmax = 20;
+  if (kmpc::active_set_eligible(A, D->H)) {
+    // per-backtest state of the three-launch pipeline (dense start -> reduced solves -> stragglers)
+    const size_t need = (size_t)D->B * A.state_ld;
+    if (h->bt_state_doubles < need) {
+      if (h->bt_state) cudaFree(h->bt_state);
+      h->bt_state = nullptr; h->bt_state_doubles = 0;
+      CK(cudaMalloc(&h->bt_state, need * sizeof(double)));
+      h->bt_state_doubles = need;
+    }
+    if (h->bt_status_n < (size_t)D->B) {
+      if (h->bt_status) cudaFree(h->bt_status);
+      h->bt_status = nullptr; h->bt_status_n = 0;
+      CK(cudaMalloc(&h->bt_status, (size_t)D->B * sizeof(int)));
+      h->bt_status_n = D->B;
+    }
+    CK(cudaMemsetAsync(h->bt_status, 0, (size_t)D->B * sizeof(int), st));
+    A.state = h->bt_state; A.bt_status = h->bt_status;
+  }
   int rc = kmpc::dispatch_backtest(A, D->H, h->sm_count, st);
   h->launches++;
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_backtest_run: unsupported shape");

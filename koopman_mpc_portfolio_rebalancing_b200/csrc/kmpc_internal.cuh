@@ -41,10 +41,18 @@ struct BacktestArgs {
   int* work_counter;        // device int, zeroed before launch
   int* fix_flag;            // device int (handle-owned scratch), see MpcSolveArgs
   IpmOptions opt;
+  // active-set pipeline (mpc_lane_kernels.cuh, backtest_active_kernel): three launches share per-backtest state
+  int phase;                // 0: whole backtests (no state); 1: dense start, hands over; 2: resumes suspended backtests
+  double* state;            // [B, state_ld]: weights [N], book-keeping, step index; null = pipeline not available
+  int* bt_status;           // [B] 0 fresh, 1 ready for the active-set kernel, 2 suspended (needs the full solver), 3 done
+  int state_ld;
+  int as_hmax;              // phase 1 hands a backtest over at the first decision with at most this many held assets
 };
 
 int dispatch_mpc_solve(const MpcSolveArgs& A, int H, int sm_count, cudaStream_t st);
 int dispatch_backtest(const BacktestArgs& A, int H, int sm_count, cudaStream_t st);
+// 1 if this backtest can take the active-set pipeline (the caller then provides A.state / A.bt_status)
+int active_set_eligible(const BacktestArgs& A, int H);
 
 }  // namespace kmpc
 
@@ -80,7 +88,11 @@ struct kmpc_handle {
   int device;
   int sm_count;
   long long launches;
-  int* work_counter;      // device int for the persistent backtest kernel
+  int* work_counter;      // device ints: [0], [1], [3] work counters of the backtest launches, [2] structure flag
+  double* bt_state;       // per-backtest state of the active-set pipeline, grown on demand
+  size_t bt_state_doubles;
+  int* bt_status;
+  size_t bt_status_n;
   void* scratch;          // device workspace (forecast activations), grown on demand
   size_t scratch_bytes;
   double* mv_work;        // device workspace of the block-wide mean-variance kernel, grown on demand

@@ -768,12 +768,13 @@ struct LaneIpm {
   // realised return, backtest.py:193).  All loads are issued first; ONE rolled copy of the exp code then works through
   // my column of the reduction tile (free between reductions; nobody else touches my column): see div_fast for why
   // the code is kept small.  Call with the tile idle, i.e. after the previous reduction's results have been consumed.
-  __device__ __forceinline__ float load_returns(const float* y, size_t stride, float y_extra) {
+  // `ycol` = my asset's column of y (tid, except for the compacted problems of the active-set kernel).
+  __device__ __forceinline__ float load_returns(const float* y, size_t stride, float y_extra, int ycol) {
     static_assert(H + 1 <= SMALL_ROWS, "tile too small");
     double* col = sm + OFF_TILE + tid;
     float x[H];
 #pragma unroll
-    for (int k = 0; k < H; ++k) x[k] = valid ? y[(size_t)k * stride + tid] : 0.0f;
+    for (int k = 0; k < H; ++k) x[k] = valid ? y[(size_t)k * stride + ycol] : 0.0f;
 #pragma unroll
     for (int k = 0; k < H; ++k) col[k * LD] = (double)x[k];
     col[H * LD] = (double)y_extra;

@@ -95,6 +95,17 @@ struct SlotBook {
   long long it_total;
   int n, n_opt, n_inacc, n_fail;
 };
+// A backtest that changes kernels (active-set pipeline) travels as state[b] = weights [N] | book-keeping [14] | step index.
+__device__ __forceinline__ void book_save(const SlotBook& k, int t, double* S) {
+  S[0] = k.V; S[1] = k.ccoef; S[2] = k.mean; S[3] = k.m2; S[4] = k.cum; S[5] = k.peak; S[6] = k.maxdd; S[7] = k.sum_turn;
+  S[8] = k.v_first; S[9] = (double)k.it_total; S[10] = k.n; S[11] = k.n_opt; S[12] = k.n_inacc; S[13] = k.n_fail; S[14] = t;
+}
+__device__ __forceinline__ void book_load(SlotBook& k, const double* S) {
+  k.V = S[0]; k.ccoef = S[1]; k.mean = S[2]; k.m2 = S[3]; k.cum = S[4]; k.peak = S[5]; k.maxdd = S[6]; k.sum_turn = S[7];
+  k.v_first = S[8]; k.it_total = (long long)S[9]; k.n = (int)S[10]; k.n_opt = (int)S[11]; k.n_inacc = (int)S[12]; k.n_fail = (int)S[13];
+}
+// a weight at or below this counts as "not held" (an interior-point solve leaves ~1e-11 on assets at their bound)
+constexpr double kHeldThr = 1e-9;
 
 template <int H, int G, int P, bool FIX>
 __global__ void KMPC_LANE_BT_ATTR(32 * G * P)
@@ -114,10 +125,21 @@ backtest_lane_kernel(BacktestArgs A, int want) {
   double wc = 0.0;                                 // my asset's current weight
   float e_next = 1.0f;                             // exp(realised log-return of my asset on the day after the decision)
   auto fetch = [&]() -> bool {                     // next backtest of this slot (dynamic: iteration counts differ)
-    if (s.tid == 0) next_b[slot] = atomicAdd(A.work_counter, 1);
-    s.sync();
-    b = __shfl_sync(kFull, next_b[slot], 0);
-    if (b >= A.B) return false;
+    for (;;) {
+      if (s.tid == 0) next_b[slot] = atomicAdd(A.work_counter, 1);
+      s.sync();
+      b = __shfl_sync(kFull, next_b[slot], 0);
+      if (b >= A.B) return false;
+      if (A.phase != 2 || A.bt_status[b] == 2) break;                                  // resume pass: suspended backtests only
+      s.sync();                                                                        // everybody has read next_b
+    }
+    if (A.phase == 2) {                                                                // carry on where the active-set kernel stopped
+      const double* S = A.state + (size_t)b * A.state_ld;
+      wc = s.valid ? S[s.tid] : 0.0;
+      t = (int)S[N + 14];
+      if (s.tid == 0) book_load(books[slot], S + N);
+      return true;
+    }
     wc = s.valid ? 1.0 / (double)N : 0.0;                                              // backtest.py:161
     t = 0;
     if (s.tid == 0) {
@@ -144,11 +166,27 @@ backtest_lane_kernel(BacktestArgs A, int want) {
       for (;;) {
         if (uni(need_start) || uni(st == ST_RESTART)) {
           const bool restart = !need_start;                          // second attempt: same returns, same weights
+          if (uni(!restart && A.phase == 1 && t > 0)) {
+            // dense start of the active-set pipeline: once few assets are held, the backtest moves to the kernel that
+            // solves reduced problems (one warp per problem)
+            s.sync();
+            const double held = s.block_sum1((s.valid && wc > kHeldThr) ? 1.0 : 0.0);
+            if (uni(held <= (double)A.as_hmax)) {
+              double* S = A.state + (size_t)b * A.state_ld;
+              if (s.valid) S[s.tid] = wc;
+              if (s.tid == 0) { book_save(books[slot], t, S + N); A.bt_status[b] = 1; }
+              __syncwarp();
+              s.sync();
+              active = fetch();
+              if (!active) break;
+              continue;
+            }
+          }
           if (!restart) {
             const size_t yb = (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride;
             const size_t rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
             const float y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + s.tid] : 0.0f;
-            e_next = s.load_returns(A.yhat + yb + (size_t)t * H * N, (size_t)N, y_next);    // mpc.py:55
+            e_next = s.load_returns(A.yhat + yb + (size_t)t * H * N, (size_t)N, y_next, s.tid);    // mpc.py:55
           } else {
             s.sync();
           }
@@ -224,6 +262,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         need_start = true; st = -1;
         if (uni(last)) {
           if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
+          if (A.bt_status && s.tid == 0) A.bt_status[b] = 3;
           active = fetch();
           if (!active) break;
         }
@@ -235,6 +274,13 @@ backtest_lane_kernel(BacktestArgs A, int want) {
     // apart is slower (357 vs 273 ms).
     // (the barrier doubles as the exit vote: all slots out of work)
     KMPC_PROF(s, 0)
+#ifdef KMPC_AS_DEBUG
+    if (trip > 30000u) {
+      if (s.lane == 0) printf("G kernel stuck: block %d slot %d warp %d phase %d active %d b %d t %d st %d need_start %d it %d\n",
+                              (int)blockIdx.x, slot, s.warp, A.phase, (int)active, b, t, st, (int)need_start, s.it_);
+      break;
+    }
+#endif
     if ((trip % KMPC_LANE_SYNC_EVERY) == 0) {
       if (__syncthreads_and(!active)) break;
     }
@@ -263,6 +309,328 @@ backtest_lane_kernel(BacktestArgs A, int want) {
   // backtests without any step: NaN metrics (the host never asks for this; kept for completeness)
   if (A.n_steps <= 0) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < A.B * 5; q += gridDim.x * blockDim.x) A.metrics[q] = CUDART_NAN;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Active-set backtest kernel.  Once a portfolio has concentrated, the optimum of mpc.py:49-104 lives on a handful of assets:
+// on the config-2 replay 2-7 of 50 assets are held after the first dozen decisions and the plan never touches more than 8.
+// A slot here is ONE warp (LaneIpm<H, 1>: no problem-wide named barriers, eight problems per SM instead of four; measured
+// 10.3 against 18.1 ns per Newton iteration and GPU) that solves the program RESTRICTED to an active set S of at most 32
+// assets and then PROVES the restriction harmless:
+//   S        = assets held (weight > kHeldThr; lighter ones are dropped, < 5e-8 of weight in total) + the two best forecasts
+//              of every stage, compacted into the lanes of the warp;
+//   solve    = the same interior-point iteration on |S| assets (fewer iterations as well: 6.9 against 8.2 on the replay);
+//   verify   = an excluded asset i stays at w_ik = 0 for all stages iff there are y_k in [-c_k, c_k], c_k = lam + zc_k (the
+//              subgradients of |w_ik - w_i,k-1| at 0 under the cost and the cap's dual) with
+//                  nu_k - R_ik / rho_k + y_k - y_k+1 >= 0   for every stage k       (stationarity with zw_ik >= 0)
+//              where nu, rho, zc are the duals / portfolio returns of the reduced solution.  Backwards from y_H+1 = 0 the
+//              smallest admissible y_k = max(-c_k, y_k+1 - g_k) is also the best choice for stage k - 1, so the greedy
+//              recursion decides feasibility exactly; almost every asset passes the one-comparison pre-check g_k > 0 for all
+//              k, i.e. yhat_ik < log(nu_k rho_k).  The reduced plan padded with zeros then satisfies the KKT conditions of
+//              the FULL convex program: it is an optimum of it, not an approximation;
+//   repair   = an asset that fails joins S and the decision is solved again (never needed on the replay); more than 32
+//              assets in S suspend the backtest: its state is saved and the full-width kernel finishes it (phase 2).
+// Backtests arrive from phase 1 of backtest_lane_kernel (state[b]: weights, book-keeping, step index).
+constexpr double kVerifyTol = 1e-8;     // on the subgradient bound; the duals of the reduced solution carry tol_dual = 1e-8
+
+template <int H, int P, bool FIX>
+__global__ void __launch_bounds__(32 * P, 1)
+backtest_active_kernel(BacktestArgs A, int want) {
+  using Ipm = LaneIpm<H, 1, false, FIX>;
+  constexpr int MAXQ = 4;                          // assets per lane in whole-universe passes (N <= 128)
+  extern __shared__ double smem[];
+  if (want >= 0 && *A.fix_flag != want) return;
+  __shared__ SlotBook books[P];
+  const int slot = __shfl_sync(kFull, (int)threadIdx.x / 32, 0);
+  const int lane = (int)threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  Ipm s;
+  s.bind(smem + (size_t)slot * Ipm::SMEM_DOUBLES, 32, slot);
+  double* wfull = smem + (size_t)P * Ipm::SMEM_DOUBLES + (size_t)slot * (32 * MAXQ);       // weights of all N assets
+  int* sid = reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + slot * 32;   // lane -> asset
+  const int N = A.N;
+  const IpmOptions& opt = A.opt;
+  int b = 0, t = 0, count = 0, a = 0, extra_it = 0;
+  unsigned member = 0;                             // bit q: asset lane + 32 q is in S
+  double wc = 0.0;
+  float e_next = 1.0f;
+  const float* yrow = nullptr;
+  size_t rb = 0;
+  double lam_b = 0.0, tau_b = 0.0;
+
+  auto fetch = [&]() -> bool {
+    for (;;) {
+      int nb = 0;
+      if (lane == 0) nb = atomicAdd(A.work_counter, 1);
+      b = __shfl_sync(kFull, nb, 0);
+      if (b >= A.B) return false;
+      if (A.bt_status[b] == 1) break;
+    }
+    const double* S = A.state + (size_t)b * A.state_ld;
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) { const int i = lane + 32 * q; if (i < N) wfull[i] = S[i]; }
+    t = (int)S[N + 14];
+    if (lane == 0) book_load(books[slot], S + N);
+    rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
+    lam_b = A.lam ? A.lam[b] : A.lam0; tau_b = A.tau ? A.tau[b] : A.tau0;
+    __syncwarp();
+    return true;
+  };
+  auto suspend = [&]() {                           // hand the backtest to the full-width kernel
+    double* S = A.state + (size_t)b * A.state_ld;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) { const int i = lane + 32 * q; if (i < N) S[i] = wfull[i]; }
+    if (lane == 0) { book_save(books[slot], t, S + N); A.bt_status[b] = 2; }
+  };
+  // my lane's problem data for the current S, then the starting point
+  auto start_solve = [&]() -> int {
+    __syncwarp();
+    s.valid = lane < count;
+    a = s.valid ? sid[lane] : 0;
+    wc = s.valid ? wfull[a] : 0.0;
+    const float y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + a] : 0.0f;
+    e_next = s.load_returns(yrow, (size_t)N, y_next, a);                                  // mpc.py:55
+    return s.begin(wc, count, lam_b, tau_b, false, opt, false);
+  };
+  // adds the assets flagged in `add` (bit q of my lane) to S; false if S would exceed the warp
+  auto grow = [&](unsigned add) -> bool {
+    int pos[MAXQ], base = count;
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      const unsigned bal = __ballot_sync(kFull, (add >> q) & 1u);
+      pos[q] = base + __popc(bal & lt_mask);
+      base += __popc(bal);
+    }
+    if (base > 32) return false;
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) if ((add >> q) & 1u) sid[pos[q]] = lane + 32 * q;
+    member |= add; count = base;
+    return true;
+  };
+
+  bool active = fetch();
+  bool need_start = true;
+  int st = -1;
+  __syncthreads();
+#pragma unroll 1
+  for (unsigned trip = 0;; ++trip) {
+    if (uni(active)) {
+#pragma unroll 1
+      for (;;) {
+        if (uni(need_start)) {
+          // ---- a new decision: choose the active set --------------------------------------------------------------------
+          yrow = A.yhat + (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride + (size_t)t * H * N;
+          unsigned add = 0;
+          bool bad = false;                          // a forecast outside the range the full solver accepts (screening of begin())
+#pragma unroll
+          for (int q = 0; q < MAXQ; ++q) {
+            const int i = lane + 32 * q;
+            if (i < N) { if (wfull[i] > kHeldThr) add |= 1u << q; else wfull[i] = 0.0; }
+          }
+#pragma unroll 1
+          for (int k = 0; k < H; ++k) {
+            float v[MAXQ];
+#pragma unroll
+            for (int q = 0; q < MAXQ; ++q) {
+              const int i = lane + 32 * q;
+              v[q] = (i < N) ? yrow[(size_t)k * N + i] : -CUDART_INF_F;
+              if (i < N && !(fabsf(v[q]) < 80.0f)) {                   // exp() may leave the positive normal floats
+                const float r = __double2float_rn(exp((double)v[q]));
+                if (!(isfinite(r) && r > 0.0f)) bad = true;
+              }
+            }
+#pragma unroll 1
+            for (int rep = 0; rep < 2; ++rep) {                         // the two best forecasts of the stage
+              float m = v[0];
+#pragma unroll
+              for (int q = 1; q < MAXQ; ++q) m = fmaxf(m, v[q]);
+              float wm = m;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(kFull, wm, o));
+              const unsigned bal = __ballot_sync(kFull, m == wm && m > -CUDART_INF_F);
+              if (bal && lane == __ffs(bal) - 1) {
+                bool done = false;
+#pragma unroll
+                for (int q = 0; q < MAXQ; ++q) if (!done && v[q] == wm) { add |= 1u << q; v[q] = -CUDART_INF_F; done = true; }
+              }
+            }
+          }
+          member = 0; count = 0; extra_it = 0;
+          const bool fits = grow(add);
+#ifdef KMPC_AS_DEBUG
+          if (lane == 0 && blockIdx.x == 0) printf("AS slot %d b %d t %d count %d fits %d\n", slot, b, t, count, (int)fits);
+#endif
+          if (uni(!fits)) {
+            suspend();
+            active = fetch();
+            if (!active) break;
+            continue;
+          }
+          st = start_solve();
+          if (uni(__any_sync(kFull, bad))) {                           // the full solver would refuse this decision: hold
+#pragma unroll
+            for (int k = 0; k < H; ++k) s.w[k] = wc;
+            s.it_ = 0;
+            st = ST_NONFINITE;
+          }
+          need_start = false;
+        } else if (uni(st == ST_RESTART)) {                            // second attempt: same returns, same weights
+          s.sync();
+          st = s.begin(wc, count, lam_b, tau_b, false, opt, true);
+        }
+        if (uni(st == -1)) st = s.check(opt);
+        if (uni(st == ST_RESTART)) continue;
+        if (uni(st < 0)) break;                                        // take a Newton step
+        if (uni(st <= ST_INACCURATE)) {
+          // ---- converged on S: optimality conditions of the excluded assets ---------------------------------------------
+          double nuk[H], irho[H], ck[H], thr[H];
+          {
+            double lg = 0.0;
+            if (lane < H) lg = log(s.U(Ipm::U_NU, lane) * s.U(Ipm::U_RHO, lane));
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              nuk[k] = s.U(Ipm::U_NU, k); irho[k] = s.U(Ipm::U_IRHO, k);
+              ck[k] = (s.hu() ? s.lam : 0.0) + (s.hc() ? s.U(Ipm::U_ZC, k) : 0.0);
+              thr[k] = shfl_d(lg, k) - 1e-6;                            // g_k > 0 with room for the float32 rounding of R
+            }
+          }
+          unsigned viol = 0;
+#pragma unroll
+          for (int q = 0; q < MAXQ; ++q) {
+            const int i = lane + 32 * q;
+            if (i < N && !((member >> q) & 1u)) {
+              float yv[H];
+              bool safe = true;
+#pragma unroll
+              for (int k = 0; k < H; ++k) { yv[k] = yrow[(size_t)k * N + i]; safe = safe && ((double)yv[k] < thr[k]); }
+              if (!safe) {
+                double yk = 0.0;
+                bool out = false;
+#pragma unroll 1
+                for (int k = H - 1; k >= 0; --k) {
+                  const double Rk = (double)__double2float_rn(exp((double)yv[k]));
+                  const double g = nuk[k] - Rk * irho[k];
+                  yk = fmax(-ck[k], yk - g);
+                  if (!(yk <= ck[k] + kVerifyTol)) out = true;
+                }
+                if (out) viol |= 1u << q;
+              }
+            }
+          }
+#ifdef KMPC_AS_DEBUG
+          { const int anyv = __any_sync(kFull, viol != 0);
+            if (lane == 0 && blockIdx.x == 0) printf("AS slot %d b %d t %d st %d it %d viol %d\n", slot, b, t, st, s.it_, anyv); }
+#endif
+          if (uni(__any_sync(kFull, viol != 0))) {                      // somebody wants in: solve again on the larger set
+            extra_it += s.it_;
+            const bool fits = grow(viol);
+            if (uni(!fits)) {
+              suspend();
+              need_start = true; st = -1;
+              active = fetch();
+              if (!active) break;
+              continue;
+            }
+            st = start_solve();
+            continue;
+          }
+        }
+        // ---- the decision is made: portfolio step (backtest.py:175-217), as in backtest_lane_kernel -------------------
+        const bool market = (t + 1 < A.rows);
+        double wn = s.valid ? s.w[0] : 0.0;                                                // backtest.py:131
+        float r32 = 0.0f;
+        if (s.valid && market) r32 = __fsub_rn(e_next, 1.0f);                              // backtest.py:193
+        double v[3] = {fabs(wn - wc), wn * (double)r32, wc * (double)r32}, T[3];
+        s.sync();
+        s.template block_sum<3>(v, T);
+        double turnover = T[0];
+        double port_ret = market ? T[1] : 0.0;
+        if (opt.clip_first_trade && s.tau > 0.0 && turnover > s.tau) {
+          const double sc = div_fast(s.tau, turnover);
+          wn = fma(sc, wn - wc, wc);
+          if (market) port_ret = fma(sc, T[1] - T[2], T[2]);
+          turnover = s.tau;
+        }
+        wc = wn;
+        if (market) {
+          double denom = 1.0 + port_ret;
+          if (fabs(denom) < 1e-8) denom = 1e-8;
+          wc = div_fast(wn * (double)__fadd_rn(1.0f, r32), denom);                         // (1.0 + f32) stays f32
+        }
+        if (s.valid) wfull[a] = wc;
+        t += A.rebalance_freq;
+        const bool last = (t >= A.n_steps);
+        if (lane == 0) {
+          SlotBook& k = books[slot];
+          k.it_total += s.it_ + extra_it;
+          k.n_opt += (st == ST_OPTIMAL); k.n_inacc += (st == ST_INACCURATE); k.n_fail += (st >= ST_FAILED);
+          const double cost = k.ccoef * turnover * k.V;
+          double V = k.V - cost;
+          if (market) V *= (1.0 + port_ret);
+          k.V = V;
+          if (A.history) {
+            double* hrow = A.history + ((size_t)b * A.n_hist + k.n) * 4;
+            hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
+          }
+          if (k.n == 0) k.v_first = V;
+          const int n = ++k.n;
+          const double dlt = port_ret - k.mean;
+          k.mean += div_fast(dlt, (double)n);
+          k.m2 += dlt * (port_ret - k.mean);
+          k.cum *= (1.0 + port_ret);
+          k.peak = fmax(k.peak, k.cum);
+          k.maxdd = fmin(k.maxdd, div_fast(k.cum - k.peak, k.peak));
+          k.sum_turn += turnover;
+          if (__builtin_expect(last, 0)) {                     // calculate_metrics (backtest.py:221-249)
+            double* m = A.metrics + (size_t)b * 5;
+            const double inv_n = rcp_fast((double)n);
+            const double sd = sqrt(k.m2 * inv_n);
+            m[0] = div_fast(sqrt(252.0) * k.mean, sd + 1e-8);
+            m[1] = k.maxdd;
+            m[2] = k.sum_turn * inv_n;
+            m[3] = V;
+            m[4] = div_fast(V, k.v_first) - 1.0;
+            if (A.solve_stats) {
+              long long* ss = A.solve_stats + (size_t)b * 4;
+              ss[0] = k.n_opt; ss[1] = k.n_inacc; ss[2] = k.n_fail; ss[3] = k.it_total;
+            }
+            A.bt_status[b] = 3;
+          }
+        }
+        need_start = true; st = -1;
+        if (uni(last)) {
+          __syncwarp();
+          if (A.final_weights) {
+#pragma unroll
+            for (int q = 0; q < MAXQ; ++q) { const int i = lane + 32 * q; if (i < N) A.final_weights[(size_t)b * N + i] = wfull[i]; }
+          }
+          active = fetch();
+          if (!active) break;
+        }
+      }
+    }
+#ifdef KMPC_AS_DEBUG
+    if (trip > 30000u) {
+      if (lane == 0) printf("A kernel stuck: block %d slot %d active %d b %d t %d st %d need_start %d it %d count %d\n",
+                            (int)blockIdx.x, slot, (int)active, b, t, st, (int)need_start, s.it_, count);
+      break;
+    }
+#endif
+    if ((trip % KMPC_LANE_SYNC_EVERY) == 0) {
+      if (__syncthreads_and(!active)) break;
+    }
+    const bool act_u = uni(active);
+    bool ok = false;
+    if (act_u) {
+      s.factor_a();
+      ok = s.factor_b();
+    }
+    if (ok) {
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) s.newton_phase(phase, opt);
+    }
   }
 }
 
@@ -312,6 +680,26 @@ static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) 
   auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };
   if (plan != 0) backtest_lane_kernel<H, G, P, true><<<nblocks(bps1), 32 * G * P, smem, st>>>(A, plan == 2 ? 1 : -1);
   if (plan != 1) backtest_lane_kernel<H, G, P, false><<<nblocks(bps0), 32 * G * P, smem, st>>>(A, plan == 2 ? 0 : -1);
+  return (int)cudaGetLastError();
+}
+
+// Active-set pipeline for problems of G > 1 warps (32 < N <= 128), three launches on one stream (no host synchronisation):
+//   phase 1  backtest_lane_kernel<H, G>: every backtest from the equal-weight start until few assets are held;
+//   active   backtest_active_kernel<H>: reduced solves, one warp per problem;
+//   phase 2  backtest_lane_kernel<H, G>: backtests the active-set kernel suspended (active set beyond 32 assets), to their end.
+template <int H>
+static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st) {
+  constexpr int P = 8;
+  using Ipm = LaneIpm<H, 1, false, false>;
+  const size_t smem = (size_t)P * (Ipm::SMEM_DOUBLES + 32 * 4) * sizeof(double) + (size_t)P * 32 * sizeof(int);
+  static PerDeviceInt t0, t1;
+  const int bps0 = t0.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, false>, 32 * P, smem); });
+  const int bps1 = t1.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, true>, 32 * P, smem); });
+  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.B, A.fix_flag, st);
+  const int want = (A.B + P - 1) / P;
+  auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };
+  if (plan != 0) backtest_active_kernel<H, P, true><<<nblocks(bps1), 32 * P, smem, st>>>(A, plan == 2 ? 1 : -1);
+  if (plan != 1) backtest_active_kernel<H, P, false><<<nblocks(bps0), 32 * P, smem, st>>>(A, plan == 2 ? 0 : -1);
   return (int)cudaGetLastError();
 }
 
