@@ -84,7 +84,8 @@ enum {
    * long-only): only the held assets and the best forecasts of each stage enter the interior-point solve (one warp
    * per problem instead of two or four), and the optimality conditions of every excluded asset are then checked
    * against the duals of the reduced solution (an asset that fails joins the set and the problem is solved again), so
-   * the plan is an optimum of the FULL program of mpc.py:49-104.  0: every decision solves all N assets. */
+   * the plan is an optimum of the FULL program of mpc.py:49-104.  0: every decision solves all N assets.  2 (test hook):
+ * as 1 but the set starts from the held assets alone, so that the check-and-repair path does the selecting. */
   KMPC_PARAM_ACTIVE_SET = 7
 };
 int kmpc_set_solver_param(kmpc_handle* h, int which, double value);

@@ -97,7 +97,7 @@ int kmpc_set_solver_param(kmpc_handle* h, int which, double value) {
     case KMPC_PARAM_CLIP_FIRST_TRADE:
       h->ipm.clip_first_trade = (value != 0.0) ? 1 : 0; break;
     case KMPC_PARAM_ACTIVE_SET:
-      h->ipm.active_set = (int)value; break;
+      h->ipm.active_set = (value == 2.0) ? 2 : ((value != 0.0) ? 1 : 0); break;
     case KMPC_PARAM_RESET:
       h->ipm = kmpc::default_ipm_options(); break;
     default:

@@ -6,6 +6,7 @@
 #include "kmpc_internal.cuh"
 #include "mpc_lane.cuh"
 #include <stdio.h>
+#include <type_traits>
 
 // register budget of the backtest kernel: __maxnreg__ and __launch_bounds__ are mutually exclusive
 #ifdef KMPC_LANE_MAXNREG
@@ -333,12 +334,15 @@ backtest_lane_kernel(BacktestArgs A, int want) {
 //              assets in S suspend the backtest: its state is saved and the full-width kernel finishes it (phase 2).
 // Backtests arrive from phase 1 of backtest_lane_kernel (state[b]: weights, book-keeping, step index).
 constexpr double kVerifyTol = 1e-8;     // on the subgradient bound; the duals of the reduced solution carry tol_dual = 1e-8
+#ifndef KMPC_ACTIVE_SYNC_EVERY
+#define KMPC_ACTIVE_SYNC_EVERY 4        // block barrier (and exit vote) every n-th trip of the active-set kernel
+#endif
 
-template <int H, int P, bool FIX>
+template <int H, int P, bool FIX, int NQ>
 __global__ void __launch_bounds__(32 * P, 1)
 backtest_active_kernel(BacktestArgs A, int want) {
   using Ipm = LaneIpm<H, 1, false, FIX>;
-  constexpr int MAXQ = 4;                          // assets per lane in whole-universe passes (N <= 128)
+  constexpr int MAXQ = 4;                          // shared-memory layout: up to 4 assets per lane (N <= 128); this instance: N <= 32 NQ
   extern __shared__ double smem[];
   if (want >= 0 && *A.fix_flag != want) return;
   __shared__ SlotBook books[P];
@@ -350,6 +354,10 @@ backtest_active_kernel(BacktestArgs A, int want) {
   double* wfull = smem + (size_t)P * Ipm::SMEM_DOUBLES + (size_t)slot * (32 * MAXQ);       // weights of all N assets
   int* sid = reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + slot * 32;   // lane -> asset
   const int N = A.N;
+  // the decision's forecasts [H][N] and the next day's realised returns [N], staged once per decision: the selection, the
+  // solver's inputs and the verification all read them, and the global loads of a decision are in flight together
+  float* ystage = reinterpret_cast<float*>(reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + P * 32) +
+                  (size_t)slot * (H + 1) * N;
   const IpmOptions& opt = A.opt;
   int b = 0, t = 0, count = 0, a = 0, extra_it = 0;
   unsigned member = 0;                             // bit q: asset lane + 32 q is in S
@@ -369,7 +377,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
     }
     const double* S = A.state + (size_t)b * A.state_ld;
 #pragma unroll
-    for (int q = 0; q < MAXQ; ++q) { const int i = lane + 32 * q; if (i < N) wfull[i] = S[i]; }
+    for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) wfull[i] = S[i]; }
     t = (int)S[N + 14];
     if (lane == 0) book_load(books[slot], S + N);
     rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
@@ -381,7 +389,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
     double* S = A.state + (size_t)b * A.state_ld;
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < MAXQ; ++q) { const int i = lane + 32 * q; if (i < N) S[i] = wfull[i]; }
+    for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) S[i] = wfull[i]; }
     if (lane == 0) { book_save(books[slot], t, S + N); A.bt_status[b] = 2; }
   };
   // my lane's problem data for the current S, then the starting point
@@ -390,28 +398,29 @@ backtest_active_kernel(BacktestArgs A, int want) {
     s.valid = lane < count;
     a = s.valid ? sid[lane] : 0;
     wc = s.valid ? wfull[a] : 0.0;
-    const float y_next = (s.valid && t + 1 < A.rows) ? A.realized[rb + (size_t)(t + 1) * N + a] : 0.0f;
-    e_next = s.load_returns(yrow, (size_t)N, y_next, a);                                  // mpc.py:55
+    const float y_next = (s.valid && t + 1 < A.rows) ? ystage[H * N + a] : 0.0f;
+    e_next = s.load_returns(ystage, (size_t)N, y_next, a);                                // mpc.py:55
     return s.begin(wc, count, lam_b, tau_b, false, opt, false);
   };
   // adds the assets flagged in `add` (bit q of my lane) to S; false if S would exceed the warp
   auto grow = [&](unsigned add) -> bool {
-    int pos[MAXQ], base = count;
+    int pos[NQ], base = count;
 #pragma unroll
-    for (int q = 0; q < MAXQ; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const unsigned bal = __ballot_sync(kFull, (add >> q) & 1u);
       pos[q] = base + __popc(bal & lt_mask);
       base += __popc(bal);
     }
     if (base > 32) return false;
 #pragma unroll
-    for (int q = 0; q < MAXQ; ++q) if ((add >> q) & 1u) sid[pos[q]] = lane + 32 * q;
+    for (int q = 0; q < NQ; ++q) if ((add >> q) & 1u) sid[pos[q]] = lane + 32 * q;
     member |= add; count = base;
     return true;
   };
 
   bool active = fetch();
-  bool need_start = true;
+  int need_start = 1;                              // 1: a new decision (choose S), 2: the same decision on a grown S, 0: iterating
+  unsigned pending = 0;                            // assets that join S at the next start (bit q of my lane)
   int st = -1;
   __syncthreads();
 #pragma unroll 1
@@ -419,63 +428,81 @@ backtest_active_kernel(BacktestArgs A, int want) {
     if (uni(active)) {
 #pragma unroll 1
       for (;;) {
-        if (uni(need_start)) {
-          // ---- a new decision: choose the active set --------------------------------------------------------------------
-          yrow = A.yhat + (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride + (size_t)t * H * N;
-          unsigned add = 0;
+        if (uni(need_start != 0)) {
           bool bad = false;                          // a forecast outside the range the full solver accepts (screening of begin())
+          if (uni(need_start == 1)) {
+            // ---- a new decision: choose the active set ------------------------------------------------------------------
+            yrow = A.yhat + (size_t)(A.yhat_index ? A.yhat_index[b] : b) * A.yhat_stride + (size_t)t * H * N;
+            {
+              const float* rrow = A.realized + rb + (size_t)(t + 1) * N;
+              const bool market = (t + 1 < A.rows);
+              __syncwarp();
+#pragma unroll 4
+              for (int i = lane; i < (H + 1) * N; i += 32)
+                ystage[i] = (i < H * N) ? yrow[i] : (market ? rrow[i - H * N] : 0.0f);
+              __syncwarp();
+            }
+#pragma unroll 4
+            for (int i = lane; i < H * N; i += 32)
+              if (!(fabsf(ystage[i]) < 80.0f)) bad = true;             // exp() may leave the positive normal floats: looked at below
+            pending = 0;
 #pragma unroll
-          for (int q = 0; q < MAXQ; ++q) {
-            const int i = lane + 32 * q;
-            if (i < N) { if (wfull[i] > kHeldThr) add |= 1u << q; else wfull[i] = 0.0; }
-          }
-#pragma unroll 1
-          for (int k = 0; k < H; ++k) {
-            float v[MAXQ];
-#pragma unroll
-            for (int q = 0; q < MAXQ; ++q) {
+            for (int q = 0; q < NQ; ++q) {
               const int i = lane + 32 * q;
-              v[q] = (i < N) ? yrow[(size_t)k * N + i] : -CUDART_INF_F;
-              if (i < N && !(fabsf(v[q]) < 80.0f)) {                   // exp() may leave the positive normal floats
-                const float r = __double2float_rn(exp((double)v[q]));
-                if (!(isfinite(r) && r > 0.0f)) bad = true;
-              }
+              if (i < N) { if (wfull[i] > kHeldThr) pending |= 1u << q; else wfull[i] = 0.0; }
             }
+            const int n_stage = (opt.active_set == 2) ? 0 : H;    // 2 (test hook): held assets only, the repair path does the rest
 #pragma unroll 1
-            for (int rep = 0; rep < 2; ++rep) {                         // the two best forecasts of the stage
-              float m = v[0];
+            for (int k = 0; k < n_stage; ++k) {
+              float v[NQ];
 #pragma unroll
-              for (int q = 1; q < MAXQ; ++q) m = fmaxf(m, v[q]);
-              float wm = m;
+              for (int q = 0; q < NQ; ++q) {
+                const int i = lane + 32 * q;
+                v[q] = (i < N) ? ystage[k * N + i] : -CUDART_INF_F;
+              }
+#pragma unroll 1
+              for (int rep = 0; rep < 2; ++rep) {                       // the two best forecasts of the stage
+                float m = v[0];
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(kFull, wm, o));
-              const unsigned bal = __ballot_sync(kFull, m == wm && m > -CUDART_INF_F);
-              if (bal && lane == __ffs(bal) - 1) {
-                bool done = false;
+                for (int q = 1; q < NQ; ++q) m = fmaxf(m, v[q]);
+                float wm = m;
 #pragma unroll
-                for (int q = 0; q < MAXQ; ++q) if (!done && v[q] == wm) { add |= 1u << q; v[q] = -CUDART_INF_F; done = true; }
+                for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(kFull, wm, o));
+                const unsigned bal = __ballot_sync(kFull, m == wm && m > -CUDART_INF_F);
+                if (bal && lane == __ffs(bal) - 1) {
+                  bool done = false;
+#pragma unroll
+                  for (int q = 0; q < NQ; ++q) if (!done && v[q] == wm) { pending |= 1u << q; v[q] = -CUDART_INF_F; done = true; }
+                }
               }
             }
+            member = 0; count = 0; extra_it = 0;
           }
-          member = 0; count = 0; extra_it = 0;
-          const bool fits = grow(add);
-#ifdef KMPC_AS_DEBUG
-          if (lane == 0 && blockIdx.x == 0) printf("AS slot %d b %d t %d count %d fits %d\n", slot, b, t, count, (int)fits);
-#endif
-          if (uni(!fits)) {
+          const bool fits = grow(pending);
+          if (uni(!fits)) {                          // more than a warp of active assets: the full-width kernel takes over
             suspend();
+            need_start = 1; st = -1;
             active = fetch();
             if (!active) break;
             continue;
           }
           st = start_solve();
-          if (uni(__any_sync(kFull, bad))) {                           // the full solver would refuse this decision: hold
+          if (uni(__any_sync(kFull, bad))) {
+            // a suspicious forecast somewhere in the universe: would the full solver's screening refuse the decision?
+            bool refuse = false;
+#pragma unroll 1
+            for (int i = lane; i < H * N; i += 32) {
+              const float r = __double2float_rn(exp((double)ystage[i]));
+              if (!(isfinite(r) && r > 0.0f)) refuse = true;
+            }
+            if (uni(__any_sync(kFull, refuse))) {    // hold the weights, as the full solver does
 #pragma unroll
-            for (int k = 0; k < H; ++k) s.w[k] = wc;
-            s.it_ = 0;
-            st = ST_NONFINITE;
+              for (int k = 0; k < H; ++k) s.w[k] = wc;
+              s.it_ = 0;
+              st = ST_NONFINITE;
+            }
           }
-          need_start = false;
+          need_start = 0;
         } else if (uni(st == ST_RESTART)) {                            // second attempt: same returns, same weights
           s.sync();
           st = s.begin(wc, count, lam_b, tau_b, false, opt, true);
@@ -486,25 +513,23 @@ backtest_active_kernel(BacktestArgs A, int want) {
         if (uni(st <= ST_INACCURATE)) {
           // ---- converged on S: optimality conditions of the excluded assets ---------------------------------------------
           double nuk[H], irho[H], ck[H], thr[H];
-          {
-            double lg = 0.0;
-            if (lane < H) lg = log(s.U(Ipm::U_NU, lane) * s.U(Ipm::U_RHO, lane));
 #pragma unroll
-            for (int k = 0; k < H; ++k) {
-              nuk[k] = s.U(Ipm::U_NU, k); irho[k] = s.U(Ipm::U_IRHO, k);
-              ck[k] = (s.hu() ? s.lam : 0.0) + (s.hc() ? s.U(Ipm::U_ZC, k) : 0.0);
-              thr[k] = shfl_d(lg, k) - 1e-6;                            // g_k > 0 with room for the float32 rounding of R
-            }
+          for (int k = 0; k < H; ++k) {
+            nuk[k] = s.U(Ipm::U_NU, k); irho[k] = s.U(Ipm::U_IRHO, k);
+            ck[k] = (s.hu() ? s.lam : 0.0) + (s.hc() ? s.U(Ipm::U_ZC, k) : 0.0);
+            // g_k = nu_k - R_ik / rho_k > 0  <=>  yhat_ik < log(nu_k rho_k); log x >= 1 - 1/x spares the logarithm (nu rho is
+            // within a few per cent of 1), 1e-6 covers the float32 rounding of R
+            thr[k] = 1.0 - rcp_fast(nuk[k]) * irho[k] - 1e-6;
           }
           unsigned viol = 0;
 #pragma unroll
-          for (int q = 0; q < MAXQ; ++q) {
+          for (int q = 0; q < NQ; ++q) {
             const int i = lane + 32 * q;
             if (i < N && !((member >> q) & 1u)) {
               float yv[H];
               bool safe = true;
 #pragma unroll
-              for (int k = 0; k < H; ++k) { yv[k] = yrow[(size_t)k * N + i]; safe = safe && ((double)yv[k] < thr[k]); }
+              for (int k = 0; k < H; ++k) { yv[k] = ystage[k * N + i]; safe = safe && ((double)yv[k] < thr[k]); }
               if (!safe) {
                 double yk = 0.0;
                 bool out = false;
@@ -525,15 +550,8 @@ backtest_active_kernel(BacktestArgs A, int want) {
 #endif
           if (uni(__any_sync(kFull, viol != 0))) {                      // somebody wants in: solve again on the larger set
             extra_it += s.it_;
-            const bool fits = grow(viol);
-            if (uni(!fits)) {
-              suspend();
-              need_start = true; st = -1;
-              active = fetch();
-              if (!active) break;
-              continue;
-            }
-            st = start_solve();
+            pending = viol;
+            need_start = 2; st = -1;
             continue;
           }
         }
@@ -599,12 +617,12 @@ backtest_active_kernel(BacktestArgs A, int want) {
             A.bt_status[b] = 3;
           }
         }
-        need_start = true; st = -1;
+        need_start = 1; st = -1;
         if (uni(last)) {
           __syncwarp();
           if (A.final_weights) {
 #pragma unroll
-            for (int q = 0; q < MAXQ; ++q) { const int i = lane + 32 * q; if (i < N) A.final_weights[(size_t)b * N + i] = wfull[i]; }
+            for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) A.final_weights[(size_t)b * N + i] = wfull[i]; }
           }
           active = fetch();
           if (!active) break;
@@ -618,7 +636,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
       break;
     }
 #endif
-    if ((trip % KMPC_LANE_SYNC_EVERY) == 0) {
+    if ((trip % KMPC_ACTIVE_SYNC_EVERY) == 0) {
       if (__syncthreads_and(!active)) break;
     }
     const bool act_u = uni(active);
@@ -691,15 +709,22 @@ template <int H>
 static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   constexpr int P = 8;
   using Ipm = LaneIpm<H, 1, false, false>;
-  const size_t smem = (size_t)P * (Ipm::SMEM_DOUBLES + 32 * 4) * sizeof(double) + (size_t)P * 32 * sizeof(int);
-  static PerDeviceInt t0, t1;
-  const int bps0 = t0.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, false>, 32 * P, smem); });
-  const int bps1 = t1.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, true>, 32 * P, smem); });
+  const size_t smem_max = (size_t)P * (Ipm::SMEM_DOUBLES + 32 * 4) * sizeof(double) + (size_t)P * 32 * sizeof(int) +
+                          (size_t)P * (H + 1) * 128 * sizeof(float);               // at N = 128
+  const size_t smem = smem_max - (size_t)P * (H + 1) * (128 - A.N) * sizeof(float);
   const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.B, A.fix_flag, st);
   const int want = (A.B + P - 1) / P;
-  auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };
-  if (plan != 0) backtest_active_kernel<H, P, true><<<nblocks(bps1), 32 * P, smem, st>>>(A, plan == 2 ? 1 : -1);
-  if (plan != 1) backtest_active_kernel<H, P, false><<<nblocks(bps0), 32 * P, smem, st>>>(A, plan == 2 ? 0 : -1);
+  auto go = [&](auto nq) {
+    constexpr int NQ = decltype(nq)::value;
+    static PerDeviceInt t0, t1;
+    const int bps0 = t0.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, false, NQ>, 32 * P, smem_max); });
+    const int bps1 = t1.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, true, NQ>, 32 * P, smem_max); });
+    auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };
+    if (plan != 0) backtest_active_kernel<H, P, true, NQ><<<nblocks(bps1), 32 * P, smem, st>>>(A, plan == 2 ? 1 : -1);
+    if (plan != 1) backtest_active_kernel<H, P, false, NQ><<<nblocks(bps0), 32 * P, smem, st>>>(A, plan == 2 ? 0 : -1);
+  };
+  if (A.N <= 64) go(std::integral_constant<int, 2>{});
+  else go(std::integral_constant<int, 4>{});
   return (int)cudaGetLastError();
 }
 

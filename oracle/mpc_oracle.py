@@ -651,7 +651,78 @@ def _solve_structured_once(w_cur, yhat, lam, tau, allow_short=False, *, R=None, 
     if status != STATUS_OPTIMAL and np.isfinite(res[1] + res[2]) and res[0] < LOOSE_PRES and res[1] < LOOSE_DRES \
             and res[2] < LOOSE_GAP:
         status = STATUS_INACCURATE
-    return _finish(w.copy(), w_cur, R, lam, status, it, res, H)
+    out = _finish(w.copy(), w_cur, R, lam, status, it, res, H)
+    out["nu"] = np.asarray(nu, dtype=np.float64).copy()                 # budget duals, cap duals and portfolio returns of the last
+    out["zc"] = np.asarray(zc, dtype=np.float64).copy()                 # iterate: what the active-set verification reads
+    out["rho"] = (w * R).sum(axis=1)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# active-set solve (csrc/mpc_lane_kernels.cuh, backtest_active_kernel)
+# ----------------------------------------------------------------------------------------------
+HELD_THRESHOLD = 1e-9
+VERIFY_TOL = 1e-8
+
+
+def excluded_asset_violations(yhat, members, lam, nu, zc, rho, tol=VERIFY_TOL):
+    """Assets outside `members` whose optimality conditions fail at w_ik = 0 for all k, given the duals of a solution
+    of the program restricted to `members`.  Asset i may stay at zero iff there are y_k in [-c_k, c_k], c_k = lam + zc_k
+    (subgradients of |w_ik - w_i,k-1| at 0 under the cost and the cap's dual), with
+        nu_k - R_ik / rho_k + y_k - y_{k+1} >= 0  for every stage   (stationarity with a non-negative bound dual);
+    backwards from y_{H+1} = 0 the smallest admissible y_k = max(-c_k, y_{k+1} - g_k) is optimal for stage k - 1 too."""
+    R = gross_returns_f32(yhat)
+    H, N = R.shape
+    c = lam + np.asarray(zc, dtype=np.float64)
+    out = []
+    inside = set(int(i) for i in members)
+    for i in range(N):
+        if i in inside:
+            continue
+        g = nu - R[:, i] / rho
+        yk, bad = 0.0, False
+        for k in range(H - 1, -1, -1):
+            yk = max(-c[k], yk - g[k])
+            if not (yk <= c[k] + tol):
+                bad = True
+        if bad:
+            out.append(i)
+    return out
+
+
+def solve_active_set(w_cur, yhat, lam, tau, *, candidates_per_stage=2, max_active=32, **kw):
+    """The reduced solve of the active-set backtest kernel, restated: S = held assets + the best forecasts of each stage,
+    the structured interior point on S, the optimality conditions of the excluded assets, repair and re-solve.  Returns
+    the result of the last solve with `w` padded to all N assets, `members`, `rounds` (solves) and `iters` summed, or None
+    when S outgrows `max_active` (the kernel then hands the backtest to the full-width solver).  Long-only, as the kernel."""
+    w_cur = np.asarray(w_cur, dtype=np.float64)
+    yhat = np.asarray(yhat)
+    H, N = yhat.shape
+    S = set(np.nonzero(w_cur > HELD_THRESHOLD)[0].tolist())
+    for k in range(H):
+        S.update(np.argsort(yhat[k], kind="stable")[N - candidates_per_stage:].tolist() if candidates_per_stage else [])
+    iters, rounds = 0, 0
+    while True:
+        if len(S) > max_active:
+            return None
+        idx = np.array(sorted(S))
+        r = solve_structured(w_cur[idx], yhat[:, idx], lam, tau, False, apply="sweep", **kw)
+        iters += r.iters; rounds += 1
+        if r.status not in (STATUS_OPTIMAL, STATUS_INACCURATE):
+            break
+        viol = excluded_asset_violations(yhat, idx, lam if (lam > 0 or tau > 0) else 0.0, r["nu"],
+                                         r["zc"] if tau > 0 else np.zeros(H), r["rho"])
+        if not viol:
+            break
+        S.update(viol)
+    w = np.zeros((H, N))
+    w[:, idx] = r.w
+    out = _Result(r)
+    out["w"] = w; out["members"] = idx; out["rounds"] = rounds; out["iters"] = iters
+    if r.status in (STATUS_OPTIMAL, STATUS_INACCURATE):
+        w0 = np.where(w_cur > HELD_THRESHOLD, w_cur, 0.0)
+        out["value"] = objective(w, w0, gross_returns_f32(yhat), lam)
+    return out
 
 
 def solve_mpc_log_utility(current_weights, predicted_log_returns, config, method="auto"):

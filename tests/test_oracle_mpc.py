@@ -217,6 +217,37 @@ def test_certificate_bounds_both_oracles(N, H):
     assert mc.feasibility(uncapped.w, w0, 0.05)[2] > 1e-3         # judged against a cap it ignored
 
 
+@pytest.mark.parametrize("cands", [2, 0])
+def test_active_set_restatement_reaches_the_full_optimum(cands):
+    """oracle.solve_active_set (the reduced solve of csrc/mpc_lane_kernels.cuh::backtest_active_kernel, restated): the
+    program restricted to the held assets (+ the best forecasts of each stage) followed by the optimality check of the
+    excluded assets and repair reaches the optimum of the FULL program — against the full structured solve (objective
+    1e-8) and, solver-independently, against the certificate (1e-6 relative, the parity bar) — over concentrated
+    portfolios, mixed costs and caps including the uncapped and the cost-free cases.  cands = 0 starts from the held
+    assets alone, so that every asset of the plan has to come in through the check."""
+    from oracle import mpc_certificate as mc
+    rng = np.random.default_rng(97 + cands)
+    rounds = 0
+    for p in range(14):
+        N = int(rng.choice([40, 50, 64])); H = int(rng.choice([3, 5]))
+        k = int(rng.integers(1, 7))
+        w0 = np.zeros(N); w0[rng.choice(N, k, replace=False)] = rng.dirichlet(np.ones(k))
+        drift = rng.standard_normal(N) * rng.choice([0.001, 0.004])
+        y = (3e-4 + drift + rng.standard_normal((H, N)) * rng.choice([2e-4, 2e-3])).astype(np.float32)
+        lam = float(rng.choice([1e-3, 1e-3, 1e-4, 0.0, 1e-2])); tau = float(rng.choice([0.2, 0.2, 0.05, 1.0, 0.0]))
+        full = mo.solve_structured(w0, y, lam, tau, apply="sweep")
+        act = mo.solve_active_set(w0, y, lam, tau, candidates_per_stage=cands, max_active=32 if cands else N)   # (the 32 lanes of the kernel's warp are not the point of the held-only variant)
+        assert full.status == mo.STATUS_OPTIMAL and act is not None and act.status == mo.STATUS_OPTIMAL
+        assert abs(act.value - full.value) < 1e-8 * max(abs(full.value), 1e-3), (p, act.value, full.value)
+        c = mc.certify(act.w, w0, mo.gross_returns_f32(y), lam, tau)
+        assert -1e-9 < c["gap"] < 1e-6 * max(abs(c["value"]), 1e-3), (p, c)
+        assert c["feas"][0] < 1e-9 and c["feas"][1] < 1e-10 and c["feas"][2] < 1e-9
+        assert np.all(act.w[:, np.setdiff1d(np.arange(N), act.members)] == 0.0)
+        rounds += act.rounds - 1
+    if cands == 0:
+        assert rounds > 0                                        # the check-and-repair path really ran
+
+
 def test_second_attempt_solves_the_stalling_decisions(golden):
     """The 52 decisions of a config-2 step (1.0 M decisions, collected on the GPU with scripts/find_failures.py) that the
     aggressive first attempt leaves `optimal_inaccurate`: near-degenerate optima, the dual residual stalls at 1e-7..1e-5
