@@ -493,7 +493,7 @@ def run_gpu_arm(args):
                     "note": "secondary: the solver streams ~2.4 KB per decision; HBM does not bound it"}
         if cnt:
             ipc = cnt["warp_instructions_per_decision"] * decisions_per_step_rank / (st_bt * 1e-3) / (sm_count * clk_mhz * 1e6)
-            roof_bt = {"kernel": "backtest_lane_kernel (fp64 interior-point MPC + portfolio step, persistent)",
+            roof_bt = {"kernel": cnt.get("kernel", "backtest kernels") + " (fp64 interior-point MPC + portfolio step, persistent)",
                        "bound": "sm_issue", "achieved": ipc, "peak": 4.0, "unit": "warp-instructions/clk/SM", "frac": ipc / 4.0,
                        "traffic": cnt.get("dram_bytes_per_decision", 0) * decisions_per_step_rank or None,
                        "warp_instructions_per_decision": cnt["warp_instructions_per_decision"],
