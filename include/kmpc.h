@@ -85,7 +85,9 @@ enum {
    * per problem instead of two or four), and the optimality conditions of every excluded asset are then checked
    * against the duals of the reduced solution (an asset that fails joins the set and the problem is solved again), so
    * the plan is an optimum of the FULL program of mpc.py:49-104.  0: every decision solves all N assets.  2 (test hook):
- * as 1 but the set starts from the held assets alone, so that the check-and-repair path does the selecting. */
+ * as 1 but the set starts from the held assets alone, so that the check-and-repair path does the selecting.  3 (tuning):
+ * as 1 with whole backtests instead of 32-decision segments as the work items of the reduced-solve kernel; >= 8 (tuning):
+ * as 1 with that many decisions per work item. */
   KMPC_PARAM_ACTIVE_SET = 7
 };
 int kmpc_set_solver_param(kmpc_handle* h, int which, double value);

@@ -55,7 +55,7 @@ int kmpc_create(int device, kmpc_handle** out) {
   h->mv_work_doubles = 0;
   h->bt_state = nullptr; h->bt_state_doubles = 0; h->bt_status = nullptr; h->bt_status_n = 0;
   h->ipm = kmpc::default_ipm_options();
-  e = cudaMalloc(&h->work_counter, 4 * sizeof(int));      // [0], [1], [3] backtest work counters, [2] structure-flag scratch
+  e = cudaMalloc(&h->work_counter, 8 * sizeof(int));      // [0], [1], [3] backtest work counters, [2] structure-flag scratch, [4] done counter
   if (e != cudaSuccess) { delete h; return kmpc_fail_cuda(e, "cudaMalloc(work_counter)"); }
   *out = h;
   return KMPC_OK;
@@ -97,7 +97,9 @@ int kmpc_set_solver_param(kmpc_handle* h, int which, double value) {
     case KMPC_PARAM_CLIP_FIRST_TRADE:
       h->ipm.clip_first_trade = (value != 0.0) ? 1 : 0; break;
     case KMPC_PARAM_ACTIVE_SET:
-      h->ipm.active_set = (value == 2.0) ? 2 : ((value != 0.0) ? 1 : 0); break;
+      if (value >= 8.0) { h->ipm.active_set = 1; h->ipm.active_seg = (int)value; }            // tuning: decisions per work item
+      else { h->ipm.active_set = (value == 2.0) ? 2 : ((value != 0.0) ? 1 : 0); h->ipm.active_seg = (value == 3.0) ? 0 : 32; }
+      break;
     case KMPC_PARAM_RESET:
       h->ipm = kmpc::default_ipm_options(); break;
     default:
@@ -284,8 +286,7 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   kmpc_device_guard dev_guard_(h->device);
   CK(dev_guard_.err);
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(h->work_counter, 0, 2 * sizeof(int), st));
-  CK(cudaMemsetAsync(h->work_counter + 3, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(h->work_counter, 0, 8 * sizeof(int), st));
   kmpc::BacktestArgs A;
   A.yhat = D->yhat; A.realized = D->realized; A.yhat_index = D->yhat_index; A.realized_index = D->realized_index;
   A.yhat_stride = (long long)D->n_steps * D->H * D->N;
@@ -298,6 +299,8 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   A.history = D->history; A.metrics = D->metrics; A.solve_stats = (long long*)D->solve_stats;
   A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = h->ipm;
   A.phase = 0; A.state = nullptr; A.bt_status = nullptr; A.state_ld = D->N + 16; A.as_hmax = 20;
+  A.done_counter = h->work_counter + 4; A.seg = h->ipm.active_seg;
+  A.ready_ring = nullptr; A.queue_ctr = h->work_counter + 5;
   if (kmpc::active_set_eligible(A, D->H)) {
     // per-backtest state of the three-launch pipeline (dense start -> reduced solves -> stragglers)
     const size_t need = (size_t)D->B * A.state_ld;
@@ -310,11 +313,12 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
     if (h->bt_status_n < (size_t)D->B) {
       if (h->bt_status) cudaFree(h->bt_status);
       h->bt_status = nullptr; h->bt_status_n = 0;
-      CK(cudaMalloc(&h->bt_status, (size_t)D->B * sizeof(int)));
+      CK(cudaMalloc(&h->bt_status, (size_t)2 * D->B * sizeof(int)));          // status [B] | ready ring [B]
       h->bt_status_n = D->B;
     }
     CK(cudaMemsetAsync(h->bt_status, 0, (size_t)D->B * sizeof(int), st));
-    A.state = h->bt_state; A.bt_status = h->bt_status;
+    CK(cudaMemsetAsync(h->bt_status + h->bt_status_n, 0xff, (size_t)D->B * sizeof(int), st));   // -1: empty cells
+    A.state = h->bt_state; A.bt_status = h->bt_status; A.ready_ring = h->bt_status + h->bt_status_n;
   }
   int rc = kmpc::dispatch_backtest(A, D->H, h->sm_count, st);
   h->launches++;

@@ -47,6 +47,10 @@ struct BacktestArgs {
   int* bt_status;           // [B] 0 fresh, 1 ready for the active-set kernel, 2 suspended (needs the full solver), 3 done
   int state_ld;
   int as_hmax;              // phase 1 hands a backtest over at the first decision with at most this many held assets
+  int* done_counter;        // device int: backtests that have left the active-set kernel for good (finished or suspended)
+  int seg;                  // decisions per work item of the active-set kernel (0: whole backtests)
+  int* ready_ring;          // [B] ids of the backtests ready for the active-set kernel (-1: empty cell), FIFO
+  int* queue_ctr;           // device ints: [0] head, [1] tail of the ring (monotone counters, position = counter % B)
 };
 
 int dispatch_mpc_solve(const MpcSolveArgs& A, int H, int sm_count, cudaStream_t st);
@@ -88,7 +92,7 @@ struct kmpc_handle {
   int device;
   int sm_count;
   long long launches;
-  int* work_counter;      // device ints: [0], [1], [3] work counters of the backtest launches, [2] structure flag
+  int* work_counter;      // device ints: [0], [1], [3] work counters of the backtest launches, [2] structure flag, [4] done counter, [5], [6] head / tail of the ready queue
   double* bt_state;       // per-backtest state of the active-set pipeline, grown on demand
   size_t bt_state_doubles;
   int* bt_status;

@@ -34,6 +34,7 @@ struct IpmOptions {
   int second_attempt;     // 1: a solve that does not end "optimal" is repeated with the robust parameters (kRobust*)
   int clip_first_trade;   // 1: pull the executed trade of an optimal_inaccurate plan back onto the turnover cap
   int active_set;         // 1: backtests switch to reduced (active-set) solves once the portfolio has concentrated (host-side dispatch)
+  int active_seg;         // decisions per work item of the active-set kernel (0: whole backtests)
 };
 
 __host__ __device__ inline IpmOptions default_ipm_options() {
@@ -46,6 +47,7 @@ __host__ __device__ inline IpmOptions default_ipm_options() {
   o.second_attempt = 1;
   o.clip_first_trade = 1;
   o.active_set = 1;
+  o.active_seg = 32;
   return o;
 }
 

@@ -175,7 +175,11 @@ backtest_lane_kernel(BacktestArgs A, int want) {
             if (uni(held <= (double)A.as_hmax)) {
               double* S = A.state + (size_t)b * A.state_ld;
               if (s.valid) S[s.tid] = wc;
-              if (s.tid == 0) { book_save(books[slot], t, S + N); A.bt_status[b] = 1; }
+              if (s.tid == 0) {
+                book_save(books[slot], t, S + N);
+                A.bt_status[b] = 1;
+                A.ready_ring[(unsigned)atomicAdd(A.queue_ctr + 1, 1) % (unsigned)A.B] = b;      // ready queue of the active-set kernel
+              }
               __syncwarp();
               s.sync();
               active = fetch();
@@ -263,7 +267,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         need_start = true; st = -1;
         if (uni(last)) {
           if (A.final_weights && s.valid) A.final_weights[(size_t)b * N + s.tid] = wc;
-          if (A.bt_status && s.tid == 0) A.bt_status[b] = 3;
+          if (A.bt_status && s.tid == 0) { A.bt_status[b] = 3; if (A.phase == 1) atomicAdd(A.done_counter, 1); }
           active = fetch();
           if (!active) break;
         }
@@ -359,7 +363,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
   float* ystage = reinterpret_cast<float*>(reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + P * 32) +
                   (size_t)slot * (H + 1) * N;
   const IpmOptions& opt = A.opt;
-  int b = 0, t = 0, count = 0, a = 0, extra_it = 0;
+  int b = 0, t = 0, count = 0, a = 0, extra_it = 0, seg_left = 0;
   unsigned member = 0;                             // bit q: asset lane + 32 q is in S
   double wc = 0.0;
   float e_next = 1.0f;
@@ -367,30 +371,76 @@ backtest_active_kernel(BacktestArgs A, int want) {
   size_t rb = 0;
   double lam_b = 0.0, tau_b = 0.0;
 
-  auto fetch = [&]() -> bool {
-    for (;;) {
-      int nb = 0;
-      if (lane == 0) nb = atomicAdd(A.work_counter, 1);
-      b = __shfl_sync(kFull, nb, 0);
-      if (b >= A.B) return false;
-      if (A.bt_status[b] == 1) break;
+  // Work items are SEGMENTS of backtests (A.seg decisions): a slot that has run a segment saves the backtest's state and
+  // appends it to the ready queue again, then takes the backtest at the head of the queue.  Whole backtests as items leave
+  // the last round of slots partly empty (4096 backtests on 1184 slots: 3.46 rounds cost 4); with segments in FIFO order
+  // every backtest advances at the same rate and the slots run dry together.  The queue is a ring of B ids (a backtest is
+  // in it at most once): push = reserve a position with an atomic increment of the tail, then publish the id; pop = advance
+  // the head by compare-and-swap while head < tail, then take the id of the reserved position (it is published a moment
+  // after the reservation at the latest).  An idle slot only READS head and tail until there is work.
+  // done_counter counts the backtests that have left this kernel for good (finished, or suspended for the full-width kernel).
+  // returns 1: a backtest is loaded; 0: none ready right now (the others are running); -1: every backtest has left the kernel
+  auto fetch = [&]() -> int {
+    int got = -1;
+    if (lane == 0) {
+      volatile int* head = A.queue_ctr;
+      volatile int* tail = A.queue_ctr + 1;
+#pragma unroll 1
+      for (int tries = 0; tries < 16; ++tries) {
+        if (*(volatile int*)A.done_counter >= A.B) { got = -2; break; }
+        const int hd = *head;
+        if (hd >= *tail) break;                        // empty
+        if (atomicCAS(A.queue_ctr, hd, hd + 1) == hd) {
+          int* cell = A.ready_ring + (unsigned)hd % (unsigned)A.B;
+          int v;
+          while ((v = atomicExch(cell, -1)) < 0) { }   // reserved by its pusher an instant ago
+          got = v;
+          break;
+        }
+      }
     }
+    got = __shfl_sync(kFull, got, 0);
+    if (got == -2) return -1;
+    if (got < 0) return 0;
+    b = got;
+    __threadfence();                                 // the state below was written by the backtest's previous slot
     const double* S = A.state + (size_t)b * A.state_ld;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) wfull[i] = S[i]; }
-    t = (int)S[N + 14];
-    if (lane == 0) book_load(books[slot], S + N);
+    for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) wfull[i] = __ldcg(S + i); }
+    t = (int)__ldcg(S + N + 14);
+    if (lane == 0) {
+      double bk[14];
+#pragma unroll
+      for (int i = 0; i < 14; ++i) bk[i] = __ldcg(S + N + i);
+      book_load(books[slot], bk);
+    }
     rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
     lam_b = A.lam ? A.lam[b] : A.lam0; tau_b = A.tau ? A.tau[b] : A.tau0;
+    seg_left = (A.seg > 0) ? A.seg : 0x7fffffff;
     __syncwarp();
-    return true;
+    return 1;
   };
-  auto suspend = [&]() {                           // hand the backtest to the full-width kernel
-    double* S = A.state + (size_t)b * A.state_ld;
+  // gives the backtest up: status 1 = ready for its next segment, 2 = for the full-width kernel (both with the state saved),
+  // 3 = finished
+  auto release = [&](int status) {
     __syncwarp();
+    if (status != 3) {
+      double* S = A.state + (size_t)b * A.state_ld;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) S[i] = wfull[i]; }
-    if (lane == 0) { book_save(books[slot], t, S + N); A.bt_status[b] = 2; }
+      for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) S[i] = wfull[i]; }
+      if (lane == 0) book_save(books[slot], t, S + N);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      if (status == 1) {
+        const int pos = atomicAdd(A.queue_ctr + 1, 1);
+        atomicExch(A.ready_ring + (unsigned)pos % (unsigned)A.B, b);
+      } else {
+        A.bt_status[b] = status;
+        atomicAdd(A.done_counter, 1);
+      }
+    }
   };
   // my lane's problem data for the current S, then the starting point
   auto start_solve = [&]() -> int {
@@ -418,13 +468,19 @@ backtest_active_kernel(BacktestArgs A, int want) {
     return true;
   };
 
-  bool active = fetch();
+  int have = fetch();
+  bool active = have == 1, finished = have < 0;    // active: a backtest is loaded; finished: nothing left for this kernel
   int need_start = 1;                              // 1: a new decision (choose S), 2: the same decision on a grown S, 0: iterating
   unsigned pending = 0;                            // assets that join S at the next start (bit q of my lane)
   int st = -1;
   __syncthreads();
 #pragma unroll 1
   for (unsigned trip = 0;; ++trip) {
+    if (uni(!active && !finished)) {               // idle: every ready backtest was taken a moment ago; look again
+      have = fetch();
+      active = have == 1; finished = have < 0;
+      need_start = 1; st = -1;
+    }
     if (uni(active)) {
 #pragma unroll 1
       for (;;) {
@@ -480,9 +536,10 @@ backtest_active_kernel(BacktestArgs A, int want) {
           }
           const bool fits = grow(pending);
           if (uni(!fits)) {                          // more than a warp of active assets: the full-width kernel takes over
-            suspend();
+            release(2);
             need_start = 1; st = -1;
-            active = fetch();
+            have = fetch();
+            active = have == 1; finished = have < 0;
             if (!active) break;
             continue;
           }
@@ -614,7 +671,6 @@ backtest_active_kernel(BacktestArgs A, int want) {
               long long* ss = A.solve_stats + (size_t)b * 4;
               ss[0] = k.n_opt; ss[1] = k.n_inacc; ss[2] = k.n_fail; ss[3] = k.it_total;
             }
-            A.bt_status[b] = 3;
           }
         }
         need_start = 1; st = -1;
@@ -624,7 +680,11 @@ backtest_active_kernel(BacktestArgs A, int want) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) A.final_weights[(size_t)b * N + i] = wfull[i]; }
           }
-          active = fetch();
+        }
+        if (uni(last || --seg_left == 0)) {          // the backtest is finished, or its segment is: take the next ready one
+          release(last ? 3 : 1);
+          have = fetch();
+          active = have == 1; finished = have < 0;
           if (!active) break;
         }
       }
@@ -637,7 +697,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
     }
 #endif
     if ((trip % KMPC_ACTIVE_SYNC_EVERY) == 0) {
-      if (__syncthreads_and(!active)) break;
+      if (__syncthreads_and(finished)) break;
     }
     const bool act_u = uni(active);
     bool ok = false;
