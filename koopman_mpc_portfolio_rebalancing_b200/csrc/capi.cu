@@ -321,7 +321,7 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
     A.state = h->bt_state; A.bt_status = h->bt_status; A.ready_ring = h->bt_status + h->bt_status_n;
   }
   int rc = kmpc::dispatch_backtest(A, D->H, h->sm_count, st);
-  h->launches++;
+  h->launches += A.state ? 3 : 1;                     // dense start, reduced solves, stragglers
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_backtest_run: unsupported shape");
   if (rc) return kmpc_fail_cuda((cudaError_t)rc, "backtest_kernel");
   return KMPC_OK;

@@ -393,7 +393,10 @@ backtest_active_kernel(BacktestArgs A, int want) {
         if (atomicCAS(A.queue_ctr, hd, hd + 1) == hd) {
           int* cell = A.ready_ring + (unsigned)hd % (unsigned)A.B;
           int v;
-          while ((v = atomicExch(cell, -1)) < 0) { }   // reserved by its pusher an instant ago
+          unsigned spins = 0;
+          while ((v = atomicExch(cell, -1)) < 0) {     // reserved by its pusher an instant ago
+            if (++spins > (1u << 24)) { printf("kmpc active-set kernel: ready queue cell never published\n"); __trap(); }   // fail loudly, never hang
+          }
           got = v;
           break;
         }
@@ -471,6 +474,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
   int have = fetch();
   bool active = have == 1, finished = have < 0;    // active: a backtest is loaded; finished: nothing left for this kernel
   int need_start = 1;                              // 1: a new decision (choose S), 2: the same decision on a grown S, 0: iterating
+  unsigned idle_trips = 0;
   unsigned pending = 0;                            // assets that join S at the next start (bit q of my lane)
   int st = -1;
   __syncthreads();
@@ -480,6 +484,14 @@ backtest_active_kernel(BacktestArgs A, int want) {
       have = fetch();
       active = have == 1; finished = have < 0;
       need_start = 1; st = -1;
+      if (!active && !finished) {
+        __nanosleep(500);                            // nothing to do until a neighbour releases a backtest
+        if (++idle_trips > (1u << 28)) {             // minutes of idling: trap instead of hanging the GPU
+          if (lane == 0) printf("kmpc active-set kernel: slot idle for 2^28 trips with unfinished backtests\n");
+          __trap();
+        }
+      }
+      if (active) idle_trips = 0;
     }
     if (uni(active)) {
 #pragma unroll 1
