@@ -1,0 +1,69 @@
+"""Stress of the active-set backtest pipeline against the full-width kernel over shapes and parameters (development tool):
+every case must finish (run it under `timeout`), end with the same statuses, and agree on the histories.
+  python scripts/as_stress.py [seed]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import numpy as np, torch
+    from koopman_mpc_portfolio_rebalancing_b200 import _capi, backtest as bt
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    rng = np.random.default_rng(seed)
+    h = _capi.Handle.get(0)
+    worst = 0.0
+    cases = []
+    for N in (33, 50, 64, 65, 100, 128):
+        for H in (1, 2, 3, 4, 5):
+            cases.append((N, H))
+    for ci, (N, H) in enumerate(cases):
+        B = int(rng.choice([1, 3, 40, 333, 1500]))
+        rows = int(rng.choice([8, 30, 90]))
+        freq = int(rng.choice([1, 1, 2, 5]))
+        ns = rows - 1 - H
+        if ns < 1:
+            continue
+        g = torch.Generator(device="cuda").manual_seed(1000 * seed + ci)
+        persist = float(rng.choice([0.0, 1e-3, 3e-3]))
+        noise = float(rng.choice([2e-4, 2e-3]))
+        drift = persist * torch.randn((B, 1, 1, N), device="cuda", generator=g)
+        yhat = (3e-4 + drift + noise * torch.randn((B, ns, H, N), device="cuda", generator=g)).float()
+        realized = (3e-4 + 1.2e-2 * torch.randn((B, rows, N), device="cuda", generator=g)).float()
+        if rng.random() < 0.15:
+            yhat[rng.integers(0, B), rng.integers(0, ns), rng.integers(0, H), rng.integers(0, N)] = float("nan")
+        kind = rng.choice(["scalar", "arrays", "nocap", "nocost", "tight"])
+        kw = {}
+        if kind == "arrays":
+            kw = dict(lam=rng.choice([1e-3, 1e-4, 0.0, 1e-2], B), tau=rng.choice([0.2, 0.05, 1.0, 0.0], B))
+        elif kind == "nocap":
+            kw = dict(tau0=0.0)
+        elif kind == "nocost":
+            kw = dict(lam0=0.0)
+        elif kind == "tight":
+            kw = dict(tau0=0.01)
+        res = {}
+        t0 = time.time()
+        for mode in (0, 1, 2):
+            _capi.check(_capi.lib().kmpc_set_solver_param(h.ptr, 7, float(mode)))
+            out = bt.run_backtest_batched(yhat, realized, n_steps=ns, horizon=H, rebalance_freq=freq, want_history=True, **kw)
+            torch.cuda.synchronize()
+            res[mode] = (out["history"].cpu().numpy(), out["stats"].cpu().numpy().sum(axis=0))
+        _capi.check(_capi.lib().kmpc_set_solver_param(h.ptr, 7, 1.0))
+        v0 = res[0][0][..., 0]
+        d1 = float(np.nanmax(np.abs(res[1][0][..., 0] / v0 - 1))); d2 = float(np.nanmax(np.abs(res[2][0][..., 0] / v0 - 1)))
+        same = (res[0][1][:3] == res[1][1][:3]).all() and (res[0][1][:3] == res[2][1][:3]).all()
+        worst = max(worst, d1, d2)
+        if max(d1, d2) >= 1e-4:                      # keep the worst backtest of a mismatching case for the CPU oracle
+            bw = int(np.nanargmax(np.nanmax(np.abs(res[1][0][..., 0] / v0 - 1), axis=1)))
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            np.savez(os.path.join(ROOT, "gpurun_out", f"as_mismatch_{N}_{H}.npz"), yhat=yhat[bw].cpu().numpy(), realized=realized[bw].cpu().numpy(),
+                     lam=(kw["lam"][bw] if "lam" in kw else kw.get("lam0", 1e-3)), tau=(kw["tau"][bw] if "tau" in kw else kw.get("tau0", 0.2)),
+                     freq=freq, h0=res[0][0][bw], h1=res[1][0][bw], h2=res[2][0][bw])
+        print(f"N={N:3d} H={H} B={B:4d} rows={rows:2d} freq={freq} {kind:7s} persist={persist:g} noise={noise:g}: stats {res[0][1]} / {res[1][1]} / {res[2][1]}"
+              f"  dv {d1:.1e} {d2:.1e}  {'OK' if same and max(d1, d2) < 1e-4 else 'MISMATCH'}  {time.time() - t0:.1f}s", flush=True)
+    print("worst relative value difference", worst)
+
+
+if __name__ == "__main__":
+    main()
