@@ -13,7 +13,7 @@ int KMPC_CAT(launch_mpc, KMPC_H, KMPC_G)(const MpcSolveArgs& A, int sm_count, cu
 int KMPC_CAT(launch_bt, KMPC_H, KMPC_G)(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   return launch_bt_lane<KMPC_H, KMPC_G>(A, sm_count, st);
 }
-#if KMPC_G == 1 && KMPC_H <= 5
+#if KMPC_G == 1 && (KMPC_H <= 5 || KMPC_H == 10)
 // the active-set kernel (one warp per reduced problem) lives with the one-warp variant of its horizon
 int KMPC_CAT(launch_bta, KMPC_H, KMPC_G)(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   return launch_bt_active<KMPC_H>(A, sm_count, st);

@@ -345,8 +345,8 @@ constexpr double kVerifyTol = 1e-8;     // on the subgradient bound; the duals o
 template <int H, int P, bool FIX, int NQ>
 __global__ void __launch_bounds__(32 * P, 1)
 backtest_active_kernel(BacktestArgs A, int want) {
-  using Ipm = LaneIpm<H, 1, false, FIX>;
-  constexpr int MAXQ = 4;                          // shared-memory layout: up to 4 assets per lane (N <= 128); this instance: N <= 32 NQ
+  using Ipm = LaneIpm<H, 1, (H > 5), FIX>;           // H = 10: thread-private factors (32 threads: they stay in L1)
+  constexpr int MAXQ = NQ;                         // assets per lane in passes over the whole universe (N <= 32 NQ)
   extern __shared__ double smem[];
   if (want >= 0 && *A.fix_flag != want) return;
   __shared__ SlotBook books[P];
@@ -360,8 +360,12 @@ backtest_active_kernel(BacktestArgs A, int want) {
   const int N = A.N;
   // the decision's forecasts [H][N] and the next day's realised returns [N], staged once per decision: the selection, the
   // solver's inputs and the verification all read them, and the global loads of a decision are in flight together
+  // (large universes — config 3: 11 x 500 floats per slot — read them from global memory / L2 instead)
+  const bool staged = N <= 128;
   float* ystage = reinterpret_cast<float*>(reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + P * 32) +
                   (size_t)slot * (H + 1) * N;
+  const float* ysrc = nullptr;                     // [H][N] forecasts of the decision
+  const float* rnext = nullptr;                    // [N] next day's realised log-returns
   const IpmOptions& opt = A.opt;
   int b = 0, t = 0, count = 0, a = 0, extra_it = 0, seg_left = 0;
   unsigned member = 0;                             // bit q: asset lane + 32 q is in S
@@ -451,23 +455,26 @@ backtest_active_kernel(BacktestArgs A, int want) {
     s.valid = lane < count;
     a = s.valid ? sid[lane] : 0;
     wc = s.valid ? wfull[a] : 0.0;
-    const float y_next = (s.valid && t + 1 < A.rows) ? ystage[H * N + a] : 0.0f;
-    e_next = s.load_returns(ystage, (size_t)N, y_next, a);                                // mpc.py:55
+    const float y_next = (s.valid && t + 1 < A.rows) ? rnext[a] : 0.0f;
+    e_next = s.load_returns(ysrc, (size_t)N, y_next, a);                                  // mpc.py:55
     return s.begin(wc, count, lam_b, tau_b, false, opt, false);
   };
-  // adds the assets flagged in `add` (bit q of my lane) to S; false if S would exceed the warp
-  auto grow = [&](unsigned add) -> bool {
-    int pos[NQ], base = count;
+  // adds the assets flagged in `add` (bit q of my lane) to S.  must = true: all of them, false if S would exceed the warp;
+  // must = false (candidates): as many as fit — an asset left out is still subject to the optimality check afterwards
+  auto grow = [&](unsigned add, bool must) -> bool {
+    int base = count;
 #pragma unroll
+    for (int q = 0; q < NQ; ++q) base += __popc(__ballot_sync(kFull, (add >> q) & 1u));
+    if (must && base > 32) return false;
+    base = count;
+#pragma unroll 1
     for (int q = 0; q < NQ; ++q) {
       const unsigned bal = __ballot_sync(kFull, (add >> q) & 1u);
-      pos[q] = base + __popc(bal & lt_mask);
+      const int pos = base + __popc(bal & lt_mask);
+      if (((add >> q) & 1u) && pos < 32) { sid[pos] = lane + 32 * q; member |= 1u << q; }
       base += __popc(bal);
     }
-    if (base > 32) return false;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) if ((add >> q) & 1u) sid[pos[q]] = lane + 32 * q;
-    member |= add; count = base;
+    count = base < 32 ? base : 32;
     return true;
   };
 
@@ -475,7 +482,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
   bool active = have == 1, finished = have < 0;    // active: a backtest is loaded; finished: nothing left for this kernel
   int need_start = 1;                              // 1: a new decision (choose S), 2: the same decision on a grown S, 0: iterating
   unsigned idle_trips = 0;
-  unsigned pending = 0;                            // assets that join S at the next start (bit q of my lane)
+  unsigned pending = 0, cand = 0;                  // assets that join S at the next start / candidates (bit q of my lane)
   int st = -1;
   __syncthreads();
 #pragma unroll 1
@@ -504,21 +511,27 @@ backtest_active_kernel(BacktestArgs A, int want) {
             {
               const float* rrow = A.realized + rb + (size_t)(t + 1) * N;
               const bool market = (t + 1 < A.rows);
-              __syncwarp();
+              if (staged) {
+                __syncwarp();
 #pragma unroll 4
-              for (int i = lane; i < (H + 1) * N; i += 32)
-                ystage[i] = (i < H * N) ? yrow[i] : (market ? rrow[i - H * N] : 0.0f);
-              __syncwarp();
+                for (int i = lane; i < (H + 1) * N; i += 32)
+                  ystage[i] = (i < H * N) ? yrow[i] : (market ? rrow[i - H * N] : 0.0f);
+                __syncwarp();
+                ysrc = ystage; rnext = ystage + H * N;
+              } else {
+                ysrc = yrow; rnext = rrow;
+              }
             }
 #pragma unroll 4
             for (int i = lane; i < H * N; i += 32)
-              if (!(fabsf(ystage[i]) < 80.0f)) bad = true;             // exp() may leave the positive normal floats: looked at below
+              if (!(fabsf(ysrc[i]) < 80.0f)) bad = true;               // exp() may leave the positive normal floats: looked at below
             pending = 0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
               const int i = lane + 32 * q;
               if (i < N) { if (wfull[i] > kHeldThr) pending |= 1u << q; else wfull[i] = 0.0; }
             }
+            cand = 0;
             const int n_stage = (opt.active_set == 2) ? 0 : H;    // 2 (test hook): held assets only, the repair path does the rest
 #pragma unroll 1
             for (int k = 0; k < n_stage; ++k) {
@@ -526,7 +539,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
 #pragma unroll
               for (int q = 0; q < NQ; ++q) {
                 const int i = lane + 32 * q;
-                v[q] = (i < N) ? ystage[k * N + i] : -CUDART_INF_F;
+                v[q] = (i < N) ? ysrc[k * N + i] : -CUDART_INF_F;
               }
 #pragma unroll 1
               for (int rep = 0; rep < 2; ++rep) {                       // the two best forecasts of the stage
@@ -540,13 +553,14 @@ backtest_active_kernel(BacktestArgs A, int want) {
                 if (bal && lane == __ffs(bal) - 1) {
                   bool done = false;
 #pragma unroll
-                  for (int q = 0; q < NQ; ++q) if (!done && v[q] == wm) { pending |= 1u << q; v[q] = -CUDART_INF_F; done = true; }
+                  for (int q = 0; q < NQ; ++q) if (!done && v[q] == wm) { cand |= 1u << q; v[q] = -CUDART_INF_F; done = true; }
                 }
               }
             }
             member = 0; count = 0; extra_it = 0;
           }
-          const bool fits = grow(pending);
+          const bool fits = grow(pending, true);     // the held assets (or the assets that failed the check) must all fit
+          if (uni(fits && need_start == 1)) grow(cand & ~member, false);
           if (uni(!fits)) {                          // more than a warp of active assets: the full-width kernel takes over
             release(2);
             need_start = 1; st = -1;
@@ -561,7 +575,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
             bool refuse = false;
 #pragma unroll 1
             for (int i = lane; i < H * N; i += 32) {
-              const float r = __double2float_rn(exp((double)ystage[i]));
+              const float r = __double2float_rn(exp((double)ysrc[i]));
               if (!(isfinite(r) && r > 0.0f)) refuse = true;
             }
             if (uni(__any_sync(kFull, refuse))) {    // hold the weights, as the full solver does
@@ -598,7 +612,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
               float yv[H];
               bool safe = true;
 #pragma unroll
-              for (int k = 0; k < H; ++k) { yv[k] = ystage[k * N + i]; safe = safe && ((double)yv[k] < thr[k]); }
+              for (int k = 0; k < H; ++k) { yv[k] = ysrc[k * N + i]; safe = safe && ((double)yv[k] < thr[k]); }
               if (!safe) {
                 double yk = 0.0;
                 bool out = false;
@@ -773,21 +787,22 @@ static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) 
   return (int)cudaGetLastError();
 }
 
-// Active-set pipeline for problems of G > 1 warps (32 < N <= 128), three launches on one stream (no host synchronisation):
+// Active-set pipeline for problems of G > 1 warps (32 < N <= 512), three launches on one stream (no host synchronisation):
 //   phase 1  backtest_lane_kernel<H, G>: every backtest from the equal-weight start until few assets are held;
 //   active   backtest_active_kernel<H>: reduced solves, one warp per problem;
 //   phase 2  backtest_lane_kernel<H, G>: backtests the active-set kernel suspended (active set beyond 32 assets), to their end.
 template <int H>
 static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   constexpr int P = 8;
-  using Ipm = LaneIpm<H, 1, false, false>;
-  const size_t smem_max = (size_t)P * (Ipm::SMEM_DOUBLES + 32 * 4) * sizeof(double) + (size_t)P * 32 * sizeof(int) +
-                          (size_t)P * (H + 1) * 128 * sizeof(float);               // at N = 128
-  const size_t smem = smem_max - (size_t)P * (H + 1) * (128 - A.N) * sizeof(float);
+  using Ipm = LaneIpm<H, 1, (H > 5), false>;
   const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.B, A.fix_flag, st);
   const int want = (A.B + P - 1) / P;
   auto go = [&](auto nq) {
     constexpr int NQ = decltype(nq)::value;
+    // per slot: the solver's slice, the weights of the whole universe, the lane -> asset table and (N <= 128) the staged forecasts
+    const size_t fixed = (size_t)P * (Ipm::SMEM_DOUBLES + 32 * NQ) * sizeof(double) + (size_t)P * 32 * sizeof(int);
+    const size_t smem_max = fixed + (NQ <= 4 ? (size_t)P * (H + 1) * 32 * NQ * sizeof(float) : 0);
+    const size_t smem = fixed + (A.N <= 128 ? (size_t)P * (H + 1) * A.N * sizeof(float) : 0);
     static PerDeviceInt t0, t1;
     const int bps0 = t0.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, false, NQ>, 32 * P, smem_max); });
     const int bps1 = t1.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, true, NQ>, 32 * P, smem_max); });
@@ -796,7 +811,8 @@ static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st
     if (plan != 1) backtest_active_kernel<H, P, false, NQ><<<nblocks(bps0), 32 * P, smem, st>>>(A, plan == 2 ? 0 : -1);
   };
   if (A.N <= 64) go(std::integral_constant<int, 2>{});
-  else go(std::integral_constant<int, 4>{});
+  else if (A.N <= 128) go(std::integral_constant<int, 4>{});
+  else go(std::integral_constant<int, 16>{});
   return (int)cudaGetLastError();
 }
 
