@@ -338,6 +338,12 @@ backtest_lane_kernel(BacktestArgs A, int want) {
 //              assets in S suspend the backtest: its state is saved and the full-width kernel finishes it (phase 2).
 // Backtests arrive from phase 1 of backtest_lane_kernel (state[b]: weights, book-keeping, step index).
 constexpr double kVerifyTol = 1e-8;     // on the subgradient bound; the duals of the reduced solution carry tol_dual = 1e-8
+// H = 10 one-warp problems: sweep factors and corrector targets in shared memory (45 KB per slot, four slots per SM) rather
+// than thread-private (LOC: 3 KB of local memory per thread, eight slots per SM)
+#ifndef KMPC_ACTIVE_LOC
+#define KMPC_ACTIVE_LOC(H) false
+#endif
+template <int H> struct ActiveSlots { static constexpr int P = (H > 5 && !KMPC_ACTIVE_LOC(H)) ? 4 : 8; };
 #ifndef KMPC_ACTIVE_SYNC_EVERY
 #define KMPC_ACTIVE_SYNC_EVERY 4        // block barrier (and exit vote) every n-th trip of the active-set kernel
 #endif
@@ -345,7 +351,7 @@ constexpr double kVerifyTol = 1e-8;     // on the subgradient bound; the duals o
 template <int H, int P, bool FIX, int NQ>
 __global__ void __launch_bounds__(32 * P, 1)
 backtest_active_kernel(BacktestArgs A, int want) {
-  using Ipm = LaneIpm<H, 1, (H > 5), FIX>;           // H = 10: thread-private factors (32 threads: they stay in L1)
+  using Ipm = LaneIpm<H, 1, KMPC_ACTIVE_LOC(H), FIX>;
   constexpr int MAXQ = NQ;                         // assets per lane in passes over the whole universe (N <= 32 NQ)
   extern __shared__ double smem[];
   if (want >= 0 && *A.fix_flag != want) return;
@@ -793,8 +799,8 @@ static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) 
 //   phase 2  backtest_lane_kernel<H, G>: backtests the active-set kernel suspended (active set beyond 32 assets), to their end.
 template <int H>
 static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st) {
-  constexpr int P = 8;
-  using Ipm = LaneIpm<H, 1, (H > 5), false>;
+  constexpr int P = ActiveSlots<H>::P;
+  using Ipm = LaneIpm<H, 1, KMPC_ACTIVE_LOC(H), false>;
   const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.B, A.fix_flag, st);
   const int want = (A.B + P - 1) / P;
   auto go = [&](auto nq) {
