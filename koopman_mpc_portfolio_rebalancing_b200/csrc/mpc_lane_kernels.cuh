@@ -367,11 +367,11 @@ backtest_active_kernel(BacktestArgs A, int want) {
   // the decision's forecasts [H][N] and the next day's realised returns [N], staged once per decision: the selection, the
   // solver's inputs and the verification all read them, and the global loads of a decision are in flight together
   // (large universes — config 3: 11 x 500 floats per slot — read them from global memory / L2 instead)
-  const bool staged = N <= 128;
+  constexpr bool staged = NQ <= 4;                 // N <= 128 (the launcher picks NQ from N)
   float* ystage = reinterpret_cast<float*>(reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + P * 32) +
                   (size_t)slot * (H + 1) * N;
-  const float* ysrc = nullptr;                     // [H][N] forecasts of the decision
-  const float* rnext = nullptr;                    // [N] next day's realised log-returns
+  const float* ysrc = ystage;                      // [H][N] forecasts of the decision (staged: fixed, in shared memory)
+  const float* rnext = ystage + H * N;             // [N] next day's realised log-returns
   const IpmOptions& opt = A.opt;
   int b = 0, t = 0, count = 0, a = 0, extra_it = 0, seg_left = 0;
   unsigned member = 0;                             // bit q: asset lane + 32 q is in S
@@ -523,7 +523,6 @@ backtest_active_kernel(BacktestArgs A, int want) {
                 for (int i = lane; i < (H + 1) * N; i += 32)
                   ystage[i] = (i < H * N) ? yrow[i] : (market ? rrow[i - H * N] : 0.0f);
                 __syncwarp();
-                ysrc = ystage; rnext = ystage + H * N;
               } else {
                 ysrc = yrow; rnext = rrow;
               }
