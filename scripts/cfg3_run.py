@@ -1,4 +1,4 @@
-"""One timed pass of BASELINE config 3 (LISTAKM, 500 assets, H = 10; development tool).
+"""One timed pass of BASELINE config 3 (LISTAKM, 500 assets, H = 10), 4 or 5 (development tool); add cfg4 / cfg5 to choose.
   python scripts/cfg3_run.py [lib.so] [param=value ...]      # e.g. 7=0: KMPC_PARAM_CLUSTER off"""
 import json
 import os
@@ -22,11 +22,15 @@ def main():
     prof = "prof" in args
     if prof:
         args.remove("prof")
+    which = "cfg3"
+    for a in list(args):
+        if a in ("cfg3", "cfg4", "cfg5"):
+            which = a; args.remove(a)
     if prof:                                          # CUPTI durations of the kernels of the pass (torch.profiler)
         from torch.profiler import profile, ProfilerActivity
         import collections
         with profile(activities=[ProfilerActivity.CUDA]) as pr:
-            res = bench.other_configs(dev, 0, 1, torch.cuda.synchronize, which=("cfg3",))
+            res = bench.other_configs(dev, 0, 1, torch.cuda.synchronize, which=(which,))
             torch.cuda.synchronize()
         agg = collections.defaultdict(list)
         for e in pr.events():
@@ -35,9 +39,9 @@ def main():
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))[:8]:
             print(f"{k:80s} n={len(v):4d} total={sum(v) / 1e3:10.2f} ms  each: {[round(x / 1e3, 1) for x in v[:6]]}")
     else:
-        res = bench.other_configs(dev, 0, 1, torch.cuda.synchronize, which=("cfg3",))
+        res = bench.other_configs(dev, 0, 1, torch.cuda.synchronize, which=(which,))
         torch.cuda.synchronize()
-    print(json.dumps(res["cfg3"]))
+    print(json.dumps(res[which]))
 
 
 if __name__ == "__main__":
