@@ -80,8 +80,8 @@ enum {
   KMPC_PARAM_SECOND_ATTEMPT = 5,
   /* tolerance on the complementarity gap and the primal residual (default: default_ipm_options().tol) */
   KMPC_PARAM_TOL = 6,
-  /* 1 [default]: kmpc_backtest_run solves REDUCED problems once a backtest's portfolio has concentrated (32 < N <= 128,
-   * long-only): only the held assets and the best forecasts of each stage enter the interior-point solve (one warp
+  /* 1 [default]: kmpc_backtest_run solves REDUCED problems once a backtest's portfolio has concentrated (32 < N <= 512,
+   * H <= 5 or H = 10, long-only): only the held assets and the best forecasts of each stage enter the interior-point solve (one warp
    * per problem instead of two or four), and the optimality conditions of every excluded asset are then checked
    * against the duals of the reduced solution (an asset that fails joins the set and the problem is solved again), so
    * the plan is an optimum of the FULL program of mpc.py:49-104.  0: every decision solves all N assets.  2 (test hook):
@@ -265,6 +265,10 @@ typedef struct kmpc_backtest_desc {
   double* final_weights;      /* [B,N] or NULL */
 } kmpc_backtest_desc;
 
+/* Asynchronous on `stream`.  One persistent kernel, or (KMPC_PARAM_ACTIVE_SET, default) three: the dense start of every
+ * backtest, the reduced solves once its portfolio has concentrated, and the backtests the reduced-solve kernel had to
+ * give back; they hand backtests to each other through a handle-owned state buffer ([B, N + 16] doubles), without host
+ * synchronisation.  `solve_stats` counts every Newton step a decision took, re-solves on a grown active set included. */
 int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* desc, void* stream);
 
 #ifdef __cplusplus

@@ -2,6 +2,8 @@
 // backtest.py:173-249.  mpc_solve: one block of G warps per
 // problem; backtest: a persistent block hosts several backtests ("slots" of G warps each) that walk through the
 // Newton iteration together.  Thread i of a slot = asset i, all stages of an asset in that thread's registers.
+// backtest_lane_kernel solves all N assets at every decision; backtest_active_kernel (further down) solves the held
+// assets + candidates on one warp and verifies the rest, and takes over once a portfolio has concentrated.
 #pragma once
 #include "kmpc_internal.cuh"
 #include "mpc_lane.cuh"
