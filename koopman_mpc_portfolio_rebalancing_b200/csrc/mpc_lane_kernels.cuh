@@ -109,6 +109,44 @@ __device__ __forceinline__ void book_load(SlotBook& k, const double* S) {
 }
 // a weight at or below this counts as "not held" (an interior-point solve leaves ~1e-11 on assets at their bound)
 constexpr double kHeldThr = 1e-9;
+// One decision of backtest b goes into the books (thread 0 of the slot): trading cost, portfolio value, the history row and
+// the running statistics of backtest.py:175-217; at the last step calculate_metrics (backtest.py:221-249).
+__device__ __forceinline__ void book_decision(SlotBook& k, const BacktestArgs& A, int b, int st, long long iters, double turnover,
+                                              double port_ret, bool market, bool last) {
+  k.it_total += iters;
+  k.n_opt += (st == ST_OPTIMAL); k.n_inacc += (st == ST_INACCURATE); k.n_fail += (st >= ST_FAILED);
+  const double cost = k.ccoef * turnover * k.V;
+  double V = k.V - cost;
+  if (market) V *= (1.0 + port_ret);
+  k.V = V;
+  if (A.history) {
+    double* hrow = A.history + ((size_t)b * A.n_hist + k.n) * 4;
+    hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
+  }
+  if (k.n == 0) k.v_first = V;
+  const int n = ++k.n;
+  const double dlt = port_ret - k.mean;
+  k.mean += div_fast(dlt, (double)n);
+  k.m2 += dlt * (port_ret - k.mean);
+  k.cum *= (1.0 + port_ret);
+  k.peak = fmax(k.peak, k.cum);
+  k.maxdd = fmin(k.maxdd, div_fast(k.cum - k.peak, k.peak));
+  k.sum_turn += turnover;
+  if (__builtin_expect(last, 0)) {                     // calculate_metrics (backtest.py:221-249)
+    double* m = A.metrics + (size_t)b * 5;
+    const double inv_n = rcp_fast((double)n);
+    const double sd = sqrt(k.m2 * inv_n);
+    m[0] = div_fast(sqrt(252.0) * k.mean, sd + 1e-8);
+    m[1] = k.maxdd;
+    m[2] = k.sum_turn * inv_n;
+    m[3] = V;
+    m[4] = div_fast(V, k.v_first) - 1.0;
+    if (A.solve_stats) {
+      long long* ss = A.solve_stats + (size_t)b * 4;
+      ss[0] = k.n_opt; ss[1] = k.n_inacc; ss[2] = k.n_fail; ss[3] = k.it_total;
+    }
+  }
+}
 
 template <int H, int G, int P, bool FIX>
 __global__ void KMPC_LANE_BT_ATTR(32 * G * P)
@@ -231,40 +269,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         t += A.rebalance_freq;
         const bool last = (t >= A.n_steps);
         if (s.tid == 0) {
-          SlotBook& k = books[slot];
-          k.it_total += s.it_;
-          k.n_opt += (st == ST_OPTIMAL); k.n_inacc += (st == ST_INACCURATE); k.n_fail += (st >= ST_FAILED);
-          const double cost = k.ccoef * turnover * k.V;
-          double V = k.V - cost;
-          if (market) V *= (1.0 + port_ret);
-          k.V = V;
-          if (A.history) {
-            double* hrow = A.history + ((size_t)b * A.n_hist + k.n) * 4;
-            hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
-          }
-          if (k.n == 0) k.v_first = V;
-          const int n = ++k.n;
-          const double dlt = port_ret - k.mean;
-          k.mean += div_fast(dlt, (double)n);
-          k.m2 += dlt * (port_ret - k.mean);
-          k.cum *= (1.0 + port_ret);
-          k.peak = fmax(k.peak, k.cum);
-          k.maxdd = fmin(k.maxdd, div_fast(k.cum - k.peak, k.peak));
-          k.sum_turn += turnover;
-          if (__builtin_expect(last, 0)) {                     // calculate_metrics (backtest.py:221-249)
-            double* m = A.metrics + (size_t)b * 5;
-            const double inv_n = rcp_fast((double)n);
-            const double sd = sqrt(k.m2 * inv_n);
-            m[0] = div_fast(sqrt(252.0) * k.mean, sd + 1e-8);
-            m[1] = k.maxdd;
-            m[2] = k.sum_turn * inv_n;
-            m[3] = V;
-            m[4] = div_fast(V, k.v_first) - 1.0;
-            if (A.solve_stats) {
-              long long* ss = A.solve_stats + (size_t)b * 4;
-              ss[0] = k.n_opt; ss[1] = k.n_inacc; ss[2] = k.n_fail; ss[3] = k.it_total;
-            }
-          }
+          book_decision(books[slot], A, b, st, s.it_, turnover, port_ret, market, last);
         }
         need_start = true; st = -1;
         if (uni(last)) {
@@ -671,40 +676,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
         t += A.rebalance_freq;
         const bool last = (t >= A.n_steps);
         if (lane == 0) {
-          SlotBook& k = books[slot];
-          k.it_total += s.it_ + extra_it;
-          k.n_opt += (st == ST_OPTIMAL); k.n_inacc += (st == ST_INACCURATE); k.n_fail += (st >= ST_FAILED);
-          const double cost = k.ccoef * turnover * k.V;
-          double V = k.V - cost;
-          if (market) V *= (1.0 + port_ret);
-          k.V = V;
-          if (A.history) {
-            double* hrow = A.history + ((size_t)b * A.n_hist + k.n) * 4;
-            hrow[0] = V; hrow[1] = port_ret; hrow[2] = turnover; hrow[3] = cost;
-          }
-          if (k.n == 0) k.v_first = V;
-          const int n = ++k.n;
-          const double dlt = port_ret - k.mean;
-          k.mean += div_fast(dlt, (double)n);
-          k.m2 += dlt * (port_ret - k.mean);
-          k.cum *= (1.0 + port_ret);
-          k.peak = fmax(k.peak, k.cum);
-          k.maxdd = fmin(k.maxdd, div_fast(k.cum - k.peak, k.peak));
-          k.sum_turn += turnover;
-          if (__builtin_expect(last, 0)) {                     // calculate_metrics (backtest.py:221-249)
-            double* m = A.metrics + (size_t)b * 5;
-            const double inv_n = rcp_fast((double)n);
-            const double sd = sqrt(k.m2 * inv_n);
-            m[0] = div_fast(sqrt(252.0) * k.mean, sd + 1e-8);
-            m[1] = k.maxdd;
-            m[2] = k.sum_turn * inv_n;
-            m[3] = V;
-            m[4] = div_fast(V, k.v_first) - 1.0;
-            if (A.solve_stats) {
-              long long* ss = A.solve_stats + (size_t)b * 4;
-              ss[0] = k.n_opt; ss[1] = k.n_inacc; ss[2] = k.n_fail; ss[3] = k.it_total;
-            }
-          }
+          book_decision(books[slot], A, b, st, s.it_ + extra_it, turnover, port_ret, market, last);
         }
         need_start = 1; st = -1;
         if (uni(last)) {
