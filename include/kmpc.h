@@ -265,10 +265,10 @@ typedef struct kmpc_backtest_desc {
   double* final_weights;      /* [B,N] or NULL */
 } kmpc_backtest_desc;
 
-/* Asynchronous on `stream`.  One persistent kernel, or (KMPC_PARAM_ACTIVE_SET, default) three: the dense start of every
- * backtest, the reduced solves once its portfolio has concentrated, and the backtests the reduced-solve kernel had to
- * give back; they hand backtests to each other through a handle-owned state buffer ([B, N + 16] doubles), without host
- * synchronisation.  `solve_stats` counts every Newton step a decision took, re-solves on a grown active set included. */
+/* Asynchronous on `stream`.  One persistent kernel, or (KMPC_PARAM_ACTIVE_SET, default) a fixed sequence of five: the dense
+ * start of every backtest, the reduced solves once its portfolio has concentrated, and — for backtests the reduced-solve
+ * kernel had to give back — a full-width pass, a second reduced-solve pass and a final full-width pass; they hand
+ * backtests to each other through a handle-owned state buffer ([B, N + 16] doubles), without host synchronisation.  `solve_stats` counts every Newton step a decision took, re-solves on a grown active set included. */
 int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* desc, void* stream);
 
 #ifdef __cplusplus

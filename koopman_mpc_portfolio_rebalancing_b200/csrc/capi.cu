@@ -298,7 +298,7 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
   A.allow_short = D->allow_short; A.B = D->B; A.N = D->N;
   A.history = D->history; A.metrics = D->metrics; A.solve_stats = (long long*)D->solve_stats;
   A.final_weights = D->final_weights; A.work_counter = h->work_counter; A.fix_flag = h->work_counter + 2; A.opt = h->ipm;
-  A.phase = 0; A.state = nullptr; A.bt_status = nullptr; A.state_ld = D->N + 16; A.as_hmax = (D->H > 5) ? 24 : 20;
+  A.phase = 0; A.state = nullptr; A.bt_status = nullptr; A.state_ld = D->N + 16; A.as_hmax = 24;       // (28 made config-3 backtests overflow the warp twice and finish full-width: 1.9 s instead of 1.0 s)
   A.done_counter = h->work_counter + 4; A.seg = h->ipm.active_seg;
   A.ready_ring = nullptr; A.queue_ctr = h->work_counter + 5;
   if (kmpc::active_set_eligible(A, D->H)) {
@@ -321,7 +321,7 @@ int kmpc_backtest_run(kmpc_handle* h, const kmpc_backtest_desc* D, void* stream)
     A.state = h->bt_state; A.bt_status = h->bt_status; A.ready_ring = h->bt_status + h->bt_status_n;
   }
   int rc = kmpc::dispatch_backtest(A, D->H, h->sm_count, st);
-  h->launches += A.state ? 3 : 1;                     // dense start, reduced solves, stragglers
+  h->launches += A.state ? 5 : 1;                     // dense start, reduced solves, second chance (2), stragglers
   if (rc == -2) return fail(KMPC_E_UNSUPPORTED, "kmpc_backtest_run: unsupported shape");
   if (rc) return kmpc_fail_cuda((cudaError_t)rc, "backtest_kernel");
   return KMPC_OK;

@@ -42,7 +42,8 @@ struct BacktestArgs {
   int* fix_flag;            // device int (handle-owned scratch), see MpcSolveArgs
   IpmOptions opt;
   // active-set pipeline (mpc_lane_kernels.cuh, backtest_active_kernel): three launches share per-backtest state
-  int phase;                // 0: whole backtests (no state); 1: dense start, hands over; 2: resumes suspended backtests
+  int phase;                // 0: whole backtests (no state); 1: dense start, hands over; 3: resumes suspended backtests and hands
+                            // them over again; 2: resumes suspended backtests, to their end
   double* state;            // [B, state_ld]: weights [N], book-keeping, step index; null = pipeline not available
   int* bt_status;           // [B] 0 fresh, 1 ready for the active-set kernel, 2 suspended (needs the full solver), 3 done
   int state_ld;

@@ -162,7 +162,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
   const int N = A.N;
   const IpmOptions& opt = A.opt;
   // ---- per-thread state of the slot's current backtest ----------------------------------------------------------
-  int b = 0, t = 0;
+  int b = 0, t = 0, t_in = -1;                     // t_in: step at which a resumed backtest came in (it runs at least one decision here)
   double wc = 0.0;                                 // my asset's current weight
   float e_next = 1.0f;                             // exp(realised log-return of my asset on the day after the decision)
   auto fetch = [&]() -> bool {                     // next backtest of this slot (dynamic: iteration counts differ)
@@ -171,16 +171,18 @@ backtest_lane_kernel(BacktestArgs A, int want) {
       s.sync();
       b = __shfl_sync(kFull, next_b[slot], 0);
       if (b >= A.B) return false;
-      if (A.phase != 2 || A.bt_status[b] == 2) break;                                  // resume pass: suspended backtests only
+      if (A.phase < 2 || A.bt_status[b] == 2) break;                                   // resume passes: suspended backtests only
       s.sync();                                                                        // everybody has read next_b
     }
-    if (A.phase == 2) {                                                                // carry on where the active-set kernel stopped
+    if (A.phase >= 2) {                                                                // carry on where the active-set kernel stopped
       const double* S = A.state + (size_t)b * A.state_ld;
       wc = s.valid ? S[s.tid] : 0.0;
       t = (int)S[N + 14];
+      t_in = t;
       if (s.tid == 0) book_load(books[slot], S + N);
       return true;
     }
+    t_in = -1;
     wc = s.valid ? 1.0 / (double)N : 0.0;                                              // backtest.py:161
     t = 0;
     if (s.tid == 0) {
@@ -207,7 +209,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
       for (;;) {
         if (uni(need_start) || uni(st == ST_RESTART)) {
           const bool restart = !need_start;                          // second attempt: same returns, same weights
-          if (uni(!restart && A.phase == 1 && t > 0)) {
+          if (uni(!restart && (A.phase == 1 || A.phase == 3) && t > 0 && t != t_in)) {
             // dense start of the active-set pipeline: once few assets are held, the backtest moves to the kernel that
             // solves reduced problems (one warp per problem)
             s.sync();
@@ -218,6 +220,7 @@ backtest_lane_kernel(BacktestArgs A, int want) {
               if (s.tid == 0) {
                 book_save(books[slot], t, S + N);
                 A.bt_status[b] = 1;
+                if (A.phase == 3) atomicSub(A.done_counter, 1);                        // it had been counted out when it was suspended
                 A.ready_ring[(unsigned)atomicAdd(A.queue_ctr + 1, 1) % (unsigned)A.B] = b;      // ready queue of the active-set kernel
               }
               __syncwarp();
@@ -769,7 +772,11 @@ static int launch_bt_lane(const BacktestArgs& A, int sm_count, cudaStream_t st) 
 // Active-set pipeline for problems of G > 1 warps (32 < N <= 512), three launches on one stream (no host synchronisation):
 //   phase 1  backtest_lane_kernel<H, G>: every backtest from the equal-weight start until few assets are held;
 //   active   backtest_active_kernel<H>: reduced solves, one warp per problem;
-//   phase 2  backtest_lane_kernel<H, G>: backtests the active-set kernel suspended (active set beyond 32 assets), to their end.
+//   phase 3  backtest_lane_kernel<H, G>: backtests the active-set kernel suspended (active set beyond 32 assets) run
+//            full-width until few assets are held again (at least one decision), then return to the ready queue;
+//   active   the reduced-solve kernel once more for those;
+//   phase 2  backtest_lane_kernel<H, G>: whatever was suspended a second time, to its end.
+// With nothing suspended the last three launches find no work (a few microseconds each).
 template <int H>
 static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   constexpr int P = ActiveSlots<H>::P;
