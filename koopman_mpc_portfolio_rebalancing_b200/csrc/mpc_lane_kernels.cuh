@@ -148,6 +148,35 @@ __device__ __forceinline__ void book_decision(SlotBook& k, const BacktestArgs& A
   }
 }
 
+// The portfolio step of one decision for my asset (backtest.py:175-217): executes the first trade of the plan held in s.w[0]
+// from the weight wc, returns the drifted weight (the new wc) and, in every thread, the turnover and the portfolio's return
+// of the day.  e_next = exp(realised log-return of my asset on the next day), float32 as the reference computes it.
+template <typename Ipm>
+__device__ __forceinline__ double portfolio_step(Ipm& s, const IpmOptions& opt, double wc, float e_next, bool market, double& turnover,
+                                                 double& port_ret) {
+  double wn = s.valid ? s.w[0] : 0.0;                                                // backtest.py:131
+  float r32 = 0.0f;
+  if (s.valid && market) r32 = __fsub_rn(e_next, 1.0f);                              // backtest.py:193
+  double v[3] = {fabs(wn - wc), wn * (double)r32, wc * (double)r32}, T[3];
+  s.sync();
+  s.template block_sum<3>(v, T);
+  turnover = T[0];
+  port_ret = market ? T[1] : 0.0;
+  if (opt.clip_first_trade && s.tau > 0.0 && turnover > s.tau) {
+    // An iterate accepted after the factorisation broke down next to the optimum (status optimal_inaccurate)
+    // can sit ~1e-5 outside the turnover cap, whose slack the iteration does not re-derive from w: pull the
+    // trade back onto the cap along its own direction (budget and sign constraints are kept).
+    const double sc = div_fast(s.tau, turnover);
+    wn = fma(sc, wn - wc, wc);
+    if (market) port_ret = fma(sc, T[1] - T[2], T[2]);
+    turnover = s.tau;
+  }
+  if (!market) return wn;
+  double denom = 1.0 + port_ret;
+  if (fabs(denom) < 1e-8) denom = 1e-8;
+  return div_fast(wn * (double)__fadd_rn(1.0f, r32), denom);                         // (1.0 + f32) stays f32
+}
+
 template <int H, int G, int P, bool FIX>
 __global__ void KMPC_LANE_BT_ATTR(32 * G * P)
 backtest_lane_kernel(BacktestArgs A, int want) {
@@ -246,29 +275,8 @@ backtest_lane_kernel(BacktestArgs A, int want) {
         if (uni(st < 0)) break;                                    // take a Newton step
         // ---- the decision is made: portfolio step (backtest.py:175-217) ---------------------------------------
         const bool market = (t + 1 < A.rows);
-        double wn = s.valid ? s.w[0] : 0.0;                                                // backtest.py:131
-        float r32 = 0.0f;
-        if (s.valid && market) r32 = __fsub_rn(e_next, 1.0f);                              // backtest.py:193
-        double v[3] = {fabs(wn - wc), wn * (double)r32, wc * (double)r32}, T[3];
-        s.sync();
-        s.template block_sum<3>(v, T);
-        double turnover = T[0];
-        double port_ret = market ? T[1] : 0.0;
-        if (opt.clip_first_trade && s.tau > 0.0 && turnover > s.tau) {
-          // An iterate accepted after the factorisation broke down next to the optimum (status optimal_inaccurate)
-          // can sit ~1e-5 outside the turnover cap, whose slack the iteration does not re-derive from w: pull the
-          // trade back onto the cap along its own direction (budget and sign constraints are kept).
-          const double sc = div_fast(s.tau, turnover);
-          wn = fma(sc, wn - wc, wc);
-          if (market) port_ret = fma(sc, T[1] - T[2], T[2]);
-          turnover = s.tau;
-        }
-        wc = wn;
-        if (market) {
-          double denom = 1.0 + port_ret;
-          if (fabs(denom) < 1e-8) denom = 1e-8;
-          wc = div_fast(wn * (double)__fadd_rn(1.0f, r32), denom);                         // (1.0 + f32) stays f32
-        }
+        double turnover, port_ret;
+        wc = portfolio_step(s, opt, wc, e_next, market, turnover, port_ret);
         t += A.rebalance_freq;
         const bool last = (t >= A.n_steps);
         if (s.tid == 0) {
@@ -655,26 +663,8 @@ backtest_active_kernel(BacktestArgs A, int want) {
         }
         // ---- the decision is made: portfolio step (backtest.py:175-217), as in backtest_lane_kernel -------------------
         const bool market = (t + 1 < A.rows);
-        double wn = s.valid ? s.w[0] : 0.0;                                                // backtest.py:131
-        float r32 = 0.0f;
-        if (s.valid && market) r32 = __fsub_rn(e_next, 1.0f);                              // backtest.py:193
-        double v[3] = {fabs(wn - wc), wn * (double)r32, wc * (double)r32}, T[3];
-        s.sync();
-        s.template block_sum<3>(v, T);
-        double turnover = T[0];
-        double port_ret = market ? T[1] : 0.0;
-        if (opt.clip_first_trade && s.tau > 0.0 && turnover > s.tau) {
-          const double sc = div_fast(s.tau, turnover);
-          wn = fma(sc, wn - wc, wc);
-          if (market) port_ret = fma(sc, T[1] - T[2], T[2]);
-          turnover = s.tau;
-        }
-        wc = wn;
-        if (market) {
-          double denom = 1.0 + port_ret;
-          if (fabs(denom) < 1e-8) denom = 1e-8;
-          wc = div_fast(wn * (double)__fadd_rn(1.0f, r32), denom);                         // (1.0 + f32) stays f32
-        }
+        double turnover, port_ret;
+        wc = portfolio_step(s, opt, wc, e_next, market, turnover, port_ret);
         if (s.valid) wfull[a] = wc;
         t += A.rebalance_freq;
         const bool last = (t >= A.n_steps);
