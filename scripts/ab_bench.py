@@ -1,6 +1,6 @@
 """A/B timing of tuning builds of the lane MPC kernel (development tool, not product code).
 
-  python scripts/ab_bench.py build <name> "<-D flags>"     # here (no GPU): build_ab/libkmpc_<name>.so, (H,G) = (5,2) only
+  python scripts/ab_bench.py build <name> "<-D flags>"     # here (no GPU): build_ab/libkmpc_<name>.so, (H,G) = (5,1) + (5,2) only
   python scripts/ab_bench.py run [steps]                    # on the GPU box: time every build_ab/*.so + the product lib
   python scripts/ab_bench.py one <lib.so> [steps]           # one library (child process of `run`)
 
@@ -62,7 +62,7 @@ def main():
         os.makedirs(AB, exist_ok=True)
         name, defs = sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
         gdefs = sys.argv[4] if len(sys.argv) > 4 else ""          # -D flags for the tcgen05 GEMM units
-        kb.build(verbose=False, lib=os.path.join(AB, f"libkmpc_{name}.so"), lane_variants=[(5, 2)], lane_defs=defs, gemm_defs=gdefs)
+        kb.build(verbose=False, lib=os.path.join(AB, f"libkmpc_{name}.so"), lane_variants=[(5, 1), (5, 2)], lane_defs=defs, gemm_defs=gdefs)
         kb.build(verbose=False)                     # restore the generated variant list of the product build
         print("built", name, defs)
     elif mode == "run":
