@@ -361,43 +361,104 @@ constexpr double kVerifyTol = 1e-8;     // on the subgradient bound; the duals o
 #ifndef KMPC_ACTIVE_LOC
 #define KMPC_ACTIVE_LOC(H) false
 #endif
-template <int H> struct ActiveSlots { static constexpr int P = (H > 5 && !KMPC_ACTIVE_LOC(H)) ? 4 : 8; };
+// Slots per block of the reduced-solve kernel.  G = 1: one warp per problem (eight problems per SM; H = 10 with the sweep
+// factors in shared memory: four).  G = 4 ("wide": universes beyond 128 assets, where the full-width solver needs 16 warps
+// per problem): four warps per problem, two problems per SM, the solver in the layout of backtest_lane_kernel<H, 4>.
+template <int H, int G = 1> struct ActiveSlots {
+  static constexpr int P = (G > 1) ? 2 : ((H > 5 && !KMPC_ACTIVE_LOC(H)) ? 4 : 8);
+  static constexpr bool LOC = (G > 1) ? (H > 5) : KMPC_ACTIVE_LOC(H);
+};
 #ifndef KMPC_ACTIVE_SYNC_EVERY
 #define KMPC_ACTIVE_SYNC_EVERY 4        // block barrier (and exit vote) every n-th trip of the active-set kernel
 #endif
 
-template <int H, int P, bool FIX, int NQ>
-__global__ void __launch_bounds__(32 * P, 1)
+template <int H, int P, bool FIX, int NQ, int G = 1>
+__global__ void __launch_bounds__(32 * G * P, 1)
 backtest_active_kernel(BacktestArgs A, int want) {
-  using Ipm = LaneIpm<H, 1, KMPC_ACTIVE_LOC(H), FIX>;
-  constexpr int MAXQ = NQ;                         // assets per lane in passes over the whole universe (N <= 32 NQ)
+  using Ipm = LaneIpm<H, G, ActiveSlots<H, G>::LOC, FIX>;
+  constexpr int NT = 32 * G;                       // threads (= active assets at most) per problem
+  constexpr int MAXQ = NQ;                         // assets per thread in passes over the whole universe (N <= NT NQ)
   extern __shared__ double smem[];
   if (want >= 0 && *A.fix_flag != want) return;
   __shared__ SlotBook books[P];
-  const int slot = __shfl_sync(kFull, (int)threadIdx.x / 32, 0);
+  __shared__ int xch[P][2][8];                     // G > 1: exchange between the warps of a slot (two alternating rows)
+  const int slot = __shfl_sync(kFull, (int)threadIdx.x / NT, 0);
   const int lane = (int)threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   Ipm s;
-  s.bind(smem + (size_t)slot * Ipm::SMEM_DOUBLES, 32, slot);
-  double* wfull = smem + (size_t)P * Ipm::SMEM_DOUBLES + (size_t)slot * (32 * MAXQ);       // weights of all N assets
-  int* sid = reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + slot * 32;   // lane -> asset
+  s.bind(smem + (size_t)slot * Ipm::SMEM_DOUBLES, NT, slot);
+  const int tid = s.tid;                           // thread of the problem: [0, NT)
+  double* wfull = smem + (size_t)P * Ipm::SMEM_DOUBLES + (size_t)slot * (NT * MAXQ);       // weights of all N assets
+  int* sid = reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + NT * MAXQ)) + slot * NT;   // thread -> asset
   const int N = A.N;
   // the decision's forecasts [H][N] and the next day's realised returns [N], staged once per decision: the selection, the
   // solver's inputs and the verification all read them, and the global loads of a decision are in flight together
   // (large universes — config 3: 11 x 500 floats per slot — read them from global memory / L2 instead)
-  constexpr bool staged = NQ <= 4;                 // N <= 128 (the launcher picks NQ from N)
-  float* ystage = reinterpret_cast<float*>(reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + 32 * MAXQ)) + P * 32) +
+  constexpr bool staged = (G == 1) && NQ <= 4;     // N <= 128 (the launcher picks NQ from N)
+  float* ystage = reinterpret_cast<float*>(reinterpret_cast<int*>(smem + (size_t)P * (Ipm::SMEM_DOUBLES + NT * MAXQ)) + P * NT) +
                   (size_t)slot * (H + 1) * N;
   const float* ysrc = ystage;                      // [H][N] forecasts of the decision (staged: fixed, in shared memory)
   const float* rnext = ystage + H * N;             // [N] next day's realised log-returns
   const IpmOptions& opt = A.opt;
   int b = 0, t = 0, count = 0, a = 0, extra_it = 0, seg_left = 0;
-  unsigned member = 0;                             // bit q: asset lane + 32 q is in S
+  unsigned member = 0;                             // bit q: asset tid + NT q is in S
   double wc = 0.0;
   float e_next = 1.0f;
   const float* yrow = nullptr;
   size_t rb = 0;
   double lam_b = 0.0, tau_b = 0.0;
+
+  // ---- collectives over the threads of the slot (G = 1: the warp; G > 1: through xch and the slot's named barrier; every
+  //      thread of the slot calls them in the same order, from slot-uniform control flow) -----------------------------------
+  int xsel = 0;
+  auto slot_sync = [&]() { s.sync(); };
+  auto slot_bcast0 = [&](int v) -> int {           // the value of thread 0 of the slot
+    if (G == 1) return __shfl_sync(kFull, v, 0);
+    xsel ^= 1;
+    if (tid == 0) xch[slot][xsel][0] = v;
+    s.sync();
+    return xch[slot][xsel][0];
+  };
+  auto slot_any = [&](bool c) -> bool {
+    const bool w = __any_sync(kFull, c) != 0;
+    if (G == 1) return w;
+    xsel ^= 1;
+    if (lane == 0) xch[slot][xsel][s.warp] = w ? 1 : 0;
+    s.sync();
+    int r = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) r |= xch[slot][xsel][g];
+    return r != 0;
+  };
+  auto slot_maxf = [&](float m) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if (G == 1) return m;
+    xsel ^= 1;
+    if (lane == 0) xch[slot][xsel][s.warp] = __float_as_int(m);
+    s.sync();
+    float r = __int_as_float(xch[slot][xsel][0]);
+#pragma unroll
+    for (int g = 1; g < G; ++g) r = fmaxf(r, __int_as_float(xch[slot][xsel][g]));
+    return r;
+  };
+  // (exclusive prefix over the slot, total) of a per-thread count
+  auto slot_scan = [&](int c, int& total) -> int {
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+    int base = 0;
+    total = __shfl_sync(kFull, inc, 31);
+    if (G > 1) {
+      xsel ^= 1;
+      if (lane == 31) xch[slot][xsel][s.warp] = inc;
+      s.sync();
+      total = 0;
+#pragma unroll
+      for (int g = 0; g < G; ++g) { const int v = xch[slot][xsel][g]; if (g < s.warp) base += v; total += v; }
+    }
+    return base + inc - c;
+  };
 
   // Work items are SEGMENTS of backtests (A.seg decisions): a slot that has run a segment saves the backtest's state and
   // appends it to the ready queue again, then takes the backtest at the head of the queue.  Whole backtests as items leave
@@ -410,7 +471,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
   // returns 1: a backtest is loaded; 0: none ready right now (the others are running); -1: every backtest has left the kernel
   auto fetch = [&]() -> int {
     int got = -1;
-    if (lane == 0) {
+    if (tid == 0) {
       volatile int* head = A.queue_ctr;
       volatile int* tail = A.queue_ctr + 1;
 #pragma unroll 1
@@ -430,16 +491,16 @@ backtest_active_kernel(BacktestArgs A, int want) {
         }
       }
     }
-    got = __shfl_sync(kFull, got, 0);
+    got = slot_bcast0(got);
     if (got == -2) return -1;
     if (got < 0) return 0;
     b = got;
     __threadfence();                                 // the state below was written by the backtest's previous slot
     const double* S = A.state + (size_t)b * A.state_ld;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) wfull[i] = __ldcg(S + i); }
+    for (int q = 0; q < NQ; ++q) { const int i = tid + NT * q; if (i < N) wfull[i] = __ldcg(S + i); }
     t = (int)__ldcg(S + N + 14);
-    if (lane == 0) {
+    if (tid == 0) {
       double bk[14];
 #pragma unroll
       for (int i = 0; i < 14; ++i) bk[i] = __ldcg(S + N + i);
@@ -448,22 +509,22 @@ backtest_active_kernel(BacktestArgs A, int want) {
     rb = (size_t)(A.realized_index ? A.realized_index[b] : b) * A.realized_stride;
     lam_b = A.lam ? A.lam[b] : A.lam0; tau_b = A.tau ? A.tau[b] : A.tau0;
     seg_left = (A.seg > 0) ? A.seg : 0x7fffffff;
-    __syncwarp();
+    slot_sync();
     return 1;
   };
   // gives the backtest up: status 1 = ready for its next segment, 2 = for the full-width kernel (both with the state saved),
   // 3 = finished
   auto release = [&](int status) {
-    __syncwarp();
+    slot_sync();
     if (status != 3) {
       double* S = A.state + (size_t)b * A.state_ld;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) S[i] = wfull[i]; }
-      if (lane == 0) book_save(books[slot], t, S + N);
+      for (int q = 0; q < NQ; ++q) { const int i = tid + NT * q; if (i < N) S[i] = wfull[i]; }
+      if (tid == 0) book_save(books[slot], t, S + N);
     }
     __threadfence();
-    __syncwarp();
-    if (lane == 0) {
+    slot_sync();
+    if (tid == 0) {
       if (status == 1) {
         const int pos = atomicAdd(A.queue_ctr + 1, 1);
         atomicExch(A.ready_ring + (unsigned)pos % (unsigned)A.B, b);
@@ -473,32 +534,46 @@ backtest_active_kernel(BacktestArgs A, int want) {
       }
     }
   };
-  // my lane's problem data for the current S, then the starting point
+  // my thread's problem data for the current S, then the starting point
   auto start_solve = [&]() -> int {
-    __syncwarp();
-    s.valid = lane < count;
-    a = s.valid ? sid[lane] : 0;
+    slot_sync();
+    s.valid = tid < count;
+    a = s.valid ? sid[tid] : 0;
     wc = s.valid ? wfull[a] : 0.0;
     const float y_next = (s.valid && t + 1 < A.rows) ? rnext[a] : 0.0f;
     e_next = s.load_returns(ysrc, (size_t)N, y_next, a);                                  // mpc.py:55
     return s.begin(wc, count, lam_b, tau_b, false, opt, false);
   };
-  // adds the assets flagged in `add` (bit q of my lane) to S.  must = true: all of them, false if S would exceed the warp;
+  // adds the assets flagged in `add` (bit q of my thread) to S.  must = true: all of them, false if S would exceed the slot;
   // must = false (candidates): as many as fit — an asset left out is still subject to the optimality check afterwards
   auto grow = [&](unsigned add, bool must) -> bool {
-    int base = count;
+    if (G == 1) {
+      int base = count;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) base += __popc(__ballot_sync(kFull, (add >> q) & 1u));
-    if (must && base > 32) return false;
-    base = count;
+      for (int q = 0; q < NQ; ++q) base += __popc(__ballot_sync(kFull, (add >> q) & 1u));
+      if (must && base > 32) return false;
+      base = count;
 #pragma unroll 1
-    for (int q = 0; q < NQ; ++q) {
-      const unsigned bal = __ballot_sync(kFull, (add >> q) & 1u);
-      const int pos = base + __popc(bal & lt_mask);
-      if (((add >> q) & 1u) && pos < 32) { sid[pos] = lane + 32 * q; member |= 1u << q; }
-      base += __popc(bal);
+      for (int q = 0; q < NQ; ++q) {
+        const unsigned bal = __ballot_sync(kFull, (add >> q) & 1u);
+        const int pos = base + __popc(bal & lt_mask);
+        if (((add >> q) & 1u) && pos < 32) { sid[pos] = lane + 32 * q; member |= 1u << q; }
+        base += __popc(bal);
+      }
+      count = base < 32 ? base : 32;
+      return true;
     }
-    count = base < 32 ? base : 32;
+    int total;
+    int pos = count + slot_scan(__popc(add & ((1u << NQ) - 1u)), total);
+    if (must && count + total > NT) return false;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if ((add >> q) & 1u) {
+        if (pos < NT) { sid[pos] = tid + NT * q; member |= 1u << q; }
+        ++pos;
+      }
+    }
+    count = (count + total < NT) ? count + total : NT;
     return true;
   };
 
@@ -506,7 +581,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
   bool active = have == 1, finished = have < 0;    // active: a backtest is loaded; finished: nothing left for this kernel
   int need_start = 1;                              // 1: a new decision (choose S), 2: the same decision on a grown S, 0: iterating
   unsigned idle_trips = 0;
-  unsigned pending = 0, cand = 0;                  // assets that join S at the next start / candidates (bit q of my lane)
+  unsigned pending = 0, cand = 0;                  // assets that join S at the next start / candidates (bit q of my thread)
   int st = -1;
   __syncthreads();
 #pragma unroll 1
@@ -518,7 +593,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
       if (!active && !finished) {
         __nanosleep(500);                            // nothing to do until a neighbour releases a backtest
         if (++idle_trips > (1u << 28)) {             // minutes of idling: trap instead of hanging the GPU
-          if (lane == 0) printf("kmpc active-set kernel: slot idle for 2^28 trips with unfinished backtests\n");
+          if (tid == 0) printf("kmpc active-set kernel: slot idle for 2^28 trips with unfinished backtests\n");
           __trap();
         }
       }
@@ -543,15 +618,16 @@ backtest_active_kernel(BacktestArgs A, int want) {
                 __syncwarp();
               } else {
                 ysrc = yrow; rnext = rrow;
+                slot_sync();                           // the weights the previous decision left in wfull (written per asset)
               }
             }
 #pragma unroll 4
-            for (int i = lane; i < H * N; i += 32)
+            for (int i = tid; i < H * N; i += NT)
               if (!(fabsf(ysrc[i]) < 80.0f)) bad = true;               // exp() may leave the positive normal floats: looked at below
             pending = 0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-              const int i = lane + 32 * q;
+              const int i = tid + NT * q;
               if (i < N) { if (wfull[i] > kHeldThr) pending |= 1u << q; else wfull[i] = 0.0; }
             }
             cand = 0;
@@ -561,7 +637,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
               float v[NQ];
 #pragma unroll
               for (int q = 0; q < NQ; ++q) {
-                const int i = lane + 32 * q;
+                const int i = tid + NT * q;
                 v[q] = (i < N) ? ysrc[k * N + i] : -CUDART_INF_F;
               }
 #pragma unroll 1
@@ -569,9 +645,8 @@ backtest_active_kernel(BacktestArgs A, int want) {
                 float m = v[0];
 #pragma unroll
                 for (int q = 1; q < NQ; ++q) m = fmaxf(m, v[q]);
-                float wm = m;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(kFull, wm, o));
+                const float wm = slot_maxf(m);
+                // (G > 1: a tie between two warps makes both of their assets candidates, which is as good)
                 const unsigned bal = __ballot_sync(kFull, m == wm && m > -CUDART_INF_F);
                 if (bal && lane == __ffs(bal) - 1) {
                   bool done = false;
@@ -584,7 +659,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
           }
           const bool fits = grow(pending, true);     // the held assets (or the assets that failed the check) must all fit
           if (uni(fits && need_start == 1)) grow(cand & ~member, false);
-          if (uni(!fits)) {                          // more than a warp of active assets: the full-width kernel takes over
+          if (uni(!fits)) {                          // more active assets than threads: the full-width kernel takes over
             release(2);
             need_start = 1; st = -1;
             have = fetch();
@@ -593,15 +668,15 @@ backtest_active_kernel(BacktestArgs A, int want) {
             continue;
           }
           st = start_solve();
-          if (uni(__any_sync(kFull, bad))) {
+          if (uni(slot_any(bad))) {
             // a suspicious forecast somewhere in the universe: would the full solver's screening refuse the decision?
             bool refuse = false;
 #pragma unroll 1
-            for (int i = lane; i < H * N; i += 32) {
+            for (int i = tid; i < H * N; i += NT) {
               const float r = __double2float_rn(exp((double)ysrc[i]));
               if (!(isfinite(r) && r > 0.0f)) refuse = true;
             }
-            if (uni(__any_sync(kFull, refuse))) {    // hold the weights, as the full solver does
+            if (uni(slot_any(refuse))) {             // hold the weights, as the full solver does
 #pragma unroll
               for (int k = 0; k < H; ++k) s.w[k] = wc;
               s.it_ = 0;
@@ -630,7 +705,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
           unsigned viol = 0;
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
-            const int i = lane + 32 * q;
+            const int i = tid + NT * q;
             if (i < N && !((member >> q) & 1u)) {
               float yv[H];
               bool safe = true;
@@ -654,7 +729,7 @@ backtest_active_kernel(BacktestArgs A, int want) {
           { const int anyv = __any_sync(kFull, viol != 0);
             if (lane == 0 && blockIdx.x == 0) printf("AS slot %d b %d t %d st %d it %d viol %d\n", slot, b, t, st, s.it_, anyv); }
 #endif
-          if (uni(__any_sync(kFull, viol != 0))) {                      // somebody wants in: solve again on the larger set
+          if (uni(slot_any(viol != 0))) {                               // somebody wants in: solve again on the larger set
             extra_it += s.it_;
             pending = viol;
             need_start = 2; st = -1;
@@ -668,15 +743,15 @@ backtest_active_kernel(BacktestArgs A, int want) {
         if (s.valid) wfull[a] = wc;
         t += A.rebalance_freq;
         const bool last = (t >= A.n_steps);
-        if (lane == 0) {
+        if (tid == 0) {
           book_decision(books[slot], A, b, st, s.it_ + extra_it, turnover, port_ret, market, last);
         }
         need_start = 1; st = -1;
         if (uni(last)) {
-          __syncwarp();
+          slot_sync();
           if (A.final_weights) {
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) { const int i = lane + 32 * q; if (i < N) A.final_weights[(size_t)b * N + i] = wfull[i]; }
+            for (int q = 0; q < NQ; ++q) { const int i = tid + NT * q; if (i < N) A.final_weights[(size_t)b * N + i] = wfull[i]; }
           }
         }
         if (uni(last || --seg_left == 0)) {          // the backtest is finished, or its segment is: take the next ready one
@@ -775,10 +850,10 @@ static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st
   const int want = (A.B + P - 1) / P;
   auto go = [&](auto nq) {
     constexpr int NQ = decltype(nq)::value;
-    // per slot: the solver's slice, the weights of the whole universe, the lane -> asset table and (N <= 128) the staged forecasts
+    // per slot: the solver's slice, the weights of the whole universe, the lane -> asset table and the staged forecasts
     const size_t fixed = (size_t)P * (Ipm::SMEM_DOUBLES + 32 * NQ) * sizeof(double) + (size_t)P * 32 * sizeof(int);
-    const size_t smem_max = fixed + (NQ <= 4 ? (size_t)P * (H + 1) * 32 * NQ * sizeof(float) : 0);
-    const size_t smem = fixed + (A.N <= 128 ? (size_t)P * (H + 1) * A.N * sizeof(float) : 0);
+    const size_t smem_max = fixed + (size_t)P * (H + 1) * 32 * NQ * sizeof(float);
+    const size_t smem = fixed + (size_t)P * (H + 1) * A.N * sizeof(float);
     static PerDeviceInt t0, t1;
     const int bps0 = t0.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, false, NQ>, 32 * P, smem_max); });
     const int bps1 = t1.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, true, NQ>, 32 * P, smem_max); });
@@ -788,7 +863,27 @@ static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st
   };
   if (A.N <= 64) go(std::integral_constant<int, 2>{});
   else if (A.N <= 128) go(std::integral_constant<int, 4>{});
-  else go(std::integral_constant<int, 16>{});
+  else return -2;                                   // larger universes take the wide kernel (launch_bt_active_wide)
+  return (int)cudaGetLastError();
+}
+
+// The reduced-solve kernel for universes of 129..512 assets: four warps per problem (up to 128 active assets), forecasts read
+// from global memory / L2.  Compiled with the (H, 4) variants of the horizons that have a 16-warp full-width kernel.
+constexpr int kWideG = 4, kWideNQ = 4;
+template <int H>
+static int launch_bt_active_wide(const BacktestArgs& A, int sm_count, cudaStream_t st) {
+  constexpr int G = kWideG, NQ = kWideNQ, P = ActiveSlots<H, G>::P;
+  using Ipm = LaneIpm<H, G, ActiveSlots<H, G>::LOC, false>;
+  if (A.N > 32 * G * NQ) return -2;
+  const int plan = lane_fix_plan(A.lam, A.tau, A.lam0, A.tau0, A.allow_short, A.opt.dual_init, A.B, A.fix_flag, st);
+  const int want = (A.B + P - 1) / P;
+  const size_t smem = (size_t)P * (Ipm::SMEM_DOUBLES + 32 * G * NQ) * sizeof(double) + (size_t)P * 32 * G * sizeof(int);
+  static PerDeviceInt t0, t1;
+  const int bps0 = t0.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, false, NQ, G>, 32 * G * P, smem); });
+  const int bps1 = t1.get([&] { return lane_blocks_per_sm(backtest_active_kernel<H, P, true, NQ, G>, 32 * G * P, smem); });
+  auto nblocks = [&](int bps) { int b = want < sm_count * bps ? want : sm_count * bps; return b < 1 ? 1 : b; };
+  if (plan != 0) backtest_active_kernel<H, P, true, NQ, G><<<nblocks(bps1), 32 * G * P, smem, st>>>(A, plan == 2 ? 1 : -1);
+  if (plan != 1) backtest_active_kernel<H, P, false, NQ, G><<<nblocks(bps0), 32 * G * P, smem, st>>>(A, plan == 2 ? 0 : -1);
   return (int)cudaGetLastError();
 }
 

@@ -151,7 +151,7 @@ def test_persistent_kernel_is_schedule_independent(N, H, mixed):
     assert np.array_equal(h, full_h[perm]) and np.array_equal(m, full_m[perm])
 
 
-@pytest.mark.parametrize("N,H", [(50, 5), (100, 5), (40, 3), (140, 10)])
+@pytest.mark.parametrize("N,H", [(50, 5), (100, 5), (40, 3), (140, 10), (300, 5)])
 def test_active_set_pipeline_matches_full_solver(N, H):
     """KMPC_PARAM_ACTIVE_SET (default on): once a backtest's portfolio has concentrated, the persistent kernel hands it to
     backtest_active_kernel, which solves every decision on the held assets + the best forecasts of each stage (one warp per
@@ -160,8 +160,9 @@ def test_active_set_pipeline_matches_full_solver(N, H):
     per-asset drifts (so that portfolios do concentrate), mixed per-backtest costs and caps: every decision optimal in
     both, histories equal at the end-to-end bar, fewer Newton steps.  Mode 2 starts every set from the held assets alone,
     so that the assets of the plan have to come in through the check-and-repair path: same histories, more solves.
-    (140, 10): the config-3 route — full-width kernel of 16 warps with thread-private state for the dense start, one-warp
-    H = 10 problems afterwards, forecasts read from global memory instead of the shared-memory stage."""
+    (140, 10), (300, 5): the config-3 route — full-width kernel of 16 warps for the dense start, then the WIDE reduced-solve
+    kernel (four warps per problem, up to 128 active assets, hand-over at 100 / 110 held assets), forecasts read from global
+    memory instead of the shared-memory stage."""
     import torch
     from koopman_mpc_portfolio_rebalancing_b200 import _capi, backtest as bt
     B, rows = 96, 70
