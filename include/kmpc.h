@@ -82,7 +82,7 @@ enum {
   KMPC_PARAM_TOL = 6,
   /* 1 [default]: kmpc_backtest_run solves REDUCED problems once a backtest's portfolio has concentrated (32 < N <= 512,
    * H <= 5 or H = 10, long-only): only the held assets and the best forecasts of each stage enter the interior-point solve (one warp
-   * per problem instead of two or four), and the optimality conditions of every excluded asset are then checked
+   * per problem instead of two or four; eight instead of sixteen for universes beyond 128 assets), and the optimality conditions of every excluded asset are then checked
    * against the duals of the reduced solution (an asset that fails joins the set and the problem is solved again), so
    * the plan is an optimum of the FULL program of mpc.py:49-104.  0: every decision solves all N assets.  2 (test hook):
  * as 1 but the set starts from the held assets alone, so that the check-and-repair path does the selecting.  3 (tuning):

@@ -20,9 +20,10 @@ int KMPC_CAT(launch_bta, KMPC_H, KMPC_G)(const BacktestArgs& A, int sm_count, cu
 }
 #endif
 #if KMPC_G == 4 && (KMPC_H == 5 || KMPC_H == 10)
-// the wide active-set kernel (four warps per reduced problem, universes beyond 128 assets) lives with the four-warp variant
+// the wide active-set kernel (KMPC_WIDE_G warps per reduced problem, universes beyond 128 assets) lives with the four-warp variant
 int KMPC_CAT(launch_btaw, KMPC_H, KMPC_G)(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   return launch_bt_active_wide<KMPC_H>(A, sm_count, st);
 }
+int KMPC_CAT(wide_threads, KMPC_H, KMPC_G)() { return 32 * kWideG; }      // threads = active assets at most of a wide problem
 #endif
 }  // namespace kmpc

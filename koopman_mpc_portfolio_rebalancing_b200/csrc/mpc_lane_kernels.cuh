@@ -362,10 +362,11 @@ constexpr double kVerifyTol = 1e-8;     // on the subgradient bound; the duals o
 #define KMPC_ACTIVE_LOC(H) false
 #endif
 // Slots per block of the reduced-solve kernel.  G = 1: one warp per problem (eight problems per SM; H = 10 with the sweep
-// factors in shared memory: four).  G = 4 ("wide": universes beyond 128 assets, where the full-width solver needs 16 warps
-// per problem): four warps per problem, two problems per SM, the solver in the layout of backtest_lane_kernel<H, 4>.
+// factors in shared memory: four).  G > 1 ("wide": universes beyond 128 assets, where the full-width solver needs 16 warps
+// per problem at 128 registers per thread): KMPC_WIDE_G warps per problem at the full register budget, 8 / G problems per SM,
+// the solver in the layout of backtest_lane_kernel<H, G> (H = 10: thread-private sweep factors).
 template <int H, int G = 1> struct ActiveSlots {
-  static constexpr int P = (G > 1) ? 2 : ((H > 5 && !KMPC_ACTIVE_LOC(H)) ? 4 : 8);
+  static constexpr int P = (G > 1) ? (8 / G) : ((H > 5 && !KMPC_ACTIVE_LOC(H)) ? 4 : 8);
   static constexpr bool LOC = (G > 1) ? (H > 5) : KMPC_ACTIVE_LOC(H);
 };
 #ifndef KMPC_ACTIVE_SYNC_EVERY
@@ -867,9 +868,14 @@ static int launch_bt_active(const BacktestArgs& A, int sm_count, cudaStream_t st
   return (int)cudaGetLastError();
 }
 
-// The reduced-solve kernel for universes of 129..512 assets: four warps per problem (up to 128 active assets), forecasts read
-// from global memory / L2.  Compiled with the (H, 4) variants of the horizons that have a 16-warp full-width kernel.
-constexpr int kWideG = 4, kWideNQ = 4;
+// The reduced-solve kernel for universes of 129..512 assets: KMPC_WIDE_G warps per problem (up to 32 G active assets), forecasts
+// read from global memory / L2.  Compiled with the (H, 4) variants of the horizons that have a 16-warp full-width kernel.
+// Measured per Newton iteration and problem at H = 10, one problem per SM (scripts/lane_latency.py): 57-59 us for 32, 64 and
+// 128 assets on 1, 2, 4 warps; 197 / 215 us for 256 / 500 assets on the 16 warps of the full-width kernel.
+#ifndef KMPC_WIDE_G
+#define KMPC_WIDE_G 8     // config 3 (148 backtests x 500 assets, H = 10): 4 warps 516 ms, 8 warps 371 ms per pass (one-warp route: 1010 ms)
+#endif
+constexpr int kWideG = KMPC_WIDE_G, kWideNQ = 16 / KMPC_WIDE_G;
 template <int H>
 static int launch_bt_active_wide(const BacktestArgs& A, int sm_count, cudaStream_t st) {
   constexpr int G = kWideG, NQ = kWideNQ, P = ActiveSlots<H, G>::P;

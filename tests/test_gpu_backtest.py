@@ -161,7 +161,7 @@ def test_active_set_pipeline_matches_full_solver(N, H):
     both, histories equal at the end-to-end bar, fewer Newton steps.  Mode 2 starts every set from the held assets alone,
     so that the assets of the plan have to come in through the check-and-repair path: same histories, more solves.
     (140, 10), (300, 5): the config-3 route — full-width kernel of 16 warps for the dense start, then the WIDE reduced-solve
-    kernel (four warps per problem, up to 128 active assets, hand-over at 100 / 110 held assets), forecasts read from global
+    kernel (eight warps per problem, up to 256 active assets, hand-over at 228 / 238 held assets), forecasts read from global
     memory instead of the shared-memory stage."""
     import torch
     from koopman_mpc_portfolio_rebalancing_b200 import _capi, backtest as bt
