@@ -1,6 +1,6 @@
 """Stress of the active-set backtest pipeline against the full-width kernel over shapes and parameters (development tool):
 every case must finish (run it under `timeout`), end with the same statuses, and agree on the histories.
-  python scripts/as_stress.py [seed]"""
+  python scripts/as_stress.py [seed] [wide]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,17 +9,19 @@ sys.path.insert(0, ROOT)
 def main():
     import numpy as np, torch
     from koopman_mpc_portfolio_rebalancing_b200 import _capi, backtest as bt
-    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    wide = "wide" in sys.argv[1:]                   # universes beyond 128 assets: 16-warp dense start + wide reduced problems
+    args = [a for a in sys.argv[1:] if a != "wide"]
+    seed = int(args[0]) if args else 0
     rng = np.random.default_rng(seed)
     h = _capi.Handle.get(0)
     worst = 0.0
     cases = []
-    for N in (33, 50, 64, 65, 100, 128):
-        for H in (1, 2, 3, 4, 5):
+    for N in ((129, 200, 256, 257, 400, 512) if wide else (33, 50, 64, 65, 100, 128)):
+        for H in ((5, 10) if wide else (1, 2, 3, 4, 5)):
             cases.append((N, H))
     for ci, (N, H) in enumerate(cases):
-        B = int(rng.choice([1, 3, 40, 333, 1500]))
-        rows = int(rng.choice([8, 30, 90]))
+        B = int(rng.choice([1, 3, 40, 150] if wide else [1, 3, 40, 333, 1500]))
+        rows = int(rng.choice([14, 30] if wide else [8, 30, 90]))
         freq = int(rng.choice([1, 1, 2, 5]))
         ns = rows - 1 - H
         if ns < 1:
