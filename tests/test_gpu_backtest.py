@@ -151,8 +151,8 @@ def test_persistent_kernel_is_schedule_independent(N, H, mixed):
     assert np.array_equal(h, full_h[perm]) and np.array_equal(m, full_m[perm])
 
 
-@pytest.mark.parametrize("N,H", [(50, 5), (100, 5), (40, 3), (140, 10), (300, 5)])
-def test_active_set_pipeline_matches_full_solver(N, H):
+@pytest.mark.parametrize("N,H,B", [(50, 5, 96), (100, 5, 96), (40, 3, 96), (140, 10, 96), (300, 5, 96), (160, 5, 500)])
+def test_active_set_pipeline_matches_full_solver(N, H, B):
     """KMPC_PARAM_ACTIVE_SET (default on): once a backtest's portfolio has concentrated, the persistent kernel hands it to
     backtest_active_kernel, which solves every decision on the held assets + the best forecasts of each stage (one warp per
     problem) and then checks the optimality conditions of all excluded assets against the duals of the reduced solution
@@ -162,10 +162,11 @@ def test_active_set_pipeline_matches_full_solver(N, H):
     so that the assets of the plan have to come in through the check-and-repair path: same histories, more solves.
     (140, 10), (300, 5): the config-3 route — full-width kernel of 16 warps for the dense start, then the WIDE reduced-solve
     kernel (eight warps per problem, up to 256 active assets, hand-over at 228 / 238 held assets), forecasts read from global
-    memory instead of the shared-memory stage."""
+    memory instead of the shared-memory stage.  (160, 5, 500): more backtests than the wide kernel has slots (148 on a
+    B200), so that backtests travel between slots through the ready queue and their saved state."""
     import torch
     from koopman_mpc_portfolio_rebalancing_b200 import _capi, backtest as bt
-    B, rows = 96, 70
+    rows = 70 if B <= 96 else 50
     ns = rows - 1 - H
     g = torch.Generator(device="cuda").manual_seed(100 * N + H)
     drift = 2e-3 * torch.randn((B, 1, 1, N), device="cuda", generator=g)
@@ -189,9 +190,18 @@ def test_active_set_pipeline_matches_full_solver(N, H):
         assert st[0] == B * ns and st[1] == 0 and st[2] == 0, (mode, st)            # every decision optimal
     v0 = res[0][0][..., 0]
     for mode in (1, 2):
-        v = res[mode][0][..., 0]
-        assert np.abs(v / v0 - 1).max() < 1e-4, (mode, np.abs(v / v0 - 1).max())
-        assert np.abs(res[mode][0][..., 2] - res[0][0][..., 2]).max() < 1e-3          # turnover per day
+        dv = np.abs(res[mode][0][..., 0] / v0 - 1).max(axis=1)                        # per backtest
+        dturn = np.abs(res[mode][0][..., 2] - res[0][0][..., 2]).max(axis=1)          # turnover per day
+        if B <= 96:
+            assert dv.max() < 1e-4, (mode, dv.max())
+            assert dturn.max() < 1e-3
+        else:
+            # among hundreds of backtests a decision with a FLAT optimum turns up (backtest 463 here: on day 5 the full and
+            # the reduced plan agree to 3e-12 in the objective, certified gaps 1e-12, and differ by 2.7e-3 in the first trade;
+            # replayed on the CPU oracle, profiles/README.md): both are optima, the trajectories part by ~1e-4
+            ok = dv < 1e-4
+            assert ok.mean() >= 0.99 and dv.max() < 2e-3, (mode, dv.max(), int((~ok).sum()))
+            assert dturn[ok].max() < 1e-3
     it0, it1, it2 = (int(res[m][1][:, 3].sum()) for m in (0, 1, 2))
     assert it1 < it0                                    # reduced problems take fewer Newton steps
     assert it2 > it1                                    # mode 2 had to re-solve: the repair path ran
