@@ -248,6 +248,28 @@ def test_active_set_restatement_reaches_the_full_optimum(cands):
         assert rounds > 0                                        # the check-and-repair path really ran
 
 
+def test_active_set_restatement_wide_universes():
+    """The same restatement at the shape of the WIDE reduced-solve kernel (universes of 129..512 assets, up to 256 active
+    assets: backtest_active_kernel<H, 1, FIX, 2, 8>): portfolios that still hold 60-220 of 300 / 500 assets, H = 5 and 10,
+    against the full structured solve and the certificate."""
+    from oracle import mpc_certificate as mc
+    rng = np.random.default_rng(311)
+    for p, (N, H) in enumerate([(300, 5), (300, 5), (500, 10), (200, 10)]):
+        k = int(rng.integers(60, min(220, N - 20)))
+        w0 = np.zeros(N); w0[rng.choice(N, k, replace=False)] = rng.dirichlet(np.ones(k))
+        drift = rng.standard_normal(N) * 0.002
+        y = (3e-4 + drift + rng.standard_normal((H, N)) * 1e-3).astype(np.float32)
+        lam, tau = (1e-3, 0.2) if p % 2 == 0 else (1e-4, 0.5)
+        full = mo.solve_structured(w0, y, lam, tau, apply="sweep")
+        act = mo.solve_active_set(w0, y, lam, tau, max_active=256)
+        assert full.status == mo.STATUS_OPTIMAL and act is not None and act.status == mo.STATUS_OPTIMAL
+        assert len(act.members) <= 256 and len(act.members) < N
+        assert abs(act.value - full.value) < 1e-8 * max(abs(full.value), 1e-3), (p, act.value, full.value)
+        c = mc.certify(act.w, w0, mo.gross_returns_f32(y), lam, tau)
+        assert -1e-9 < c["gap"] < 1e-6 * max(abs(c["value"]), 1e-3), (p, c)
+        assert np.all(act.w[:, np.setdiff1d(np.arange(N), act.members)] == 0.0)
+
+
 def test_second_attempt_solves_the_stalling_decisions(golden):
     """The 52 decisions of a config-2 step (1.0 M decisions, collected on the GPU with scripts/find_failures.py) that the
     aggressive first attempt leaves `optimal_inaccurate`: near-degenerate optima, the dual residual stalls at 1e-7..1e-5
